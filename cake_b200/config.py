@@ -1,0 +1,177 @@
+"""Model configuration for the block-forward path.
+
+Mirrors the reference's generalized ``Config`` (cake-core/src/models/common/config.rs:87-150) for the
+fields the dense Llama-family block path reads, and the two HF ``config.json`` mappings that are in
+scope: ``LlamaConfig::into_config`` (models/llama3/config.rs:62-98) and ``Qwen3Config::into_config``
+(models/qwen3/config.rs:55-93).  Field names follow the reference.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+from dataclasses import dataclass, field, asdict
+from typing import Optional
+
+DTYPES = {"bf16": 0, "f16": 1, "f32": 2}
+
+
+@dataclass
+class RopeScaling:
+    """config.rs RopeScaling (llama3 type only; cache.rs:49-80)."""
+    factor: float = 1.0
+    low_freq_factor: float = 1.0
+    high_freq_factor: float = 4.0
+    original_max_position_embeddings: int = 0
+    rope_type: Optional[str] = None
+
+
+@dataclass
+class Config:
+    hidden_size: int
+    intermediate_size: int
+    vocab_size: int
+    num_hidden_layers: int
+    num_attention_heads: int
+    num_key_value_heads: int
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 10000.0
+    rope_scaling: Optional[RopeScaling] = None
+    tie_word_embeddings: bool = False
+    max_seq_len: int = 4096
+    use_qkv_bias: bool = False
+    model_prefix: str = "model"
+    head_dim: Optional[int] = None
+    partial_rotary_factor: float = 1.0
+    use_qk_norm: bool = False
+    eos_token_id: list = field(default_factory=list)
+
+    @property
+    def hd(self) -> int:
+        # attention.rs:85
+        return self.head_dim if self.head_dim else self.hidden_size // self.num_attention_heads
+
+    @property
+    def size_q(self) -> int:
+        return self.hd * self.num_attention_heads
+
+    @property
+    def size_kv(self) -> int:
+        return self.hd * self.num_key_value_heads
+
+    def layer_name(self, i: int) -> str:
+        # text_model.rs:205  "{prefix}.layers.{i}"
+        return f"{self.model_prefix}.layers.{i}"
+
+    # ---- HF config.json mappings -------------------------------------------------------------
+    @staticmethod
+    def from_hf(d: dict) -> "Config":
+        arch = (d.get("architectures") or [""])[0]  # config.rs detect_text_model_arch
+        rs = d.get("rope_scaling")
+        rope = None
+        if rs:
+            rope = RopeScaling(
+                factor=float(rs.get("factor", 1.0)),
+                low_freq_factor=float(rs.get("low_freq_factor", 1.0)),
+                high_freq_factor=float(rs.get("high_freq_factor", 4.0)),
+                original_max_position_embeddings=int(rs.get("original_max_position_embeddings", 0)),
+                rope_type=rs.get("rope_type"),
+            )
+        eos = d.get("eos_token_id")
+        eos = [] if eos is None else (list(eos) if isinstance(eos, (list, tuple)) else [eos])
+        common = dict(
+            hidden_size=d["hidden_size"],
+            intermediate_size=d["intermediate_size"],
+            vocab_size=d["vocab_size"],
+            num_hidden_layers=d["num_hidden_layers"],
+            num_attention_heads=d["num_attention_heads"],
+            num_key_value_heads=d.get("num_key_value_heads") or d["num_attention_heads"],
+            rms_norm_eps=d["rms_norm_eps"],
+            rope_theta=float(d.get("rope_theta", 10000.0)),
+            rope_scaling=rope,
+            tie_word_embeddings=bool(d.get("tie_word_embeddings", False)),
+            max_seq_len=int(d.get("max_position_embeddings", 4096)),
+            eos_token_id=eos,
+        )
+        if arch == "Qwen3ForCausalLM":
+            return Config(**common, head_dim=d.get("head_dim"), use_qk_norm=True)
+        if arch in ("LlamaForCausalLM", ""):
+            return Config(**common)
+        raise ValueError(f"architecture {arch!r} is outside the block-forward path built here")
+
+    @staticmethod
+    def from_path(path: str) -> "Config":
+        with open(path) as f:
+            return Config.from_hf(json.load(f))
+
+    def to_hf(self, arch: str = "LlamaForCausalLM") -> dict:
+        d = dict(
+            architectures=[arch], hidden_size=self.hidden_size, intermediate_size=self.intermediate_size,
+            vocab_size=self.vocab_size, num_hidden_layers=self.num_hidden_layers,
+            num_attention_heads=self.num_attention_heads, num_key_value_heads=self.num_key_value_heads,
+            rms_norm_eps=self.rms_norm_eps, rope_theta=self.rope_theta,
+            tie_word_embeddings=self.tie_word_embeddings, max_position_embeddings=self.max_seq_len,
+        )
+        if self.head_dim:
+            d["head_dim"] = self.head_dim
+        if self.rope_scaling:
+            d["rope_scaling"] = asdict(self.rope_scaling)
+        return d
+
+    def is_eos(self, tok: int) -> bool:
+        # config.rs:6-19 EosTokenId::is_eos
+        return tok in self.eos_token_id
+
+
+class CConfig(ctypes.Structure):
+    """``cake_b200_config`` from include/cake_b200.h (and the oracle's ora_config prefix)."""
+    _fields_ = [
+        ("hidden", ctypes.c_int), ("inter", ctypes.c_int), ("n_heads", ctypes.c_int),
+        ("n_kv_heads", ctypes.c_int), ("head_dim", ctypes.c_int), ("n_layers", ctypes.c_int),
+        ("vocab", ctypes.c_int), ("max_seq", ctypes.c_int),
+        ("rms_eps", ctypes.c_float), ("rope_theta", ctypes.c_float), ("partial_rotary", ctypes.c_float),
+        ("qkv_bias", ctypes.c_int), ("qk_norm", ctypes.c_int), ("tie_embeddings", ctypes.c_int),
+        ("rope_llama3", ctypes.c_int),
+        ("rope_factor", ctypes.c_float), ("rope_low", ctypes.c_float), ("rope_high", ctypes.c_float),
+        ("rope_orig_max", ctypes.c_int),
+        ("dtype", ctypes.c_int),
+    ]
+
+    @staticmethod
+    def from_config(c: Config, dtype: str = "bf16", max_seq: Optional[int] = None) -> "CConfig":
+        rs = c.rope_scaling
+        llama3 = bool(rs and rs.rope_type == "llama3" and rs.original_max_position_embeddings > 0)
+        return CConfig(
+            c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.hd,
+            c.num_hidden_layers, c.vocab_size, max_seq or c.max_seq_len,
+            c.rms_norm_eps, c.rope_theta, c.partial_rotary_factor,
+            int(c.use_qkv_bias), int(c.use_qk_norm), int(c.tie_word_embeddings),
+            int(llama3),
+            rs.factor if llama3 else 1.0, rs.low_freq_factor if llama3 else 1.0,
+            rs.high_freq_factor if llama3 else 4.0, rs.original_max_position_embeddings if llama3 else 0,
+            DTYPES[dtype],
+        )
+
+
+# Named shapes used by tests / bench.
+def llama3_8b(max_seq: int = 8192) -> Config:
+    return Config(4096, 14336, 128256, 32, 32, 8, rms_norm_eps=1e-5, rope_theta=500000.0, max_seq_len=max_seq,
+                  eos_token_id=[128001, 128009])
+
+
+def llama3_70b(max_seq: int = 8192) -> Config:
+    return Config(8192, 28672, 128256, 80, 64, 8, rms_norm_eps=1e-5, rope_theta=500000.0, max_seq_len=max_seq,
+                  eos_token_id=[128001, 128009])
+
+
+def qwen3_0_6b(max_seq: int = 4096) -> Config:
+    return Config(1024, 3072, 151936, 28, 16, 8, rms_norm_eps=1e-6, rope_theta=1000000.0, max_seq_len=max_seq,
+                  head_dim=128, use_qk_norm=True, tie_word_embeddings=True, eos_token_id=[151645])
+
+
+def reference_test_config(**kw) -> Config:
+    """tests/unit_tests/helpers.rs:8-44 ``test_config()``."""
+    base = dict(hidden_size=64, intermediate_size=128, vocab_size=256, num_hidden_layers=4,
+                num_attention_heads=4, num_key_value_heads=2, rms_norm_eps=1e-6, rope_theta=10000.0,
+                max_seq_len=64)
+    base.update(kw)
+    return Config(**base)

@@ -1,0 +1,83 @@
+"""Synthetic HF-layout checkpoints (there are no real weights offline).
+
+Tensor names and shapes are the ones the reference loads:
+  transformer.rs:89-90   {layer}.input_layernorm.weight / post_attention_layernorm.weight  (H)
+  attention.rs:96-129    {layer}.self_attn.{q,k,v,o}_proj.weight [out,in] (+ .bias, q_norm/k_norm.weight)
+  mlp.rs:43-49           {layer}.mlp.{gate,up,down}_proj.weight
+  text_model.rs:159-193  {prefix}.embed_tokens.weight, {prefix}.norm.weight, lm_head.weight
+"""
+from __future__ import annotations
+
+import torch
+
+from .config import Config
+
+TORCH_DTYPES = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}
+
+
+def layer_tensor_shapes(cfg: Config) -> dict:
+    H, I = cfg.hidden_size, cfg.intermediate_size
+    s = {
+        "input_layernorm.weight": (H,),
+        "post_attention_layernorm.weight": (H,),
+        "self_attn.q_proj.weight": (cfg.size_q, H),
+        "self_attn.k_proj.weight": (cfg.size_kv, H),
+        "self_attn.v_proj.weight": (cfg.size_kv, H),
+        "self_attn.o_proj.weight": (H, cfg.size_q),
+        "mlp.gate_proj.weight": (I, H),
+        "mlp.up_proj.weight": (I, H),
+        "mlp.down_proj.weight": (H, I),
+    }
+    if cfg.use_qkv_bias:
+        s["self_attn.q_proj.bias"] = (cfg.size_q,)
+        s["self_attn.k_proj.bias"] = (cfg.size_kv,)
+        s["self_attn.v_proj.bias"] = (cfg.size_kv,)
+    if cfg.use_qk_norm:
+        s["self_attn.q_norm.weight"] = (cfg.hd,)
+        s["self_attn.k_norm.weight"] = (cfg.hd,)
+    return s
+
+
+def _fill(shape, name: str, gen: torch.Generator, device, dtype, std: float):
+    t = torch.randn(shape, generator=gen, device=device, dtype=torch.float32) * std
+    if name.endswith("norm.weight") or name.endswith("layernorm.weight"):
+        t = t + 1.0
+    return t.to(dtype)
+
+
+def make_layer(cfg: Config, i: int, dtype: str = "bf16", seed: int = 1234, device="cpu", std: float = 0.02) -> dict:
+    """Weights of one block, keyed by full HF name.  Deterministic per (seed, layer, device type)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed * 1000003 + i)
+    out = {}
+    for short, shape in layer_tensor_shapes(cfg).items():
+        out[f"{cfg.layer_name(i)}.{short}"] = _fill(shape, short, gen, device, TORCH_DTYPES[dtype], std)
+    return out
+
+
+def make_head(cfg: Config, dtype: str = "bf16", seed: int = 1234, device="cpu", std: float = 0.02,
+              peaked: bool = False) -> dict:
+    """embed / final norm / lm_head.  ``peaked``: lm_head rows are scaled copies of the embedding rows,
+    which gives large top-1/top-2 logit margins (used for greedy token-id parity)."""
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed * 1000003 + 999983)
+    td = TORCH_DTYPES[dtype]
+    p = cfg.model_prefix
+    out = {
+        f"{p}.embed_tokens.weight": _fill((cfg.vocab_size, cfg.hidden_size), "embed", gen, device, td, std),
+        f"{p}.norm.weight": _fill((cfg.hidden_size,), "norm.weight", gen, device, td, std),
+    }
+    if not cfg.tie_word_embeddings:
+        if peaked:
+            out["lm_head.weight"] = (out[f"{p}.embed_tokens.weight"].float() * 4.0).to(td)
+        else:
+            out["lm_head.weight"] = _fill((cfg.vocab_size, cfg.hidden_size), "lm_head", gen, device, td, std)
+    return out
+
+
+def make_checkpoint(cfg: Config, dtype: str = "bf16", seed: int = 1234, device="cpu", std: float = 0.02,
+                    peaked: bool = False) -> dict:
+    sd = make_head(cfg, dtype, seed, device, std, peaked)
+    for i in range(cfg.num_hidden_layers):
+        sd.update(make_layer(cfg, i, dtype, seed, device, std))
+    return sd

@@ -1,0 +1,65 @@
+"""Generates tests/golden/hf_*.npz — run in the authoring container (needs `transformers`).
+
+Each fixture holds a seeded synthetic checkpoint's *seed* (weights are regenerated from
+cake_b200.synth, not stored), the input ids, and the fp32 logits of HuggingFace transformers
+(LlamaForCausalLM / Qwen3ForCausalLM — an independent implementation of the architectures the
+reference's llama3/ and qwen3/ wrappers load) for every position.  tests/test_oracle_golden.py
+checks the oracle (f32 mode) against them; the GPU parity tests then compare against the oracle.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from cake_b200.config import RopeScaling, reference_test_config  # noqa: E402
+from cake_b200.synth import make_checkpoint  # noqa: E402
+
+CASES = {
+    "llama_tiny": ("LlamaForCausalLM", dict()),
+    "llama3_rope_scaled": ("LlamaForCausalLM", dict(rope_theta=500000.0,
+                           rope_scaling=RopeScaling(8.0, 1.0, 4.0, 16, "llama3"))),
+    "qwen3_tiny": ("Qwen3ForCausalLM", dict(head_dim=32, use_qk_norm=True, tie_word_embeddings=True)),
+}
+SEED, STD, N_IDS = 3, 0.1, 12
+
+
+def case_config(name):
+    arch, kw = CASES[name]
+    return arch, reference_test_config(**kw)
+
+
+def hf_logits(arch, cfg, sd, ids):
+    from transformers import LlamaConfig, LlamaForCausalLM, Qwen3Config, Qwen3ForCausalLM
+    d = cfg.to_hf(arch)
+    d.pop("architectures")
+    if arch == "LlamaForCausalLM":
+        m = LlamaForCausalLM(LlamaConfig(**d, attention_bias=False, mlp_bias=False))
+    else:
+        m = Qwen3ForCausalLM(Qwen3Config(**d))
+    sd = {k: v.float() for k, v in sd.items()}
+    if cfg.tie_word_embeddings:
+        sd["lm_head.weight"] = sd["model.embed_tokens.weight"]
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        return m.eval()(ids).logits[0].numpy()
+
+
+def main():
+    out = os.path.dirname(os.path.abspath(__file__))
+    for name in CASES:
+        arch, cfg = case_config(name)
+        sd = make_checkpoint(cfg, "f32", seed=SEED, std=STD)
+        ids = torch.randint(0, cfg.vocab_size, (1, N_IDS), generator=torch.Generator().manual_seed(11))
+        lg = hf_logits(arch, cfg, sd, ids)
+        np.savez_compressed(os.path.join(out, f"hf_{name}.npz"), ids=ids[0].numpy().astype(np.uint32),
+                            logits=lg.astype(np.float32), seed=SEED, std=STD)
+        print(name, lg.shape)
+
+
+if __name__ == "__main__":
+    main()
