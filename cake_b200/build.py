@@ -1,0 +1,58 @@
+"""Builds libcake_b200.so in-tree with nvcc for sm_100a (the only target; no fallbacks).
+
+    python -m cake_b200.build            # or: from cake_b200.build import build; build()
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SO = os.path.join(HERE, "libcake_b200.so")
+SRC = os.path.join(HERE, "csrc", "cake_b200.cu")
+
+
+def _nccl_include() -> str:
+    try:
+        import nvidia.nccl  # type: ignore
+        return os.path.join(os.path.dirname(nvidia.nccl.__file__), "include")
+    except Exception:
+        for p in sys.path:
+            cand = os.path.join(p, "nvidia", "nccl", "include")
+            if os.path.exists(os.path.join(cand, "nccl.h")):
+                return cand
+    return "/usr/include"
+
+
+def sources():
+    d = os.path.join(HERE, "csrc")
+    return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cu", ".cuh"))] + \
+           [os.path.join(ROOT, "include", "cake_b200.h")]
+
+
+def stale() -> bool:
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    return any(os.path.getmtime(s) > t for s in sources())
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not stale():
+        return SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+           "-I", _nccl_include(), "-I", os.path.join(ROOT, "include"),
+           "-o", SO, SRC, "-ldl"]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

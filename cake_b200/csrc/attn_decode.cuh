@@ -1,0 +1,242 @@
+// attn_decode.cuh — one decoded token of grouped-query attention with the KV-cache append fused in.
+//
+// Replaces, per layer and token, the reference's: narrow q/k/v (attention.rs:166-174), QK-norm
+// (:202-215), RoPE on q and k (:242-253, backends/mod.rs:444-482), Tensor::cat KV append — a full
+// re-copy of the layer's cache every token (cache.rs:195-196) — to_dtype(F32) + repeat_kv + matmul +
+// softmax + matmul (attention.rs:300-346).  Here the cache is pre-allocated (n_kv, max_seq, hd) in D and
+// the new K/V row is written in place (algorithmic 2*n_kv*hd*es bytes instead of 2*L*n_kv*hd*es*2).
+//
+// Flash-decoding layout: grid = (NSPLIT, n_kv); a CTA scans a contiguous slice of the sequence for ONE
+// kv head and all G = n_h/n_kv query heads that share it, so every K/V byte is read from HBM once
+// (not G times as with repeat_kv).  16-byte coalesced loads, HD/8 lanes per cached row, fp32
+// scores/softmax/PV exactly as the reference's f32 branch, warp-shuffle reductions.  The split
+// partials (m, l, acc) are merged by the last CTA to finish (atomic ticket), in split order, so the
+// result is deterministic.
+#pragma once
+#include "common.cuh"
+
+namespace cake {
+
+constexpr int ATTN_THREADS = 128;
+constexpr int ATTN_TILE = 256;  // positions per pass
+constexpr int ATTN_MAX_G = 8;
+
+struct AttnDecodeArgs {
+  const void *qkv;      // [(n_h + 2 n_kv) * hd] D: fused projection output of this token
+  void *kcache;         // [n_kv, cap, hd] D (this layer)
+  void *vcache;
+  const void *cos_t;    // [max_seq, rot/2] D
+  const void *sin_t;
+  const void *q_norm;   // [hd] D or nullptr
+  const void *k_norm;
+  void *y;              // [n_h * hd] D
+  float *ws_ml;         // [n_h, nsplit, 2]
+  float *ws_acc;        // [n_h, nsplit, hd]
+  unsigned *counters;   // [n_kv]
+  const int *d_pos;     // device-resident position of this token (== cache length before append)
+  int n_heads, n_kv, cap, rot, nsplit;
+  float eps, scale;
+};
+
+// RMSNorm (optional, attention.rs:202-215) + rotate-half RoPE (backends/mod.rs:444-482) of one head
+// vector by one warp, staged in shared memory as f32 (values stay D-representable).
+template <typename T, int HD>
+__device__ __forceinline__ void norm_rope_head(const T *src, float *dst_smem, const T *norm_w, float eps,
+                                               const T *cosr, const T *sinr, int rot, int lane) {
+  // stage through shared memory: simple and HD-generic
+  for (int d = lane; d < HD; d += 32) dst_smem[d] = DT<T>::to_f(src[d]);
+  __syncwarp();
+  if (norm_w) {
+    float ss = 0.f;
+    for (int d = lane; d < HD; d += 32) ss += dst_smem[d] * dst_smem[d];
+    ss = warp_sum(ss);
+    const float inv = 1.0f / sqrtf(ss / (float)HD + eps);
+    for (int d = lane; d < HD; d += 32) dst_smem[d] = rnd<T>(dst_smem[d] * inv * DT<T>::to_f(norm_w[d]));
+    __syncwarp();
+  }
+  const int half = rot / 2;
+  for (int i = lane; i < half; i += 32) {
+    const float c = DT<T>::to_f(cosr[i]), s = DT<T>::to_f(sinr[i]);
+    const float x1 = dst_smem[i], x2 = dst_smem[i + half];
+    // per-op rounding in D (half-crate / __nv_bfloat16 operator semantics)
+    dst_smem[i] = rnd<T>(rnd<T>(x1 * c) - rnd<T>(x2 * s));
+    dst_smem[i + half] = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
+  }
+  __syncwarp();
+}
+
+template <typename T, int HD>
+__global__ void __launch_bounds__(ATTN_THREADS) attn_decode_kernel(const AttnDecodeArgs a) {
+  constexpr int LPR = HD / 8;          // lanes per cached row (16 B each)
+  constexpr int RPW = 32 / LPR;        // rows per warp per iteration
+  constexpr int NW = ATTN_THREADS / 32;
+  const int G = a.n_heads / a.n_kv;
+  __shared__ float q_s[ATTN_MAX_G][HD];
+  __shared__ float kv_new[2][HD];
+  __shared__ float sc[ATTN_MAX_G][ATTN_TILE];
+  __shared__ float red[NW * RPW][HD + 4];
+  __shared__ float m_run[ATTN_MAX_G], l_run[ATTN_MAX_G], fac[ATTN_MAX_G];
+  __shared__ int is_last;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x, kvh = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  const int pos = *a.d_pos;
+  const int Tn = pos + 1;  // KV length after the append
+  int per = (Tn + a.nsplit - 1) / a.nsplit;
+  per = (per + 7) & ~7;
+  const int s0 = min(Tn, split * per), s1 = min(Tn, s0 + per);
+  const bool owner = (pos >= s0 && pos < s1);
+
+  const T *qkv = reinterpret_cast<const T *>(a.qkv);
+  const T *cosr = reinterpret_cast<const T *>(a.cos_t) + (size_t)pos * (a.rot / 2);
+  const T *sinr = reinterpret_cast<const T *>(a.sin_t) + (size_t)pos * (a.rot / 2);
+  T *kc = reinterpret_cast<T *>(a.kcache) + (size_t)kvh * a.cap * HD;
+  T *vc = reinterpret_cast<T *>(a.vcache) + (size_t)kvh * a.cap * HD;
+
+  // ---- q (all CTAs) and the new k,v row (owner CTA) -----------------------------------------------
+  for (int g = warp; g < G; g += NW)
+    norm_rope_head<T, HD>(qkv + (size_t)(kvh * G + g) * HD, q_s[g], reinterpret_cast<const T *>(a.q_norm), a.eps, cosr,
+                          sinr, a.rot, lane);
+  if (owner) {
+    if (warp == NW - 1) {
+      norm_rope_head<T, HD>(qkv + (size_t)(a.n_heads + kvh) * HD, kv_new[0], reinterpret_cast<const T *>(a.k_norm),
+                            a.eps, cosr, sinr, a.rot, lane);
+      for (int d = lane; d < HD; d += 32) kc[(size_t)pos * HD + d] = DT<T>::from_f(kv_new[0][d]);
+    } else if (warp == NW - 2) {
+      const T *vsrc = qkv + (size_t)(a.n_heads + a.n_kv + kvh) * HD;
+      for (int d = lane; d < HD; d += 32) vc[(size_t)pos * HD + d] = vsrc[d];
+    }
+  }
+  if (threadIdx.x < ATTN_MAX_G) { m_run[threadIdx.x] = -INFINITY; l_run[threadIdx.x] = 0.f; }
+  __syncthreads();  // q_s ready; the owner's cache row is visible to this CTA's later loads
+
+  const int grp = lane / LPR, gl = lane % LPR;  // row group within the warp / lane within the row
+  float acc[ATTN_MAX_G][8];
+#pragma unroll
+  for (int g = 0; g < ATTN_MAX_G; g++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc[g][i] = 0.f;
+
+  for (int t0 = s0; t0 < s1; t0 += ATTN_TILE) {
+    const int tn = min(ATTN_TILE, s1 - t0);
+    // ---- scores: s[g][p] = (q_g . k_p) * scale, f32 ---------------------------------------------
+    for (int pb = warp * RPW; pb < tn; pb += NW * RPW) {  // warp-uniform trip count (shuffles below)
+      const int p = pb + grp;
+      const bool valid = p < tn;
+      float kf[8];
+      uint4 kraw = make_uint4(0u, 0u, 0u, 0u);
+      if (valid) kraw = *reinterpret_cast<const uint4 *>(kc + (size_t)(t0 + p) * HD + gl * 8);
+      unpack8<T>(kraw, kf);
+#pragma unroll
+      for (int g = 0; g < ATTN_MAX_G; g++) {
+        if (g < G) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; i++) s = fmaf(q_s[g][gl * 8 + i], kf[i], s);
+#pragma unroll
+          for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (gl == 0 && valid) sc[g][p] = s * a.scale;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- online softmax bookkeeping, one warp per head -------------------------------------------
+    for (int g = warp; g < G; g += NW) {
+      float mx = -INFINITY;
+      for (int p = lane; p < tn; p += 32) mx = fmaxf(mx, sc[g][p]);
+      mx = warp_max(mx);
+      const float m_new = fmaxf(m_run[g], mx);
+      float sum = 0.f;
+      for (int p = lane; p < tn; p += 32) {
+        const float e = expf(sc[g][p] - m_new);
+        sc[g][p] = e;
+        sum += e;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        const float f = (m_run[g] == -INFINITY) ? 0.f : expf(m_run[g] - m_new);
+        fac[g] = f;
+        l_run[g] = l_run[g] * f + sum;
+        m_run[g] = m_new;
+      }
+    }
+    __syncthreads();
+    // ---- PV: acc[g][:] = acc*fac + sum_p e[g][p] * v_p --------------------------------------------
+#pragma unroll
+    for (int g = 0; g < ATTN_MAX_G; g++)
+      if (g < G) {
+        const float f = fac[g];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[g][i] *= f;
+      }
+    for (int p = warp * RPW + grp; p < tn; p += NW * RPW) {
+      float vf[8];
+      unpack8<T>(*reinterpret_cast<const uint4 *>(vc + (size_t)(t0 + p) * HD + gl * 8), vf);
+#pragma unroll
+      for (int g = 0; g < ATTN_MAX_G; g++)
+        if (g < G) {
+          const float e = sc[g][p];
+#pragma unroll
+          for (int i = 0; i < 8; i++) acc[g][i] = fmaf(e, vf[i], acc[g][i]);
+        }
+    }
+    __syncthreads();
+  }
+
+  // ---- reduce the NW*RPW row groups, write this split's partial ------------------------------------
+#pragma unroll
+  for (int g = 0; g < ATTN_MAX_G; g++) {
+    if (g >= G) break;  // G is CTA-uniform
+#pragma unroll
+    for (int i = 0; i < 8; i++) red[warp * RPW + grp][gl * 8 + i] = acc[g][i];
+    __syncthreads();
+    for (int d = threadIdx.x; d < HD; d += ATTN_THREADS) {
+      float s = 0.f;
+#pragma unroll
+      for (int r = 0; r < NW * RPW; r++) s += red[r][d];
+      a.ws_acc[((size_t)(kvh * G + g) * a.nsplit + split) * HD + d] = s;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < G) {
+    a.ws_ml[((size_t)(kvh * G + threadIdx.x) * a.nsplit + split) * 2 + 0] = m_run[threadIdx.x];
+    a.ws_ml[((size_t)(kvh * G + threadIdx.x) * a.nsplit + split) * 2 + 1] = l_run[threadIdx.x];
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned ticket = atomicAdd(&a.counters[kvh], 1u);
+    is_last = (ticket == (unsigned)a.nsplit - 1);
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // ---- last CTA of this kv head: merge splits in order, round once to D (attention.rs:346) ----------
+  T *y = reinterpret_cast<T *>(a.y);
+  for (int g = 0; g < G; g++) {
+    const int h = kvh * G + g;
+    const volatile float *ml = a.ws_ml + (size_t)h * a.nsplit * 2;
+    float M = -INFINITY;
+    for (int s = 0; s < a.nsplit; s++) M = fmaxf(M, ml[s * 2]);
+    float L = 0.f;
+    for (int s = 0; s < a.nsplit; s++) {
+      const float m = ml[s * 2];
+      if (m != -INFINITY) L += expf(m - M) * ml[s * 2 + 1];
+    }
+    const float invL = 1.0f / L;
+    for (int d = threadIdx.x; d < HD; d += ATTN_THREADS) {
+      float o = 0.f;
+      for (int s = 0; s < a.nsplit; s++) {
+        const float m = ml[s * 2];
+        if (m != -INFINITY) o += expf(m - M) * ((const volatile float *)a.ws_acc)[((size_t)h * a.nsplit + s) * HD + d];
+      }
+      y[(size_t)h * HD + d] = DT<T>::from_f(o * invL);
+    }
+  }
+  if (threadIdx.x == 0) a.counters[kvh] = 0;  // re-arm for the next launch / graph replay
+}
+
+}  // namespace cake

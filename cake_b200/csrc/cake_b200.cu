@@ -1,0 +1,972 @@
+// cake_b200.cu — C ABI of libcake_b200.so (see include/cake_b200.h for the contract and the
+// reference interfaces each entry replaces).  Host-side logic only: handles, buffers, kernel plans,
+// the CUDA graph of the decode step and the NCCL p2p hand-off.  All math is in the .cuh kernels.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/cake_b200.h"
+#include "attn_decode.cuh"
+#include "common.cuh"
+#include "gemv.cuh"
+#include "prefill.cuh"
+
+using namespace cake;
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CU(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) return fail(CAKE_B200_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+  } while (0)
+#define RC(call)              \
+  do {                        \
+    int rc_ = (call);         \
+    if (rc_ != CAKE_B200_OK) return rc_; \
+  } while (0)
+
+extern "C" const char *cake_b200_last_error(void) { return g_err; }
+extern "C" const char *cake_b200_version(void) { return "cake_b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------ NCCL (dlopen, like the reference's rocm/ffi.rs function table)
+struct NcclApi {
+  void *lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+  if (g_nccl.lib) return CAKE_B200_OK;
+  const char *names[] = {getenv("CAKE_B200_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void *h = nullptr;
+  for (const char *n : names) {
+    if (!n) continue;
+    h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return fail(CAKE_B200_ENCCL, "cannot dlopen libnccl.so.2 (set CAKE_B200_NCCL_LIB): %s", dlerror());
+#define SYM(field, name)                                                        \
+  *(void **)(&g_nccl.field) = dlsym(h, name);                                   \
+  if (!g_nccl.field) return fail(CAKE_B200_ENCCL, "libnccl lacks symbol %s", name);
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+  g_nccl.lib = h;
+  return CAKE_B200_OK;
+}
+#define NC(call)                                                                                           \
+  do {                                                                                                     \
+    ncclResult_t r_ = (call);                                                                              \
+    if (r_ != ncclSuccess) return fail(CAKE_B200_ENCCL, "%s:%d %s -> %s", __FILE__, __LINE__, #call, g_nccl.GetErrorString(r_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ handles
+struct cake_b200_ctx {
+  int device = 0;
+  cake_b200_config cfg{};
+  int es = 2, sm_count = 148, rot = 0, nqkv = 0;
+  cudaStream_t stream = nullptr;
+  void *cos_t = nullptr, *sin_t = nullptr;
+  // head
+  void *embed = nullptr, *ln_f = nullptr, *lm_head = nullptr;
+  // decode workspaces
+  void *xa = nullptr, *xb = nullptr, *qkv = nullptr, *y = nullptr, *mm = nullptr, *logits = nullptr;
+  float *ws_ml = nullptr, *ws_acc = nullptr, *part_val = nullptr;
+  int *part_idx = nullptr, *d_step = nullptr;
+  unsigned *attn_counters = nullptr, *argmax_counter = nullptr;
+  uint32_t *d_token = nullptr, *token_ring = nullptr, *d_ids = nullptr, *d_pen = nullptr;
+  size_t d_ids_cap = 0, d_pen_cap = 0;
+  uint32_t *h_pin = nullptr;  // pinned staging (tokens)
+  void *h_pin_x = nullptr;
+  size_t h_pin_x_cap = 0;
+  int nsplit = 1;
+  // prefill workspaces
+  size_t pf_rows = 0;
+  void *pf_h = nullptr, *pf_qkv = nullptr, *pf_y = nullptr, *pf_x1 = nullptr, *pf_gu = nullptr, *pf_mm = nullptr;
+  void *io_x = nullptr;
+  size_t io_x_cap = 0;
+  // comm
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  // decode graph
+  cudaGraphExec_t gexec = nullptr;
+  cudaGraph_t graph = nullptr;
+  cake_b200_cache *g_cache = nullptr;
+  std::vector<int> g_block_idx;
+  uint64_t g_kernels = 0;
+  int g_rank = 0, g_world = 1;
+  long steps_done = 0;
+  uint64_t launches = 0;
+  bool capturing = false;
+};
+constexpr int TOKEN_RING = 1 << 16;
+
+struct cake_b200_block {
+  cake_b200_ctx *ctx;
+  int layer;
+  void *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wd = nullptr, *ln1 = nullptr, *ln2 = nullptr;
+  void *bqkv = nullptr, *qn = nullptr, *kn = nullptr;
+};
+
+struct cake_b200_cache {
+  cake_b200_ctx *ctx;
+  int batch, cap;
+  std::vector<void *> k, v;
+  std::vector<int> len;
+  int *d_pos = nullptr;
+};
+
+template <typename U> struct TypeTag { typedef U type; };
+template <typename F> static inline int dispatch_T(int dtype, F &&f) {
+  if (dtype == CAKE_B200_BF16) return f(TypeTag<__nv_bfloat16>{});
+  return f(TypeTag<__half>{});
+}
+// usage: DISPATCH_T(dtype, [&](auto tag_) -> int { typedef typename decltype(tag_)::type T; ... })
+#define DISPATCH_T(dtype, ...) dispatch_T((dtype), __VA_ARGS__)
+#define T_LAMBDA [&](auto tag_) -> int
+
+// ------------------------------------------------------------------------------------------ launch helper (PDL)
+template <typename... KArgs, typename... Args>
+static int launch_pdl(cake_b200_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  CU(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+  if (c->capturing) c->g_kernels++;
+  else c->launches++;
+  return CAKE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ GEMV plan + launch
+struct GemvPlan {
+  int R, ksplit, n_stages, max_rows, grid;
+  size_t smem;
+};
+static int plan_gemv(const cake_b200_ctx *c, int N, int K, int G, GemvPlan *p) {
+  const int es = c->es;
+  if (K % 64 != 0 || N % G != 0) return fail(CAKE_B200_EINVAL, "gemv: K=%d must be a multiple of 64, N=%d of %d", K, N, G);
+  int ksplit = 1;
+  while ((size_t)(K / ksplit) * es > 16384 && (K / (ksplit * 2)) % 64 == 0) ksplit *= 2;
+  const size_t seg = (size_t)(K / ksplit) * es;
+  int R = 1;
+  while (R < 8 && (size_t)(R * 2) * seg <= 16384) R *= 2;
+  if (ksplit > 1) R = 1;
+  const int units = N / G;
+  const int grid = units < c->sm_count ? units : c->sm_count;
+  const int max_rows = (units / grid + 1) * G;
+  const size_t stage = (size_t)R * seg;
+  const size_t budget = 110 * 1024;
+  int ns = GEMV_MAX_STAGES;
+  while (ns > 2 && gemv_smem_bytes(K, R, ksplit, ns, max_rows, es) > budget) ns--;
+  const size_t smem = gemv_smem_bytes(K, R, ksplit, ns, max_rows, es);
+  if (smem > 227 * 1024) return fail(CAKE_B200_EINVAL, "gemv: N=%d K=%d needs %zu B of shared memory", N, K, smem);
+  (void)stage;
+  *p = GemvPlan{R, ksplit, ns, max_rows, grid, smem};
+  return CAKE_B200_OK;
+}
+
+template <typename T, int EPI> static int launch_gemv_T(cake_b200_ctx *c, GemvArgs a, const GemvPlan &p) {
+  a.R = p.R;
+  a.ksplit = p.ksplit;
+  a.n_stages = p.n_stages;
+  a.max_rows = p.max_rows;
+  dim3 grid(p.grid), block(GEMV_THREADS);
+  switch (p.R) {
+    case 1: return launch_pdl(c, gemv_kernel<T, EPI, 1>, grid, block, p.smem, a);
+    case 2: return launch_pdl(c, gemv_kernel<T, EPI, 2>, grid, block, p.smem, a);
+    case 4: return launch_pdl(c, gemv_kernel<T, EPI, 4>, grid, block, p.smem, a);
+    default: return launch_pdl(c, gemv_kernel<T, EPI, 8>, grid, block, p.smem, a);
+  }
+}
+template <int EPI> static int launch_gemv(cake_b200_ctx *c, GemvArgs a) {
+  GemvPlan p;
+  RC(plan_gemv(c, a.N, a.K, EPI == EPI_SWIGLU ? 2 : 1, &p));
+  return DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+      typedef typename decltype(tag_)::type T; return launch_gemv_T<T, EPI>(c, a, p); });
+}
+
+template <typename T> static int set_smem_attrs_T() {
+  const int maxs = 227 * 1024;
+#define SETA(EPI)                                                                                                   \
+  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));              \
+  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));              \
+  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));              \
+  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+  SETA(EPI_PLAIN) SETA(EPI_RESIDUAL) SETA(EPI_SWIGLU) SETA(EPI_ARGMAX)
+#undef SETA
+  return CAKE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ context
+static void rope_tables_host(const cake_b200_config &c, std::vector<float> &cs, std::vector<float> &sn, int rot) {
+  // cache.rs:43-96 (same arithmetic the reference performs on the host; computed once per ctx)
+  const int half = rot / 2;
+  std::vector<float> theta(half > 0 ? half : 1);
+  for (int j = 0; j < half; j++) theta[j] = 1.0f / powf(c.rope_theta, (float)(2 * j) / (float)rot);
+  if (c.rope_llama3 && c.rope_orig_max > 0) {
+    const float old = (float)c.rope_orig_max;
+    const float low_wl = old / c.rope_low, high_wl = old / c.rope_high;
+    for (int j = 0; j < half; j++) {
+      const float wl = 2.0f * 3.14159265358979323846f / theta[j];
+      if (wl < high_wl) {
+      } else if (wl > low_wl) {
+        theta[j] /= c.rope_factor;
+      } else {
+        const float smooth = (old / wl - c.rope_low) / (c.rope_high - c.rope_low);
+        theta[j] = (1.0f - smooth) * (theta[j] / c.rope_factor) + smooth * theta[j];
+      }
+    }
+  }
+  cs.resize((size_t)c.max_seq * half);
+  sn.resize((size_t)c.max_seq * half);
+  for (int p = 0; p < c.max_seq; p++)
+    for (int j = 0; j < half; j++) {
+      const float ang = (float)p * theta[j];
+      cs[(size_t)p * half + j] = cosf(ang);
+      sn[(size_t)p * half + j] = sinf(ang);
+    }
+}
+static void f32_to_D(const std::vector<float> &src, std::vector<uint16_t> &dst, int dtype) {
+  dst.resize(src.size());
+  for (size_t i = 0; i < src.size(); i++) {
+    if (dtype == CAKE_B200_BF16) {
+      bf16 v = __float2bfloat16_rn(src[i]);
+      memcpy(&dst[i], &v, 2);
+    } else {
+      __half v = __float2half_rn(src[i]);
+      memcpy(&dst[i], &v, 2);
+    }
+  }
+}
+
+extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cake_b200_ctx **out) {
+  if (!cfg || !out) return fail(CAKE_B200_EINVAL, "null argument");
+  if (cfg->dtype != CAKE_B200_BF16 && cfg->dtype != CAKE_B200_F16)
+    return fail(CAKE_B200_EINVAL, "dtype %d unsupported (bf16=0, f16=1)", cfg->dtype);
+  if (cfg->n_heads % cfg->n_kv_heads != 0 || cfg->n_heads / cfg->n_kv_heads > ATTN_MAX_G)
+    return fail(CAKE_B200_EINVAL, "n_heads/n_kv_heads must be an integer <= %d", ATTN_MAX_G);
+  if (cfg->head_dim != 16 && cfg->head_dim != 32 && cfg->head_dim != 64 && cfg->head_dim != 128 && cfg->head_dim != 256)
+    return fail(CAKE_B200_EINVAL, "head_dim %d unsupported (16/32/64/128/256)", cfg->head_dim);
+  if (cfg->hidden % 64 || cfg->inter % 64 || (cfg->n_heads * cfg->head_dim) % 64)
+    return fail(CAKE_B200_EINVAL, "hidden, intermediate and n_heads*head_dim must be multiples of 64");
+  int ndev = 0;
+  CU(cudaGetDeviceCount(&ndev));
+  if (ndev == 0) return fail(CAKE_B200_ECUDA, "no CUDA device: libcake_b200 has no CPU fallback");
+  CU(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(CAKE_B200_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  auto *c = new cake_b200_ctx();
+  c->device = device;
+  c->cfg = *cfg;
+  c->es = 2;
+  c->sm_count = prop.multiProcessorCount;
+  c->rot = (int)((float)cfg->head_dim * cfg->partial_rotary);
+  c->nqkv = (cfg->n_heads + 2 * cfg->n_kv_heads) * cfg->head_dim;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  RC(set_smem_attrs_T<__nv_bfloat16>());
+  RC(set_smem_attrs_T<__half>());
+  // RoPE tables -> D
+  std::vector<float> cs, sn;
+  rope_tables_host(*cfg, cs, sn, c->rot);
+  std::vector<uint16_t> cd, sd;
+  f32_to_D(cs, cd, cfg->dtype);
+  f32_to_D(sn, sd, cfg->dtype);
+  const size_t tb = cd.size() * 2 + 16;
+  CU(cudaMalloc(&c->cos_t, tb));
+  CU(cudaMalloc(&c->sin_t, tb));
+  CU(cudaMemcpy(c->cos_t, cd.data(), cd.size() * 2, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->sin_t, sd.data(), sd.size() * 2, cudaMemcpyHostToDevice));
+  // decode workspaces
+  const int H = cfg->hidden, I = cfg->inter, nh = cfg->n_heads, hd = cfg->head_dim;
+  c->nsplit = c->sm_count / cfg->n_kv_heads;
+  if (c->nsplit < 1) c->nsplit = 1;
+  if (c->nsplit > 32) c->nsplit = 32;
+  CU(cudaMalloc(&c->xa, (size_t)H * 2));
+  CU(cudaMalloc(&c->xb, (size_t)H * 2));
+  CU(cudaMalloc(&c->qkv, (size_t)c->nqkv * 2));
+  CU(cudaMalloc(&c->y, (size_t)nh * hd * 2));
+  CU(cudaMalloc(&c->mm, (size_t)I * 2));
+  CU(cudaMalloc(&c->logits, (size_t)cfg->vocab * 2));
+  CU(cudaMalloc(&c->ws_ml, (size_t)nh * c->nsplit * 2 * 4));
+  CU(cudaMalloc(&c->ws_acc, (size_t)nh * c->nsplit * hd * 4));
+  CU(cudaMalloc(&c->attn_counters, (size_t)cfg->n_kv_heads * 4));
+  CU(cudaMemset(c->attn_counters, 0, (size_t)cfg->n_kv_heads * 4));
+  CU(cudaMalloc(&c->part_val, 1024 * 4));
+  CU(cudaMalloc(&c->part_idx, 1024 * 4));
+  CU(cudaMalloc(&c->argmax_counter, 4));
+  CU(cudaMemset(c->argmax_counter, 0, 4));
+  CU(cudaMalloc(&c->d_token, 4));
+  CU(cudaMalloc(&c->d_step, 4));
+  CU(cudaMemset(c->d_step, 0, 4));
+  CU(cudaMalloc(&c->token_ring, (size_t)TOKEN_RING * 4));
+  CU(cudaMallocHost(&c->h_pin, 64 * 4));
+  *out = c;
+  return CAKE_B200_OK;
+}
+
+extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  if (c->gexec) cudaGraphExecDestroy(c->gexec);
+  if (c->graph) cudaGraphDestroy(c->graph);
+  if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  void *bufs[] = {c->cos_t, c->sin_t, c->embed, c->ln_f, c->xa, c->xb, c->qkv, c->y, c->mm, c->logits, c->ws_ml,
+                  c->ws_acc, c->part_val, c->part_idx, c->d_step, c->attn_counters, c->argmax_counter, c->d_token,
+                  c->token_ring, c->d_ids, c->d_pen, c->pf_h, c->pf_qkv, c->pf_y, c->pf_x1, c->pf_gu, c->pf_mm, c->io_x};
+  for (void *b : bufs)
+    if (b) cudaFree(b);
+  if (c->lm_head && c->lm_head != c->embed) cudaFree(c->lm_head);
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->h_pin_x) cudaFreeHost(c->h_pin_x);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+extern "C" int cake_b200_sync(cake_b200_ctx *c) {
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return CAKE_B200_OK;
+}
+extern "C" void *cake_b200_stream(cake_b200_ctx *c) { return (void *)c->stream; }
+extern "C" int cake_b200_launch_count(cake_b200_ctx *c, uint64_t *k) {
+  *k = c->launches;
+  return CAKE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ blocks
+static int upload(void **dst, const void *src, size_t bytes) {
+  CU(cudaMalloc(dst, bytes + 16));
+  CU(cudaMemcpy(*dst, src, bytes, cudaMemcpyDefault));
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void *q, const void *k, const void *v,
+                                    const void *o, const void *gate, const void *up, const void *down, const void *ln1,
+                                    const void *ln2, const void *q_bias, const void *k_bias, const void *v_bias,
+                                    const void *q_norm, const void *k_norm, cake_b200_block **out) {
+  if (!c || !q || !k || !v || !o || !gate || !up || !down || !ln1 || !ln2 || !out) return fail(CAKE_B200_EINVAL, "null weight pointer");
+  if (c->cfg.qkv_bias && (!q_bias || !k_bias || !v_bias)) return fail(CAKE_B200_EINVAL, "config has qkv_bias but a bias pointer is null");
+  if (c->cfg.qk_norm && (!q_norm || !k_norm)) return fail(CAKE_B200_EINVAL, "config has qk_norm but a norm pointer is null");
+  CU(cudaSetDevice(c->device));
+  const size_t es = c->es, H = c->cfg.hidden, I = c->cfg.inter, hd = c->cfg.head_dim;
+  const size_t sq = (size_t)c->cfg.n_heads * hd, skv = (size_t)c->cfg.n_kv_heads * hd;
+  auto *b = new cake_b200_block{c, layer_idx};
+  // attention.rs:109-113: Wqkv = cat([q,k,v], 0)
+  CU(cudaMalloc(&b->wqkv, (sq + 2 * skv) * H * es + 16));
+  CU(cudaMemcpy(b->wqkv, q, sq * H * es, cudaMemcpyDefault));
+  CU(cudaMemcpy((char *)b->wqkv + sq * H * es, k, skv * H * es, cudaMemcpyDefault));
+  CU(cudaMemcpy((char *)b->wqkv + (sq + skv) * H * es, v, skv * H * es, cudaMemcpyDefault));
+  RC(upload(&b->wo, o, H * sq * es));
+  // mlp.rs:43-45 fuses gate|up by cat; here the fused matrix is ROW-INTERLEAVED (row 2i = gate_i,
+  // row 2i+1 = up_i) so that silu(gate_i)*up_i is local to one warp's epilogue.  Numerically identical.
+  CU(cudaMalloc(&b->wgu, 2 * I * H * es + 16));
+  CU(cudaMemcpy2D(b->wgu, 2 * H * es, gate, H * es, H * es, I, cudaMemcpyDefault));
+  CU(cudaMemcpy2D((char *)b->wgu + H * es, 2 * H * es, up, H * es, H * es, I, cudaMemcpyDefault));
+  RC(upload(&b->wd, down, H * I * es));
+  RC(upload(&b->ln1, ln1, H * es));
+  RC(upload(&b->ln2, ln2, H * es));
+  if (c->cfg.qkv_bias) {
+    CU(cudaMalloc(&b->bqkv, (sq + 2 * skv) * es + 16));
+    CU(cudaMemcpy(b->bqkv, q_bias, sq * es, cudaMemcpyDefault));
+    CU(cudaMemcpy((char *)b->bqkv + sq * es, k_bias, skv * es, cudaMemcpyDefault));
+    CU(cudaMemcpy((char *)b->bqkv + (sq + skv) * es, v_bias, skv * es, cudaMemcpyDefault));
+  }
+  if (c->cfg.qk_norm) {
+    RC(upload(&b->qn, q_norm, hd * es));
+    RC(upload(&b->kn, k_norm, hd * es));
+  }
+  *out = b;
+  return CAKE_B200_OK;
+}
+extern "C" void cake_b200_block_free(cake_b200_block *b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  void *bufs[] = {b->wqkv, b->wo, b->wgu, b->wd, b->ln1, b->ln2, b->bqkv, b->qn, b->kn};
+  for (void *p : bufs)
+    if (p) cudaFree(p);
+  delete b;
+}
+extern "C" int cake_b200_block_layer(const cake_b200_block *b) { return b->layer; }
+
+// ------------------------------------------------------------------------------------------ cache
+extern "C" int cake_b200_cache_create(cake_b200_ctx *c, int batch, int max_seq, cake_b200_cache **out) {
+  if (!c || !out || batch < 1 || max_seq < 1) return fail(CAKE_B200_EINVAL, "bad cache arguments");
+  if (max_seq > c->cfg.max_seq) return fail(CAKE_B200_EINVAL, "cache max_seq %d exceeds config max_seq %d (RoPE table rows)", max_seq, c->cfg.max_seq);
+  CU(cudaSetDevice(c->device));
+  auto *k = new cake_b200_cache{c, batch, max_seq};
+  k->k.assign(c->cfg.n_layers, nullptr);
+  k->v.assign(c->cfg.n_layers, nullptr);
+  k->len.assign(c->cfg.n_layers, 0);
+  CU(cudaMalloc(&k->d_pos, 4));
+  CU(cudaMemset(k->d_pos, 0, 4));
+  *out = k;
+  return CAKE_B200_OK;
+}
+static int cache_ensure(cake_b200_cache *k, int layer) {
+  if (layer < 0 || layer >= (int)k->k.size()) return fail(CAKE_B200_EINVAL, "block_idx %d out of range", layer);
+  if (k->k[layer]) return CAKE_B200_OK;
+  const size_t bytes = (size_t)k->batch * k->ctx->cfg.n_kv_heads * k->cap * k->ctx->cfg.head_dim * k->ctx->es;
+  CU(cudaMalloc(&k->k[layer], bytes + 16));
+  CU(cudaMalloc(&k->v[layer], bytes + 16));
+  return CAKE_B200_OK;
+}
+extern "C" int cake_b200_cache_clear(cake_b200_cache *k) {
+  for (auto &l : k->len) l = 0;
+  return CAKE_B200_OK;
+}
+extern "C" void cake_b200_cache_free(cake_b200_cache *k) {
+  if (!k) return;
+  cudaSetDevice(k->ctx->device);
+  cudaStreamSynchronize(k->ctx->stream);
+  for (void *p : k->k)
+    if (p) cudaFree(p);
+  for (void *p : k->v)
+    if (p) cudaFree(p);
+  cudaFree(k->d_pos);
+  delete k;
+}
+extern "C" int cake_b200_cache_len(const cake_b200_cache *k, int block_idx) {
+  if (block_idx < 0 || block_idx >= (int)k->len.size()) return -1;
+  return k->len[block_idx];
+}
+extern "C" int cake_b200_cache_read(cake_b200_cache *k, int block_idx, int which, void *out_host, size_t bytes) {
+  cake_b200_ctx *c = k->ctx;
+  CU(cudaSetDevice(c->device));
+  if (block_idx < 0 || block_idx >= (int)k->len.size() || !k->k[block_idx]) return fail(CAKE_B200_EINVAL, "layer %d has no cache", block_idx);
+  const int len = k->len[block_idx], hd = c->cfg.head_dim, nkv = c->cfg.n_kv_heads;
+  const size_t need = (size_t)k->batch * nkv * len * hd * c->es;
+  if (bytes < need) return fail(CAKE_B200_EINVAL, "cache_read needs %zu bytes", need);
+  CU(cudaStreamSynchronize(c->stream));
+  const char *src = (const char *)(which ? k->v[block_idx] : k->k[block_idx]);
+  CU(cudaMemcpy2D(out_host, (size_t)len * hd * c->es, src, (size_t)k->cap * hd * c->es, (size_t)len * hd * c->es,
+                  (size_t)k->batch * nkv, cudaMemcpyDeviceToHost));
+  return CAKE_B200_OK;
+}
+extern "C" int cake_b200_cache_fill_synthetic(cake_b200_cache *k, const int *block_idx, int n_blocks, int len,
+                                              uint32_t seed) {
+  cake_b200_ctx *c = k->ctx;
+  CU(cudaSetDevice(c->device));
+  if (len > k->cap) return fail(CAKE_B200_EINVAL, "len %d > cache capacity %d", len, k->cap);
+  for (int i = 0; i < n_blocks; i++) {
+    const int l = block_idx[i];
+    RC(cache_ensure(k, l));
+    const size_t n = (size_t)k->batch * c->cfg.n_kv_heads * k->cap * c->cfg.head_dim;
+    RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+      typedef typename decltype(tag_)::type T;
+      fill_synth_kernel<T><<<1024, 256, 0, c->stream>>>((T *)k->k[l], n, seed + 2 * l, 1.0f);
+      fill_synth_kernel<T><<<1024, 256, 0, c->stream>>>((T *)k->v[l], n, seed + 2 * l + 1, 1.0f);
+      return CAKE_B200_OK;
+    }));
+    k->len[l] = len;
+  }
+  CU(cudaGetLastError());
+  return CAKE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ decode path (batch 1, seq 1)
+// x_in -> x_out through `n` blocks; position comes from cache->d_pos (device).  5 kernels per layer.
+static int enqueue_qkv(cake_b200_ctx *c, const cake_b200_block *b, const void *x) {
+  // rms_1 + fused qkv projection (+bias)                           transformer.rs:112, attention.rs:162-164
+  GemvArgs a{};
+  a.W = b->wqkv; a.x = x; a.norm_w = b->ln1; a.bias = b->bqkv; a.out = c->qkv; a.eps = c->cfg.rms_eps;
+  a.N = c->nqkv; a.K = c->cfg.hidden;
+  return launch_gemv<EPI_PLAIN>(c, a);
+}
+static int enqueue_attn(cake_b200_ctx *c, const cake_b200_block *b, cake_b200_cache *kc, int l) {
+  // qk-norm, RoPE, KV append, GQA attention                        attention.rs:202-346, cache.rs:184-210
+  const cake_b200_config &f = c->cfg;
+  AttnDecodeArgs a{};
+  a.qkv = c->qkv; a.kcache = kc->k[l]; a.vcache = kc->v[l]; a.cos_t = c->cos_t; a.sin_t = c->sin_t;
+  a.q_norm = b->qn; a.k_norm = b->kn; a.y = c->y; a.ws_ml = c->ws_ml; a.ws_acc = c->ws_acc;
+  a.counters = c->attn_counters; a.d_pos = kc->d_pos; a.n_heads = f.n_heads; a.n_kv = f.n_kv_heads;
+  a.cap = kc->cap; a.rot = c->rot; a.nsplit = c->nsplit; a.eps = f.rms_eps;
+  a.scale = (float)(1.0 / sqrt((double)f.head_dim));
+  dim3 grid(c->nsplit, f.n_kv_heads), block(ATTN_THREADS);
+  return DISPATCH_T(f.dtype, T_LAMBDA {
+    typedef typename decltype(tag_)::type T;
+    switch (f.head_dim) {
+      case 16: return launch_pdl(c, attn_decode_kernel<T, 16>, grid, block, 0, a);
+      case 32: return launch_pdl(c, attn_decode_kernel<T, 32>, grid, block, 0, a);
+      case 64: return launch_pdl(c, attn_decode_kernel<T, 64>, grid, block, 0, a);
+      case 128: return launch_pdl(c, attn_decode_kernel<T, 128>, grid, block, 0, a);
+      default: return launch_pdl(c, attn_decode_kernel<T, 256>, grid, block, 0, a);
+    }
+  });
+}
+static int enqueue_oproj(cake_b200_ctx *c, const cake_b200_block *b, const void *residual, void *out) {
+  // o_proj + residual                                              attention.rs:354, transformer.rs:123
+  GemvArgs a{};
+  a.W = b->wo; a.x = c->y; a.residual = residual; a.out = out; a.N = c->cfg.hidden;
+  a.K = c->cfg.n_heads * c->cfg.head_dim;
+  return launch_gemv<EPI_RESIDUAL>(c, a);
+}
+static int enqueue_gate_up(cake_b200_ctx *c, const cake_b200_block *b, const void *x1) {
+  // rms_2 + gate_up + silu*mul                                     transformer.rs:129, mlp.rs:22-28
+  GemvArgs a{};
+  a.W = b->wgu; a.x = x1; a.norm_w = b->ln2; a.out = c->mm; a.eps = c->cfg.rms_eps; a.N = 2 * c->cfg.inter;
+  a.K = c->cfg.hidden;
+  return launch_gemv<EPI_SWIGLU>(c, a);
+}
+static int enqueue_down(cake_b200_ctx *c, const cake_b200_block *b, const void *residual, void *out) {
+  // down + residual                                                mlp.rs:30, transformer.rs:131
+  GemvArgs a{};
+  a.W = b->wd; a.x = c->mm; a.residual = residual; a.out = out; a.N = c->cfg.hidden; a.K = c->cfg.inter;
+  return launch_gemv<EPI_RESIDUAL>(c, a);
+}
+
+static int enqueue_decode_layers(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *block_idx, int n,
+                                 cake_b200_cache *kc, const void *x_in, void *x_out) {
+  const void *cur = x_in;
+  for (int i = 0; i < n; i++) {
+    const cake_b200_block *b = blocks[i];
+    void *dst = (i == n - 1) ? x_out : c->xa;
+    RC(enqueue_qkv(c, b, cur));
+    RC(enqueue_attn(c, b, kc, block_idx[i]));
+    RC(enqueue_oproj(c, b, cur, c->xb));
+    RC(enqueue_gate_up(c, b, c->xb));
+    RC(enqueue_down(c, b, c->xb, dst));
+    cur = dst;
+  }
+  return CAKE_B200_OK;
+}
+
+// ln_f + lm_head + greedy argmax on one hidden row -> logits_out (nullable), token -> c->d_token
+static int enqueue_head(cake_b200_ctx *c, const void *x_row, void *logits_out, bool ring) {
+  GemvArgs a{};
+  a.W = c->lm_head; a.x = x_row; a.norm_w = c->ln_f; a.out = logits_out; a.eps = c->cfg.rms_eps;
+  a.N = c->cfg.vocab; a.K = c->cfg.hidden;
+  a.part_val = c->part_val; a.part_idx = c->part_idx; a.counter = c->argmax_counter; a.token_out = c->d_token;
+  a.token_ring = ring ? c->token_ring : nullptr; a.step = c->d_step; a.ring_cap = TOKEN_RING;
+  return launch_gemv<EPI_ARGMAX>(c, a);
+}
+
+// ------------------------------------------------------------------------------------------ prefill path (any batch / seq)
+static int pf_reserve(cake_b200_ctx *c, size_t rows) {
+  if (rows <= c->pf_rows) return CAKE_B200_OK;
+  CU(cudaStreamSynchronize(c->stream));
+  void **bufs[] = {&c->pf_h, &c->pf_qkv, &c->pf_y, &c->pf_x1, &c->pf_gu, &c->pf_mm};
+  for (void **b : bufs)
+    if (*b) { cudaFree(*b); *b = nullptr; }
+  const cake_b200_config &f = c->cfg;
+  const size_t es = c->es;
+  CU(cudaMalloc(&c->pf_h, rows * f.hidden * es));
+  CU(cudaMalloc(&c->pf_qkv, rows * c->nqkv * es));
+  CU(cudaMalloc(&c->pf_y, rows * f.n_heads * f.head_dim * es));
+  CU(cudaMalloc(&c->pf_x1, rows * f.hidden * es));
+  CU(cudaMalloc(&c->pf_gu, rows * 2 * f.inter * es));
+  CU(cudaMalloc(&c->pf_mm, rows * f.inter * es));
+  c->pf_rows = rows;
+  return CAKE_B200_OK;
+}
+
+template <typename T>
+static int gemm_T(cake_b200_ctx *c, const void *A, const void *W, const void *bias, const void *res, void *C, int M,
+                  int N, int K) {
+  dim3 grid((N + GV0_BN - 1) / GV0_BN, (M + GV0_BM - 1) / GV0_BM), block(256);
+  return launch_pdl(c, gemm_v0_kernel<T>, grid, block, 0, (const T *)A, (const T *)W, (const T *)bias, (const T *)res,
+                    (T *)C, M, N, K);
+}
+
+static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *block_idx, int n,
+                                  cake_b200_cache *kc, const void *x_in, void *x_out, int B, int S, int pos0) {
+  const cake_b200_config &f = c->cfg;
+  const int H = f.hidden, I = f.inter, hd = f.head_dim, sq = f.n_heads * hd, M = B * S;
+  RC(pf_reserve(c, (size_t)M));
+  return DISPATCH_T(f.dtype, T_LAMBDA {
+      typedef typename decltype(tag_)::type T;
+    const void *cur = x_in;
+    for (int i = 0; i < n; i++) {
+      const cake_b200_block *b = blocks[i];
+      const int l = block_idx[i];
+      RC(launch_pdl(c, rmsnorm_rows_kernel<T>, dim3(M), dim3(256), 0, (const T *)cur, (const T *)b->ln1, (T *)c->pf_h, H, f.rms_eps));
+      RC(gemm_T<T>(c, c->pf_h, b->wqkv, b->bqkv, nullptr, c->pf_qkv, M, c->nqkv, H));
+      {
+        const long items = (long)M * (f.n_heads + 2 * f.n_kv_heads);
+        RC(launch_pdl(c, rope_append_kernel<T>, dim3((unsigned)((items + 3) / 4)), dim3(128), (size_t)4 * hd * 4,
+                      (T *)c->pf_qkv, (T *)kc->k[l], (T *)kc->v[l], (const T *)c->cos_t, (const T *)c->sin_t,
+                      (const T *)b->qn, (const T *)b->kn, B, S, f.n_heads, f.n_kv_heads, hd, c->rot, kc->cap, pos0, f.rms_eps));
+      }
+      {
+        const long items = (long)M * f.n_heads;
+        RC(launch_pdl(c, attn_prefill_v0_kernel<T>, dim3((unsigned)((items + 3) / 4)), dim3(128), 0, (const T *)c->pf_qkv,
+                      (const T *)kc->k[l], (const T *)kc->v[l], (T *)c->pf_y, B, S, f.n_heads, f.n_kv_heads, hd, kc->cap,
+                      pos0, (float)(1.0 / sqrt((double)hd))));
+      }
+      RC(gemm_T<T>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq));
+      RC(launch_pdl(c, rmsnorm_rows_kernel<T>, dim3(M), dim3(256), 0, (const T *)c->pf_x1, (const T *)b->ln2, (T *)c->pf_h, H, f.rms_eps));
+      RC(gemm_T<T>(c, c->pf_h, b->wgu, nullptr, nullptr, c->pf_gu, M, 2 * I, H));
+      RC(launch_pdl(c, swiglu_rows_kernel<T>, dim3(c->sm_count * 4), dim3(256), 0, (const T *)c->pf_gu, (T *)c->pf_mm, (size_t)M * I));
+      RC(gemm_T<T>(c, c->pf_mm, b->wd, nullptr, c->pf_x1, x_out, M, H, I));
+      cur = x_out;
+    }
+    return CAKE_B200_OK;
+  });
+}
+
+// ------------------------------------------------------------------------------------------ forward_batch
+extern "C" int cake_b200_forward_batch(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *block_idx,
+                                       int n_blocks, cake_b200_cache *kc, const void *x_dev, void *y_dev, int batch,
+                                       int seq, int index_pos) {
+  if (!c || !blocks || !block_idx || !kc || !x_dev || !y_dev || n_blocks < 1) return fail(CAKE_B200_EINVAL, "null/empty argument");
+  if (batch != kc->batch) return fail(CAKE_B200_EINVAL, "batch %d != cache batch %d", batch, kc->batch);
+  if (seq < 1 || index_pos < 0 || index_pos + seq > kc->cap)
+    return fail(CAKE_B200_ESTATE, "index_pos %d + seq %d exceeds cache capacity %d", index_pos, seq, kc->cap);
+  CU(cudaSetDevice(c->device));
+  for (int i = 0; i < n_blocks; i++) {
+    RC(cache_ensure(kc, block_idx[i]));
+    if (kc->len[block_idx[i]] != index_pos)
+      return fail(CAKE_B200_ESTATE, "block %d: index_pos %d != cache length %d (clear the cache or feed positions in order)",
+                  block_idx[i], index_pos, kc->len[block_idx[i]]);
+  }
+  if (batch == 1 && seq == 1) {
+    set_int_kernel<<<1, 1, 0, c->stream>>>(kc->d_pos, index_pos);
+    c->launches++;
+    RC(enqueue_decode_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev));
+  } else {
+    RC(enqueue_prefill_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev, batch, seq, index_pos));
+  }
+  for (int i = 0; i < n_blocks; i++) kc->len[block_idx[i]] = index_pos + seq;
+  CU(cudaGetLastError());
+  return CAKE_B200_OK;
+}
+
+static int io_reserve(cake_b200_ctx *c, size_t bytes) {
+  if (bytes > c->io_x_cap) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->io_x) cudaFree(c->io_x);
+    CU(cudaMalloc(&c->io_x, bytes));
+    c->io_x_cap = bytes;
+  }
+  if (bytes > c->h_pin_x_cap) {
+    if (c->h_pin_x) cudaFreeHost(c->h_pin_x);
+    CU(cudaMallocHost(&c->h_pin_x, bytes));
+    c->h_pin_x_cap = bytes;
+  }
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_forward_batch_host(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *block_idx,
+                                            int n_blocks, cake_b200_cache *kc, const void *x_host, void *y_host,
+                                            int batch, int seq, int index_pos) {
+  if (!c || !x_host || !y_host) return fail(CAKE_B200_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)batch * seq * c->cfg.hidden * c->es;
+  RC(io_reserve(c, bytes));
+  memcpy(c->h_pin_x, x_host, bytes);
+  CU(cudaMemcpyAsync(c->io_x, c->h_pin_x, bytes, cudaMemcpyHostToDevice, c->stream));
+  RC(cake_b200_forward_batch(c, blocks, block_idx, n_blocks, kc, c->io_x, c->io_x, batch, seq, index_pos));
+  CU(cudaMemcpyAsync(c->h_pin_x, c->io_x, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  memcpy(y_host, c->h_pin_x, bytes);
+  return CAKE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ head / tail
+extern "C" int cake_b200_head_load(cake_b200_ctx *c, const void *embed, const void *ln_f, const void *lm_head) {
+  if (!c || !embed || !ln_f) return fail(CAKE_B200_EINVAL, "null argument");
+  if (!lm_head && !c->cfg.tie_embeddings) return fail(CAKE_B200_EINVAL, "lm_head is NULL but tie_embeddings is 0");
+  CU(cudaSetDevice(c->device));
+  const size_t es = c->es, H = c->cfg.hidden, V = c->cfg.vocab;
+  RC(upload(&c->embed, embed, V * H * es));
+  RC(upload(&c->ln_f, ln_f, H * es));
+  if (lm_head) RC(upload(&c->lm_head, lm_head, V * H * es));
+  else c->lm_head = c->embed;  // text_model.rs:164-167
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_embed(cake_b200_ctx *c, const uint32_t *ids_host, int batch, int seq, void *x_dev) {
+  if (!c || !ids_host || !x_dev || !c->embed) return fail(CAKE_B200_EINVAL, "null argument or head not loaded");
+  CU(cudaSetDevice(c->device));
+  const size_t n = (size_t)batch * seq;
+  if (n > c->d_ids_cap) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_ids) cudaFree(c->d_ids);
+    CU(cudaMalloc(&c->d_ids, n * 4));
+    c->d_ids_cap = n;
+  }
+  CU(cudaMemcpyAsync(c->d_ids, ids_host, n * 4, cudaMemcpyHostToDevice, c->stream));
+  // the ids buffer is pageable in general: the copy above returns after staging, safe to reuse
+  RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+      typedef typename decltype(tag_)::type T;
+    return launch_pdl(c, embed_kernel<T>, dim3((unsigned)n), dim3(128), 0, (const T *)c->embed, (const uint32_t *)c->d_ids,
+                      (T *)x_dev, (int)n, c->cfg.hidden, c->cfg.vocab);
+  }));
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_logits(cake_b200_ctx *c, const void *x_dev, int batch, int seq, void *logits_dev,
+                                uint32_t *argmax_host) {
+  if (!c || !x_dev || !c->lm_head) return fail(CAKE_B200_EINVAL, "null argument or head not loaded");
+  if (batch > 64) return fail(CAKE_B200_EINVAL, "batch > 64");
+  CU(cudaSetDevice(c->device));
+  const size_t H = c->cfg.hidden, V = c->cfg.vocab, es = c->es;
+  for (int b = 0; b < batch; b++) {
+    const char *row = (const char *)x_dev + ((size_t)b * seq + (seq - 1)) * H * es;  // text_model.rs:342-346
+    void *lo = logits_dev ? (char *)logits_dev + (size_t)b * V * es : c->logits;
+    RC(enqueue_head(c, row, lo, false));
+    if (argmax_host) CU(cudaMemcpyAsync(c->h_pin + b, c->d_token, 4, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (argmax_host) {
+    CU(cudaStreamSynchronize(c->stream));
+    for (int b = 0; b < batch; b++) argmax_host[b] = c->h_pin[b];
+  }
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_repeat_penalty_argmax(cake_b200_ctx *c, void *logits_dev, float penalty,
+                                               const uint32_t *ctx_tokens_host, int n_tokens, uint32_t *argmax_host) {
+  if (!c || !logits_dev || !argmax_host) return fail(CAKE_B200_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  // text_model.rs:66-72: de-duplicate, keeping first occurrences
+  std::vector<uint32_t> uniq;
+  for (int i = 0; i < n_tokens; i++) {
+    bool dup = false;
+    for (uint32_t u : uniq) dup |= (u == ctx_tokens_host[i]);
+    if (!dup) uniq.push_back(ctx_tokens_host[i]);
+  }
+  if (!uniq.empty() && penalty != 1.0f) {
+    if (uniq.size() > c->d_pen_cap) {
+      CU(cudaStreamSynchronize(c->stream));
+      if (c->d_pen) cudaFree(c->d_pen);
+      CU(cudaMalloc(&c->d_pen, uniq.size() * 4));
+      c->d_pen_cap = uniq.size();
+    }
+    CU(cudaMemcpyAsync(c->d_pen, uniq.data(), uniq.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));  // uniq is a stack-owned pageable buffer
+    RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+      typedef typename decltype(tag_)::type T;
+      repeat_penalty_kernel<T><<<(unsigned)((uniq.size() + 127) / 128), 128, 0, c->stream>>>((T *)logits_dev, c->cfg.vocab, penalty, c->d_pen, (int)uniq.size());
+      return CAKE_B200_OK;
+    }));
+    c->launches++;
+  }
+  RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+      typedef typename decltype(tag_)::type T;
+    argmax_kernel<T><<<1, 1024, 0, c->stream>>>((const T *)logits_dev, c->cfg.vocab, c->d_token);
+    return CAKE_B200_OK;
+  }));
+  c->launches++;
+  CU(cudaMemcpyAsync(c->h_pin, c->d_token, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *argmax_host = c->h_pin[0];
+  return CAKE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ comm
+extern "C" int cake_b200_comm_unique_id(void *out128) {
+  RC(nccl_load());
+  ncclUniqueId id;
+  NC(g_nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out128, &id, 128);
+  return CAKE_B200_OK;
+}
+extern "C" int cake_b200_comm_init(cake_b200_ctx *c, const void *unique_id128, int rank, int world) {
+  if (!c || !unique_id128 || rank < 0 || rank >= world) return fail(CAKE_B200_EINVAL, "bad comm arguments");
+  RC(nccl_load());
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, unique_id128, 128);
+  NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
+  c->rank = rank;
+  c->world = world;
+  return CAKE_B200_OK;
+}
+extern "C" int cake_b200_send(cake_b200_ctx *c, const void *x_dev, size_t bytes, int peer) {
+  if (!c || !c->comm) return fail(CAKE_B200_ESTATE, "communicator not initialised");
+  NC(g_nccl.Send(x_dev, bytes, ncclUint8, peer, c->comm, c->stream));
+  return CAKE_B200_OK;
+}
+extern "C" int cake_b200_recv(cake_b200_ctx *c, void *x_dev, size_t bytes, int peer) {
+  if (!c || !c->comm) return fail(CAKE_B200_ESTATE, "communicator not initialised");
+  NC(g_nccl.Recv(x_dev, bytes, ncclUint8, peer, c->comm, c->stream));
+  return CAKE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ decode loop (one CUDA graph per shard)
+extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *block_idx,
+                                      int n_blocks, cake_b200_cache *kc, int rank, int world) {
+  if (!c || !kc || n_blocks < 0 || world < 1 || rank < 0 || rank >= world) return fail(CAKE_B200_EINVAL, "bad decode_build arguments");
+  if (kc->batch != 1) return fail(CAKE_B200_EINVAL, "decode graph is batch 1 (cake run/serve never batch, text_model.rs:418-420)");
+  if (world > 1 && !c->comm) return fail(CAKE_B200_ESTATE, "world > 1 needs cake_b200_comm_init first");
+  if (rank == 0 && !c->lm_head) return fail(CAKE_B200_ESTATE, "rank 0 needs cake_b200_head_load first");
+  CU(cudaSetDevice(c->device));
+  for (int i = 0; i < n_blocks; i++) RC(cache_ensure(kc, block_idx[i]));
+  if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
+  if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+  const size_t xbytes = (size_t)c->cfg.hidden * c->es;
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  c->capturing = true;
+  c->g_kernels = 0;
+  int rc = [&]() -> int {
+    if (rank == 0) {
+      RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+      typedef typename decltype(tag_)::type T;
+        return launch_pdl(c, embed_kernel<T>, dim3(1), dim3(128), 0, (const T *)c->embed, (const uint32_t *)c->d_token,
+                          (T *)c->xa, 1, c->cfg.hidden, c->cfg.vocab);
+      }));
+    } else {
+      RC(cake_b200_recv(c, c->xa, xbytes, rank - 1));
+    }
+    if (n_blocks > 0) RC(enqueue_decode_layers(c, blocks, block_idx, n_blocks, kc, c->xa, c->xa));
+    if (world > 1) {
+      RC(cake_b200_send(c, c->xa, xbytes, (rank + 1) % world));
+      if (rank == 0) RC(cake_b200_recv(c, c->xa, xbytes, world - 1));
+    }
+    if (rank == 0) RC(enqueue_head(c, c->xa, c->logits, true));
+    RC(launch_pdl(c, advance_kernel, dim3(1), dim3(32), 0, kc->d_pos, c->d_step));
+    return CAKE_B200_OK;
+  }();
+  c->capturing = false;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+  if (rc != CAKE_B200_OK) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(CAKE_B200_ECUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  c->graph = g;
+  CU(cudaGraphInstantiate(&c->gexec, g, 0));
+  c->g_cache = kc;
+  c->g_block_idx.assign(block_idx, block_idx + n_blocks);
+  c->g_rank = rank;
+  c->g_world = world;
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_decode_begin(cake_b200_ctx *c, uint32_t first_token, int index_pos) {
+  if (!c || !c->gexec) return fail(CAKE_B200_ESTATE, "decode_build has not been called");
+  CU(cudaSetDevice(c->device));
+  cake_b200_cache *kc = c->g_cache;
+  for (int l : c->g_block_idx)
+    if (kc->len[l] != index_pos)
+      return fail(CAKE_B200_ESTATE, "block %d: index_pos %d != cache length %d", l, index_pos, kc->len[l]);
+  if (index_pos >= kc->cap) return fail(CAKE_B200_ESTATE, "cache full");
+  set_int_kernel<<<1, 1, 0, c->stream>>>(kc->d_pos, index_pos);
+  set_int_kernel<<<1, 1, 0, c->stream>>>(c->d_step, 0);
+  set_u32_kernel<<<1, 1, 0, c->stream>>>(c->d_token, first_token);
+  c->launches += 3;
+  c->steps_done = 0;
+  CU(cudaGetLastError());
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_decode_run(cake_b200_ctx *c, int n_steps) {
+  if (!c || !c->gexec) return fail(CAKE_B200_ESTATE, "decode_build has not been called");
+  CU(cudaSetDevice(c->device));
+  cake_b200_cache *kc = c->g_cache;
+  int cur = c->g_block_idx.empty() ? 0 : kc->len[c->g_block_idx[0]];
+  if (!c->g_block_idx.empty() && cur + n_steps > kc->cap)
+    return fail(CAKE_B200_ESTATE, "decode_run: %d steps from position %d exceed cache capacity %d", n_steps, cur, kc->cap);
+  for (int i = 0; i < n_steps; i++) CU(cudaGraphLaunch(c->gexec, c->stream));
+  for (int l : c->g_block_idx) kc->len[l] += n_steps;
+  c->steps_done += n_steps;
+  c->launches += c->g_kernels * (uint64_t)n_steps;
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_decode_tokens(cake_b200_ctx *c, uint32_t *out_host, int n) {
+  if (!c || !out_host || n < 0 || n > TOKEN_RING || n > c->steps_done) return fail(CAKE_B200_EINVAL, "bad decode_tokens arguments");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  std::vector<uint32_t> ring(TOKEN_RING);
+  CU(cudaMemcpy(ring.data(), c->token_ring, (size_t)TOKEN_RING * 4, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) out_host[i] = ring[(size_t)(c->steps_done - n + i) % TOKEN_RING];
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_decode_step_host(cake_b200_ctx *c, uint32_t token_in, uint32_t *token_out) {
+  if (!c || !c->gexec || !token_out) return fail(CAKE_B200_ESTATE, "decode_build has not been called");
+  CU(cudaSetDevice(c->device));
+  c->h_pin[32] = token_in;
+  CU(cudaMemcpyAsync(c->d_token, c->h_pin + 32, 4, cudaMemcpyHostToDevice, c->stream));
+  RC(cake_b200_decode_run(c, 1));
+  CU(cudaMemcpyAsync(c->h_pin + 33, c->d_token, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *token_out = c->h_pin[33];
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_decode_logits(cake_b200_ctx *c, void *logits_host, size_t bytes) {
+  if (!c || !logits_host) return fail(CAKE_B200_EINVAL, "null argument");
+  const size_t need = (size_t)c->cfg.vocab * c->es;
+  if (bytes < need) return fail(CAKE_B200_EINVAL, "decode_logits needs %zu bytes", need);
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(logits_host, c->logits, need, cudaMemcpyDeviceToHost));
+  return CAKE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ measurement aid
+extern "C" int cake_b200_bench_kernel(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *block_idx,
+                                      int n_blocks, cake_b200_cache *kc, int which, int reps, float *ms_per_launch) {
+  if (!c || !blocks || !kc || !ms_per_launch || n_blocks < 1 || reps < 1 || which < 0 || which > 4)
+    return fail(CAKE_B200_EINVAL, "bad bench_kernel arguments");
+  CU(cudaSetDevice(c->device));
+  for (int i = 0; i < n_blocks; i++) RC(cache_ensure(kc, block_idx[i]));
+  const int len = kc->len[block_idx[0]];
+  if (which == 4 && len < 1) return fail(CAKE_B200_ESTATE, "attention bench needs a non-empty cache");
+  if (which == 4) {  // scores the token at position len-1 again: reads len rows, rewrites row len-1
+    set_int_kernel<<<1, 1, 0, c->stream>>>(kc->d_pos, len - 1);
+  }
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0));
+  CU(cudaEventCreate(&e1));
+  auto round = [&]() -> int {
+    for (int i = 0; i < n_blocks; i++) {
+      const cake_b200_block *b = blocks[i];
+      switch (which) {
+        case 0: RC(enqueue_qkv(c, b, c->xa)); break;
+        case 1: RC(enqueue_oproj(c, b, c->xa, c->xb)); break;
+        case 2: RC(enqueue_gate_up(c, b, c->xb)); break;
+        case 3: RC(enqueue_down(c, b, c->xb, c->xb)); break;
+        default: RC(enqueue_attn(c, b, kc, block_idx[i])); break;
+      }
+    }
+    return CAKE_B200_OK;
+  };
+  RC(round());  // warm-up
+  CU(cudaEventRecord(e0, c->stream));
+  for (int r = 0; r < reps; r++) RC(round());
+  CU(cudaEventRecord(e1, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_per_launch = ms / (float)(reps * n_blocks);
+  return CAKE_B200_OK;
+}

@@ -1,0 +1,278 @@
+// prefill.cuh — the seq>1 / batch>1 side of the block forward (prompt ingestion), plus the small
+// bookkeeping kernels.  Same rounding points as the decode path.
+//
+// The GEMM here is the generic CUDA-core tile kernel used for correctness bring-up of the prefill
+// path; the tcgen05 (UMMA + TMEM + TMA) GEMM replaces it for large M (see gemm_tc.cuh once present).
+#pragma once
+#include "common.cuh"
+
+namespace cake {
+
+// ---- RMSNorm over rows (backends/mod.rs:244-246): one CTA per row ---------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const T *__restrict__ x, const T *__restrict__ w,
+                                                           T *__restrict__ out, int n, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8];
+  const T *xr = x + (size_t)blockIdx.x * n;
+  T *orow = out + (size_t)blockIdx.x * n;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float v = DT<T>::to_f(xr[i]);
+    ss += v * v;
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); i++) tot += red[i];
+  const float inv = 1.0f / sqrtf(tot / (float)n + eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    orow[i] = DT<T>::from_f(DT<T>::to_f(xr[i]) * inv * DT<T>::to_f(w[i]));
+}
+
+// ---- C[M,N] = A[M,K] · W[N,K]^T, fp32 accumulate, ->D, then (+bias ->D) or (+residual ->D) --------
+constexpr int GV0_BM = 64, GV0_BN = 64, GV0_BK = 16;
+template <typename T>
+__global__ void __launch_bounds__(256) gemm_v0_kernel(const T *__restrict__ A, const T *__restrict__ W,
+                                                      const T *__restrict__ bias, const T *__restrict__ residual,
+                                                      T *__restrict__ C, int M, int N, int K) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float As[GV0_BK][GV0_BM + 4];
+  __shared__ float Ws[GV0_BK][GV0_BN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * GV0_BM, n0 = blockIdx.x * GV0_BN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += GV0_BK) {
+    for (int i = threadIdx.x; i < GV0_BM * GV0_BK; i += 256) {
+      const int r = i / GV0_BK, c = i % GV0_BK;
+      As[c][r] = (m0 + r < M && k0 + c < K) ? DT<T>::to_f(A[(size_t)(m0 + r) * K + k0 + c]) : 0.f;
+      Ws[c][r] = (n0 + r < N && k0 + c < K) ? DT<T>::to_f(W[(size_t)(n0 + r) * K + k0 + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < GV0_BK; k++) {
+      float av[4], wv[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { av[i] = As[k][ty * 4 + i]; wv[i] = Ws[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) {
+      const int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+      if (m < M && n < N) {
+        float v = rnd<T>(acc[i][j]);
+        if (bias) v = rnd<T>(v + DT<T>::to_f(bias[n]));
+        if (residual) v = v + DT<T>::to_f(residual[(size_t)m * N + n]);
+        C[(size_t)m * N + n] = DT<T>::from_f(v);
+      }
+    }
+}
+
+// ---- silu(gate)*up on the row-interleaved gate_up output: gu[m][2i]=gate_i, gu[m][2i+1]=up_i -------
+template <typename T>
+__global__ void swiglu_rows_kernel(const T *__restrict__ gu, T *__restrict__ out, size_t total /* M*I */) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const float g = DT<T>::to_f(gu[2 * i]), u = DT<T>::to_f(gu[2 * i + 1]);
+    const float s = rnd<T>(g / (1.0f + expf(-g)));
+    out[i] = DT<T>::from_f(s * u);
+  }
+}
+
+// ---- QK-norm + RoPE + KV append for S positions (attention.rs:202-253, cache.rs:184-210) -----------
+// qkv: [B, S, (n_h + 2 n_kv) * hd].  q is normalised/rotated in place; k,v go to the cache rows
+// [pos0 + t].  One warp per (b, t, head) with head in [0, n_h + 2 n_kv).
+template <typename T>
+__global__ void __launch_bounds__(128) rope_append_kernel(T *__restrict__ qkv, T *__restrict__ kcache,
+                                                          T *__restrict__ vcache, const T *__restrict__ cos_t,
+                                                          const T *__restrict__ sin_t, const T *__restrict__ q_norm,
+                                                          const T *__restrict__ k_norm, int B, int S, int n_heads,
+                                                          int n_kv, int hd, int rot, int cap, int pos0, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ float sm[];  // 4 warps * hd
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nh_all = n_heads + 2 * n_kv;
+  const long item = (long)blockIdx.x * 4 + warp;
+  if (item >= (long)B * S * nh_all) return;
+  const int head = (int)(item % nh_all);
+  const int t = (int)((item / nh_all) % S);
+  const int b = (int)(item / ((long)nh_all * S));
+  T *src = qkv + ((size_t)(b * S + t) * nh_all + head) * hd;
+  float *buf = sm + warp * hd;
+  const int pos = pos0 + t;
+  if (head >= n_heads + n_kv) {  // v: straight copy into the cache
+    const int kvh = head - n_heads - n_kv;
+    T *dst = vcache + (((size_t)b * n_kv + kvh) * cap + pos) * hd;
+    for (int d = lane; d < hd; d += 32) dst[d] = src[d];
+    return;
+  }
+  const bool is_k = head >= n_heads;
+  const T *nw = is_k ? k_norm : q_norm;
+  for (int d = lane; d < hd; d += 32) buf[d] = DT<T>::to_f(src[d]);
+  __syncwarp();
+  if (nw) {
+    float ss = 0.f;
+    for (int d = lane; d < hd; d += 32) ss += buf[d] * buf[d];
+    ss = warp_sum(ss);
+    const float inv = 1.0f / sqrtf(ss / (float)hd + eps);
+    for (int d = lane; d < hd; d += 32) buf[d] = rnd<T>(buf[d] * inv * DT<T>::to_f(nw[d]));
+    __syncwarp();
+  }
+  const int half = rot / 2;
+  const T *cr = cos_t + (size_t)pos * half, *sr = sin_t + (size_t)pos * half;
+  for (int i = lane; i < half; i += 32) {
+    const float c = DT<T>::to_f(cr[i]), s = DT<T>::to_f(sr[i]);
+    const float x1 = buf[i], x2 = buf[i + half];
+    buf[i] = rnd<T>(rnd<T>(x1 * c) - rnd<T>(x2 * s));
+    buf[i + half] = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
+  }
+  __syncwarp();
+  T *dst = is_k ? kcache + (((size_t)b * n_kv + (head - n_heads)) * cap + pos) * hd : src;
+  for (int d = lane; d < hd; d += 32) dst[d] = DT<T>::from_f(buf[d]);
+}
+
+// ---- causal attention for S query positions against the cache (attention.rs:300-346) ---------------
+// One warp per (b, head, t).  f32 throughout, online softmax, result ->D.  Query t (absolute position
+// pos0+t) sees cache rows [0, pos0+t]  (mask j-(T-S) > i, attention.rs:314-341).
+template <typename T>
+__global__ void __launch_bounds__(128) attn_prefill_v0_kernel(const T *__restrict__ qkv, const T *__restrict__ kcache,
+                                                              const T *__restrict__ vcache, T *__restrict__ y, int B,
+                                                              int S, int n_heads, int n_kv, int hd, int cap, int pos0,
+                                                              float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long item = (long)blockIdx.x * 4 + warp;
+  if (item >= (long)B * S * n_heads) return;
+  const int h = (int)(item % n_heads);
+  const int t = (int)((item / n_heads) % S);
+  const int b = (int)(item / ((long)n_heads * S));
+  const int nh_all = n_heads + 2 * n_kv, G = n_heads / n_kv;
+  const T *q = qkv + ((size_t)(b * S + t) * nh_all + h) * hd;
+  const T *kc = kcache + ((size_t)b * n_kv + h / G) * cap * hd;
+  const T *vc = vcache + ((size_t)b * n_kv + h / G) * cap * hd;
+  constexpr int MAXD = 8;  // hd <= 256
+  float qf[MAXD], acc[MAXD];
+  const int nd = (hd + 31) / 32;
+#pragma unroll
+  for (int i = 0; i < MAXD; i++) {
+    const int d = lane + 32 * i;
+    qf[i] = (i < nd && d < hd) ? DT<T>::to_f(q[d]) : 0.f;
+    acc[i] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  const int kv_len = pos0 + t + 1;
+  for (int p = 0; p < kv_len; p++) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXD; i++) {
+      const int d = lane + 32 * i;
+      if (i < nd && d < hd) s = fmaf(qf[i], DT<T>::to_f(kc[(size_t)p * hd + d]), s);
+    }
+    s = warp_sum(s) * scale;
+    const float mn = fmaxf(m, s);
+    const float f = (m == -INFINITY) ? 0.f : expf(m - mn);
+    const float e = expf(s - mn);
+    l = l * f + e;
+#pragma unroll
+    for (int i = 0; i < MAXD; i++) {
+      const int d = lane + 32 * i;
+      if (i < nd && d < hd) acc[i] = acc[i] * f + e * DT<T>::to_f(vc[(size_t)p * hd + d]);
+    }
+    m = mn;
+  }
+  const float inv = 1.0f / l;
+  T *yo = y + ((size_t)(b * S + t) * n_heads + h) * hd;
+#pragma unroll
+  for (int i = 0; i < MAXD; i++) {
+    const int d = lane + 32 * i;
+    if (i < nd && d < hd) yo[d] = DT<T>::from_f(acc[i] * inv);
+  }
+}
+
+// ---- embedding gather (backends/mod.rs:513-528) ---------------------------------------------------
+template <typename T>
+__global__ void embed_kernel(const T *__restrict__ E, const uint32_t *__restrict__ ids, T *__restrict__ x, int n_tok,
+                             int H, int vocab) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int t = blockIdx.x;
+  if (t >= n_tok) return;
+  uint32_t id = ids[t];
+  if (id >= (uint32_t)vocab) id = 0;
+  const uint4 *src = reinterpret_cast<const uint4 *>(E + (size_t)id * H);
+  uint4 *dst = reinterpret_cast<uint4 *>(x + (size_t)t * H);
+  for (int i = threadIdx.x; i < H * (int)sizeof(T) / 16; i += blockDim.x) dst[i] = src[i];
+}
+
+// ---- decode-loop bookkeeping ----------------------------------------------------------------------
+__global__ void set_int_kernel(int *p, int v) { *p = v; }
+__global__ void set_u32_kernel(uint32_t *p, uint32_t v) { *p = v; }
+__global__ void advance_kernel(int *pos, int *step) {
+  pdl_launch_dependents();
+  pdl_wait();
+  if (threadIdx.x == 0) { *pos += 1; *step += 1; }
+}
+
+// ---- argmax over logits already in memory (first maximum wins), single CTA ------------------------
+template <typename T>
+__global__ void __launch_bounds__(1024) argmax_kernel(const T *__restrict__ logits, int V, uint32_t *out) {
+  __shared__ float bv[32];
+  __shared__ int bi[32];
+  float best = -INFINITY;
+  int idx = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = DT<T>::to_f(logits[i]);
+    if (v > best) { best = v; idx = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ov > best || (ov == best && oi < idx)) { best = ov; idx = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { bv[threadIdx.x >> 5] = best; bi[threadIdx.x >> 5] = idx; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+      if (bv[w] > best || (bv[w] == best && bi[w] < idx)) { best = bv[w]; idx = bi[w]; }
+    *out = (uint32_t)idx;
+  }
+}
+
+// ---- repeat penalty (text_model.rs:60-99) on device, arithmetic in D; tokens are pre-deduplicated --
+template <typename T>
+__global__ void repeat_penalty_kernel(T *logits, int V, float penalty, const uint32_t *toks, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t t = toks[i];
+  if (t >= (uint32_t)V) return;
+  const float recip = rnd<T>(1.0f / penalty), pen = rnd<T>(penalty);
+  const float sel = DT<T>::to_f(logits[t]);
+  const float mult = sel >= 0.f ? recip : pen;
+  const float penalized = rnd<T>(sel * mult);
+  const float delta = rnd<T>(penalized - sel);
+  logits[t] = DT<T>::from_f(sel + delta);
+}
+
+// ---- synthetic cache fill (bench only) ------------------------------------------------------------
+template <typename T>
+__global__ void fill_synth_kernel(T *p, size_t n, uint32_t seed, float amp) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    uint32_t h = (uint32_t)i * 2654435761u ^ seed;
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    p[i] = DT<T>::from_f(((float)(h & 0xffff) / 32768.0f - 1.0f) * amp);
+  }
+}
+
+}  // namespace cake

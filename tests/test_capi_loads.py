@@ -1,0 +1,60 @@
+"""CPU-side checks of the drop-in boundary: the library loads, exports every symbol that
+include/cake_b200.h declares, and fails loudly (no CPU fallback) when there is no GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from cake_b200 import capi
+from cake_b200.build import build
+from cake_b200.config import CConfig, llama3_8b
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_loads():
+    build()
+    L = capi.lib()
+    assert L.cake_b200_version().startswith(b"cake_b200")
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "cake_b200.h")).read()
+    declared = set(re.findall(r"\b(cake_b200_[a-z0-9_]+)\s*\(", hdr))
+    bound = {n for n, _, _ in capi.SYMBOLS}
+    assert declared == bound, f"header/binding mismatch: {declared ^ bound}"
+    L = capi.lib()
+    for name in declared:
+        assert hasattr(L, name)
+
+
+def test_cconfig_matches_header_layout():
+    # 20 4-byte fields, no padding
+    assert ctypes.sizeof(CConfig) == 20 * 4
+    c = CConfig.from_config(llama3_8b(), "bf16")
+    assert (c.hidden, c.inter, c.n_heads, c.n_kv_heads, c.head_dim, c.n_layers, c.vocab) == \
+           (4096, 14336, 32, 8, 128, 32, 128256)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_no_cpu_fallback():
+    c = CConfig.from_config(llama3_8b(), "bf16")
+    h = ctypes.c_void_p()
+    rc = capi.lib().cake_b200_ctx_create(0, ctypes.byref(c), ctypes.byref(h))
+    assert rc != 0 and capi.lib().cake_b200_last_error()
+    from cake_b200.model import Context
+    with pytest.raises(RuntimeError):
+        Context(llama3_8b(), {}, "bf16")
+
+
+def test_product_never_imports_the_oracle():
+    # the oracle is the checker, never the product path: nothing under cake_b200/ may import, link or call it
+    pkg = os.path.join(ROOT, "cake_b200")
+    bad = re.compile(r"^\s*(import|from)\s+oracle\b|cake_oracle|libcake_oracle|\bora_[a-z_]+\s*\(", re.M)
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
+                src = open(os.path.join(dp, f)).read()
+                assert not bad.search(src), f"{f} reaches into the oracle"

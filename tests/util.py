@@ -1,0 +1,41 @@
+"""Shared helpers for the parity tests: build the same synthetic checkpoint for the oracle and the
+CUDA path, and compare in units of the model dtype's ulp."""
+import numpy as np
+import torch
+
+from cake_b200.config import Config
+from cake_b200.synth import TORCH_DTYPES, make_checkpoint
+
+ULP = {"bf16": 2.0 ** -7, "f16": 2.0 ** -10}  # spacing relative to the binade (1 ulp of D)
+
+
+def max_ulp_err(a: np.ndarray, ref: np.ndarray, dtype: str) -> float:
+    """max |a-ref| in ulps of D at the magnitude of ref (floored at 2^-6 so values near 0 do not explode)."""
+    a, ref = np.asarray(a, np.float32), np.asarray(ref, np.float32)
+    mag = np.maximum(np.abs(ref), 2.0 ** -6)
+    ulp = ULP[dtype] * 2.0 ** np.floor(np.log2(mag))
+    return float((np.abs(a - ref) / ulp).max())
+
+
+def to_np(t: torch.Tensor) -> np.ndarray:
+    return t.detach().float().cpu().numpy()
+
+
+def rand_x(shape, dtype: str, seed: int, scale: float = 1.0) -> torch.Tensor:
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(TORCH_DTYPES[dtype])
+
+
+def medium_config(**kw) -> Config:
+    """hidden 512, 8 heads / 2 kv heads of 64, inter 1024: big enough to exercise every kernel's
+    tiling (multi-CTA row split, K split across warps, several attention splits), small enough for the
+    oracle to run in well under a second."""
+    base = dict(hidden_size=512, intermediate_size=1024, vocab_size=1024, num_hidden_layers=3,
+                num_attention_heads=8, num_key_value_heads=2, rms_norm_eps=1e-5, rope_theta=500000.0,
+                max_seq_len=512, head_dim=64)
+    base.update(kw)
+    return Config(**base)
+
+
+def checkpoint(cfg: Config, dtype: str, seed: int = 1234, std: float = 0.05, peaked: bool = False):
+    return make_checkpoint(cfg, dtype, seed=seed, std=std, peaked=peaked)
