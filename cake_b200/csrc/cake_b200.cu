@@ -170,44 +170,36 @@ static int launch_pdl(cake_b200_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 
 
 // ------------------------------------------------------------------------------------------ GEMV plan + launch
 struct GemvPlan {
-  int R, ksplit, n_stages, max_rows, grid;
+  int KC, n_stages, max_rows, grid;
   size_t smem;
 };
 static int plan_gemv(const cake_b200_ctx *c, int N, int K, int G, GemvPlan *p) {
   const int es = c->es;
   if (K % 64 != 0 || N % G != 0) return fail(CAKE_B200_EINVAL, "gemv: K=%d must be a multiple of 64, N=%d of %d", K, N, G);
-  int ksplit = 1;
-  while ((size_t)(K / ksplit) * es > 16384 && (K / (ksplit * 2)) % 64 == 0) ksplit *= 2;
-  const size_t seg = (size_t)(K / ksplit) * es;
-  int R = 1;
-  while (R < 8 && (size_t)(R * 2) * seg <= 16384) R *= 2;
-  if (ksplit > 1) R = 1;
+  // segment = KC columns of one row (2 KB at KC=1024): largest divisor of K that is <= 1024 and % 64 == 0
+  int KC = K;
+  if (K > 1024) {
+    KC = 64;
+    for (int d = 1024; d >= 64; d -= 64)
+      if (K % d == 0) { KC = d; break; }
+  }
   const int units = N / G;
   const int grid = units < c->sm_count ? units : c->sm_count;
   const int max_rows = (units / grid + 1) * G;
-  const size_t stage = (size_t)R * seg;
-  const size_t budget = 110 * 1024;
+  const size_t budget = 108 * 1024;  // two CTAs (this kernel + its PDL successor) must fit in one SM's 227 KB
   int ns = GEMV_MAX_STAGES;
-  while (ns > 2 && gemv_smem_bytes(K, R, ksplit, ns, max_rows, es) > budget) ns--;
-  const size_t smem = gemv_smem_bytes(K, R, ksplit, ns, max_rows, es);
+  while (ns > 2 && gemv_smem_bytes(K, KC, ns, max_rows, es) > budget) ns--;
+  const size_t smem = gemv_smem_bytes(K, KC, ns, max_rows, es);
   if (smem > 227 * 1024) return fail(CAKE_B200_EINVAL, "gemv: N=%d K=%d needs %zu B of shared memory", N, K, smem);
-  (void)stage;
-  *p = GemvPlan{R, ksplit, ns, max_rows, grid, smem};
+  *p = GemvPlan{KC, ns, max_rows, grid, smem};
   return CAKE_B200_OK;
 }
 
 template <typename T, int EPI> static int launch_gemv_T(cake_b200_ctx *c, GemvArgs a, const GemvPlan &p) {
-  a.R = p.R;
-  a.ksplit = p.ksplit;
+  a.KC = p.KC;
   a.n_stages = p.n_stages;
   a.max_rows = p.max_rows;
-  dim3 grid(p.grid), block(GEMV_THREADS);
-  switch (p.R) {
-    case 1: return launch_pdl(c, gemv_kernel<T, EPI, 1>, grid, block, p.smem, a);
-    case 2: return launch_pdl(c, gemv_kernel<T, EPI, 2>, grid, block, p.smem, a);
-    case 4: return launch_pdl(c, gemv_kernel<T, EPI, 4>, grid, block, p.smem, a);
-    default: return launch_pdl(c, gemv_kernel<T, EPI, 8>, grid, block, p.smem, a);
-  }
+  return launch_pdl(c, gemv_kernel<T, EPI>, dim3(p.grid), dim3(GEMV_THREADS), p.smem, a);
 }
 template <int EPI> static int launch_gemv(cake_b200_ctx *c, GemvArgs a) {
   GemvPlan p;
@@ -218,13 +210,17 @@ template <int EPI> static int launch_gemv(cake_b200_ctx *c, GemvArgs a) {
 
 template <typename T> static int set_smem_attrs_T() {
   const int maxs = 227 * 1024;
-#define SETA(EPI)                                                                                                   \
-  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));              \
-  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));              \
-  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));              \
-  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));
+  // max-shared carveout so that a kernel and its programmatic-dependent successor co-reside on an SM
+#define SETA(EPI)                                                                                              \
+  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));            \
+  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   SETA(EPI_PLAIN) SETA(EPI_RESIDUAL) SETA(EPI_SWIGLU) SETA(EPI_ARGMAX)
 #undef SETA
+#define SETB(HD)                                                                                                  \
+  CU(cudaFuncSetAttribute(attn_decode_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));         \
+  CU(cudaFuncSetAttribute(attn_decode_kernel<T, HD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  SETB(16) SETB(32) SETB(64) SETB(128) SETB(256)
+#undef SETB
   return CAKE_B200_OK;
 }
 
@@ -312,7 +308,7 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
   const int H = cfg->hidden, I = cfg->inter, nh = cfg->n_heads, hd = cfg->head_dim;
   c->nsplit = c->sm_count / cfg->n_kv_heads;
   if (c->nsplit < 1) c->nsplit = 1;
-  if (c->nsplit > 32) c->nsplit = 32;
+  if (c->nsplit > ATTN_MAX_SPLIT) c->nsplit = ATTN_MAX_SPLIT;
   CU(cudaMalloc(&c->xa, (size_t)H * 2));
   CU(cudaMalloc(&c->xb, (size_t)H * 2));
   CU(cudaMalloc(&c->qkv, (size_t)c->nqkv * 2));
@@ -514,14 +510,15 @@ static int enqueue_attn(cake_b200_ctx *c, const cake_b200_block *b, cake_b200_ca
   a.cap = kc->cap; a.rot = c->rot; a.nsplit = c->nsplit; a.eps = f.rms_eps;
   a.scale = (float)(1.0 / sqrt((double)f.head_dim));
   dim3 grid(c->nsplit, f.n_kv_heads), block(ATTN_THREADS);
+  const size_t smem = attn_smem_bytes(f.head_dim, c->es);
   return DISPATCH_T(f.dtype, T_LAMBDA {
     typedef typename decltype(tag_)::type T;
     switch (f.head_dim) {
-      case 16: return launch_pdl(c, attn_decode_kernel<T, 16>, grid, block, 0, a);
-      case 32: return launch_pdl(c, attn_decode_kernel<T, 32>, grid, block, 0, a);
-      case 64: return launch_pdl(c, attn_decode_kernel<T, 64>, grid, block, 0, a);
-      case 128: return launch_pdl(c, attn_decode_kernel<T, 128>, grid, block, 0, a);
-      default: return launch_pdl(c, attn_decode_kernel<T, 256>, grid, block, 0, a);
+      case 16: return launch_pdl(c, attn_decode_kernel<T, 16>, grid, block, smem, a);
+      case 32: return launch_pdl(c, attn_decode_kernel<T, 32>, grid, block, smem, a);
+      case 64: return launch_pdl(c, attn_decode_kernel<T, 64>, grid, block, smem, a);
+      case 128: return launch_pdl(c, attn_decode_kernel<T, 128>, grid, block, smem, a);
+      default: return launch_pdl(c, attn_decode_kernel<T, 256>, grid, block, smem, a);
     }
   });
 }

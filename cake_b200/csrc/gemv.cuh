@@ -10,9 +10,10 @@
 //   * the producer starts streaming BEFORE griddepcontrol.wait: weights do not depend on the previous
 //     kernel, so with programmatic dependent launch the ring is already full when the activation
 //     arrives — the kernel boundary costs no HBM idle time;
-//   * 8 consumer warps split K; x (optionally RMS-normalised in-kernel, f32 sum of squares) lives in
-//     shared memory in dtype D; fp32 accumulation; partial sums are combined in a fixed order
-//     (lane tree -> warp slot -> 8 slots) so results are bit-deterministic run to run;
+//   * 8 consumer warps, each owning whole rows (its lanes split the columns); x (optionally
+//     RMS-normalised in-kernel, f32 sum of squares) lives in shared memory in dtype D; fp32
+//     accumulation in 4 independent chains per lane, one shuffle tree per row — a fixed order, so
+//     results are bit-deterministic run to run;
 //   * epilogues fuse what the reference does as separate tensor ops: +bias, +residual (transformer.rs:123,131),
 //     silu(gate)*up on row-interleaved Wgu (mlp.rs:22-28), logits + greedy argmax (text_model.rs:348-352,104-105).
 // Rounding points follow SURVEY.md Appendix A: the matmul result is rounded to D before any epilogue op.
@@ -24,8 +25,9 @@ namespace cake {
 enum { EPI_PLAIN = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_ARGMAX = 3 };
 
 constexpr int GEMV_CONSUMER_WARPS = 8;
+constexpr int GEMV_RS = GEMV_CONSUMER_WARPS;                  // rows per stage: one per consumer warp
 constexpr int GEMV_THREADS = (GEMV_CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
-constexpr int GEMV_MAX_STAGES = 12;
+constexpr int GEMV_MAX_STAGES = 16;
 
 struct GemvArgs {
   const void *W;         // [N,K] row-major, D
@@ -36,10 +38,9 @@ struct GemvArgs {
   void *out;             // [N] D  ([N/2] for EPI_SWIGLU)
   float eps;
   int N, K;
-  int R;        // rows per stage (1,2,4,8)
-  int ksplit;   // chunks per row (KC = K / ksplit)
+  int KC;        // columns per stage segment (divides K, multiple of 64 unless KC == K)
   int n_stages;
-  int max_rows; // upper bound of rows per CTA (sizes the partial-sum scratch)
+  int max_rows;  // upper bound of rows per CTA (sizes the row-sum scratch)
   // EPI_ARGMAX
   float *part_val;
   int *part_idx;
@@ -50,32 +51,35 @@ struct GemvArgs {
   int ring_cap;
 };
 
-__host__ __device__ inline size_t gemv_smem_bytes(int K, int R, int ksplit, int n_stages, int max_rows, int es) {
-  size_t stage = (size_t)R * (K / ksplit) * es;
+__host__ __device__ inline size_t gemv_smem_bytes(int K, int KC, int n_stages, int max_rows, int es) {
+  size_t stage = (size_t)GEMV_RS * KC * es;
   size_t off = (size_t)n_stages * stage;                 // ring
   off += (size_t)K * es;                                 // xs
   off = (off + 15) & ~(size_t)15;
-  off += (size_t)max_rows * GEMV_CONSUMER_WARPS * 4;     // partial sums
+  off += (size_t)max_rows * 4;                           // row sums
   off += 64 * 4;                                         // reduction scratch
   off = (off + 7) & ~(size_t)7;
   off += (size_t)2 * GEMV_MAX_STAGES * 8;                // mbarriers
   return off + 128;                                      // alignment slack
 }
 
-template <typename T, int EPI, int R>
+// A stage holds up to GEMV_RS row segments of KC columns; consumer warp w owns segment w, i.e. a warp
+// owns whole rows: its 32 lanes split the columns, accumulate in fp32 registers across the K/KC chunks
+// of the row, and do ONE 5-step shuffle reduction per row (not per stage).
+template <typename T, int EPI>
 __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int es = sizeof(T);
-  const int K = a.K, N = a.N;
-  const int KC = K / a.ksplit;
+  const int K = a.K, N = a.N, KC = a.KC;
+  const int nchunk = K / KC;
   const size_t seg_bytes = (size_t)KC * es;
-  const size_t stage_bytes = (size_t)R * seg_bytes;
+  const size_t stage_bytes = (size_t)GEMV_RS * seg_bytes;
   unsigned char *ring = smem_raw;
   T *xs = reinterpret_cast<T *>(ring + (size_t)a.n_stages * stage_bytes);
   size_t off = (size_t)a.n_stages * stage_bytes + (size_t)K * es;
   off = (off + 15) & ~(size_t)15;
-  float *partial = reinterpret_cast<float *>(smem_raw + off);
-  off += (size_t)a.max_rows * GEMV_CONSUMER_WARPS * 4;
+  float *rowsum = reinterpret_cast<float *>(smem_raw + off);
+  off += (size_t)a.max_rows * 4;
   float *scratch = reinterpret_cast<float *>(smem_raw + off);
   off += 64 * 4;
   off = (off + 7) & ~(size_t)7;
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvArgs a)
   const int r0 = (int)(units * blockIdx.x / gridDim.x) * G;
   const int r1 = (int)(units * (blockIdx.x + 1) / gridDim.x) * G;
   const int nrows = r1 - r0;
-  const int ngroups = (nrows + R - 1) / R;
+  const int ngroups = (nrows + GEMV_RS - 1) / GEMV_RS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.n_stages; s++) {
@@ -105,23 +109,23 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvArgs a)
     if (lane == 0) {
       const uint64_t pol = policy_evict_first();
       const unsigned char *Wb = reinterpret_cast<const unsigned char *>(a.W);
-      int it = 0;
+      int s = 0;
+      uint32_t ph = 0;
       for (int g = 0; g < ngroups; g++) {
-        const int row = r0 + g * R;
-        const int nr = min(R, r1 - row);
-        for (int j = 0; j < a.ksplit; j++, it++) {
-          const int s = it % a.n_stages;
-          const uint32_t ph = (uint32_t)(it / a.n_stages) & 1u;
+        const int row = r0 + g * GEMV_RS;
+        const int nr = min(GEMV_RS, r1 - row);
+        for (int j = 0; j < nchunk; j++) {
           mbar_wait(&empty[s], ph ^ 1u);
           unsigned char *dst = ring + (size_t)s * stage_bytes;
           mbar_arrive_expect_tx(&full[s], (uint32_t)(nr * seg_bytes));
-          if (a.ksplit == 1) {
+          if (nchunk == 1) {  // whole rows: the nr rows are one contiguous block
             bulk_g2s(dst, Wb + (size_t)row * K * es, (uint32_t)(nr * seg_bytes), &full[s], pol);
           } else {
             for (int r = 0; r < nr; r++)
               bulk_g2s(dst + r * seg_bytes, Wb + ((size_t)(row + r) * K + (size_t)j * KC) * es, (uint32_t)seg_bytes,
                        &full[s], pol);
           }
+          if (++s == a.n_stages) { s = 0; ph ^= 1u; }
         }
       }
     }
@@ -173,52 +177,45 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvArgs a)
     named_bar_sync(1, CT);
   }
 
-  // ---- main loop: each consumer warp owns the K-slice [warp*KC/8, (warp+1)*KC/8) of every chunk ---
+  // ---- main loop: warp w consumes segment w of every stage (row r0 + g*RS + w) --------------------
   {
-    const int nvec = KC / (GEMV_CONSUMER_WARPS * 8);  // 16-byte vectors per warp per row segment
+    const int nvec = KC / 8;  // 16-byte vectors per row segment
     const uint4 *xsv = reinterpret_cast<const uint4 *>(xs);
-    int it = 0;
+    int s = 0;
+    uint32_t ph = 0;
     for (int g = 0; g < ngroups; g++) {
-      float acc[R];
-#pragma unroll
-      for (int r = 0; r < R; r++) acc[r] = 0.f;
-      for (int j = 0; j < a.ksplit; j++, it++) {
-        const int s = it % a.n_stages;
-        const uint32_t ph = (uint32_t)(it / a.n_stages) & 1u;
+      const bool have_row = (g * GEMV_RS + warp) < nrows;
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      for (int j = 0; j < nchunk; j++) {
         mbar_wait(&full[s], ph);
-        const uint4 *st = reinterpret_cast<const uint4 *>(ring + (size_t)s * stage_bytes);
-        const int xoff = (j * KC) / 8 + warp * nvec;
-        for (int v = lane; v < nvec; v += 32) {
-          float xf[8];
-          unpack8<T>(xsv[xoff + v], xf);
-#pragma unroll
-          for (int r = 0; r < R; r++) {
-            float wf[8];
-            unpack8<T>(st[r * (KC / 8) + warp * nvec + v], wf);
-#pragma unroll
-            for (int i = 0; i < 8; i++) acc[r] = fmaf(wf[i], xf[i], acc[r]);
+        if (have_row) {
+          const uint4 *seg = reinterpret_cast<const uint4 *>(ring + (size_t)s * stage_bytes + (size_t)warp * seg_bytes);
+          const uint4 *xc = xsv + (size_t)j * nvec;
+#pragma unroll 4
+          for (int v = lane; v < nvec; v += 32) {
+            float xf[8], wf[8];
+            unpack8<T>(xc[v], xf);
+            unpack8<T>(seg[v], wf);
+            acc0 = fmaf(wf[0], xf[0], acc0); acc1 = fmaf(wf[1], xf[1], acc1);
+            acc2 = fmaf(wf[2], xf[2], acc2); acc3 = fmaf(wf[3], xf[3], acc3);
+            acc0 = fmaf(wf[4], xf[4], acc0); acc1 = fmaf(wf[5], xf[5], acc1);
+            acc2 = fmaf(wf[6], xf[6], acc2); acc3 = fmaf(wf[7], xf[7], acc3);
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == a.n_stages) { s = 0; ph ^= 1u; }
       }
-      const int nr = min(R, nrows - g * R);
-#pragma unroll
-      for (int r = 0; r < R; r++) {
-        float v = warp_sum(acc[r]);
-        if (lane == 0 && r < nr) partial[(g * R + r) * GEMV_CONSUMER_WARPS + warp] = v;
+      if (have_row) {
+        const float v = warp_sum((acc0 + acc1) + (acc2 + acc3));
+        if (lane == 0) rowsum[g * GEMV_RS + warp] = v;
       }
     }
   }
   named_bar_sync(1, CT);
 
   // ---- epilogue -----------------------------------------------------------------------------------
-  auto row_sum = [&](int rl) {
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < GEMV_CONSUMER_WARPS; w++) s += partial[rl * GEMV_CONSUMER_WARPS + w];
-    return rnd<T>(s);  // matmul result ->D
-  };
+  auto row_sum = [&](int rl) { return rnd<T>(rowsum[rl]); };  // matmul result ->D
   T *out = reinterpret_cast<T *>(a.out);
   if (EPI == EPI_PLAIN) {
     const T *bias = reinterpret_cast<const T *>(a.bias);

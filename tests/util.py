@@ -9,12 +9,25 @@ from cake_b200.synth import TORCH_DTYPES, make_checkpoint
 ULP = {"bf16": 2.0 ** -7, "f16": 2.0 ** -10}  # spacing relative to the binade (1 ulp of D)
 
 
+def ulp_at_scale(ref: np.ndarray, dtype: str) -> float:
+    """1 ulp of D at the magnitude of the largest reference element.  Block outputs are sums of terms of
+    that magnitude (residual + projection), so a 1-ulp flip of an intermediate shows up as an absolute
+    error of this size even on outputs that happen to be small."""
+    scale = max(float(np.abs(ref).max()), 2.0 ** -6)
+    return ULP[dtype] * 2.0 ** np.floor(np.log2(scale))
+
+
 def max_ulp_err(a: np.ndarray, ref: np.ndarray, dtype: str) -> float:
-    """max |a-ref| in ulps of D at the magnitude of ref (floored at 2^-6 so values near 0 do not explode)."""
+    """max |a-ref| in ulps of D at the tensor's scale (see ulp_at_scale)."""
     a, ref = np.asarray(a, np.float32), np.asarray(ref, np.float32)
-    mag = np.maximum(np.abs(ref), 2.0 ** -6)
-    ulp = ULP[dtype] * 2.0 ** np.floor(np.log2(mag))
-    return float((np.abs(a - ref) / ulp).max())
+    assert a.shape == ref.shape, (a.shape, ref.shape)
+    assert np.isfinite(a).all()
+    return float(np.abs(a - ref).max() / ulp_at_scale(ref, dtype))
+
+
+def mean_ulp_err(a: np.ndarray, ref: np.ndarray, dtype: str) -> float:
+    a, ref = np.asarray(a, np.float32), np.asarray(ref, np.float32)
+    return float(np.abs(a - ref).mean() / ulp_at_scale(ref, dtype))
 
 
 def to_np(t: torch.Tensor) -> np.ndarray:
