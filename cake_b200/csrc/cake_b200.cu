@@ -170,36 +170,49 @@ static int launch_pdl(cake_b200_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 
 
 // ------------------------------------------------------------------------------------------ GEMV plan + launch
 struct GemvPlan {
-  int KC, n_stages, max_rows, grid;
+  int KC, RS, WPR, RPW, n_stages, max_rows, grid;
   size_t smem;
 };
 static int plan_gemv(const cake_b200_ctx *c, int N, int K, int G, GemvPlan *p) {
   const int es = c->es;
   if (K % 64 != 0 || N % G != 0) return fail(CAKE_B200_EINVAL, "gemv: K=%d must be a multiple of 64, N=%d of %d", K, N, G);
-  // segment = KC columns of one row (2 KB at KC=1024): largest divisor of K that is <= 1024 and % 64 == 0
+  // segment: whole rows up to 16 KB, else the row is halved until it is (K=14336 -> 2 x 14 KB)
   int KC = K;
-  if (K > 1024) {
-    KC = 64;
-    for (int d = 1024; d >= 64; d -= 64)
-      if (K % d == 0) { KC = d; break; }
-  }
+  while ((size_t)KC * es > 16384 && (KC / 2) % 64 == 0) KC /= 2;
+  const size_t seg = (size_t)KC * es;
+  // column slices: keep >= 64 16-byte vectors per warp per row where the row is long enough
+  int WPR = 1;
+  while (WPR < 8 && (KC / 8) / (WPR * 2) >= 64) WPR *= 2;
+  if (WPR > 4) WPR = 4;
+  const int slots = GEMV_CONSUMER_WARPS / WPR;
+  int RPW = 1;  // rows per warp per stage: grow the stage towards 32 KB
+  while (RPW < 4 && (size_t)(slots * RPW * 2) * seg <= 32768) RPW *= 2;
+  const int RS = slots * RPW;
   const int units = N / G;
   const int grid = units < c->sm_count ? units : c->sm_count;
   const int max_rows = (units / grid + 1) * G;
-  const size_t budget = 108 * 1024;  // two CTAs (this kernel + its PDL successor) must fit in one SM's 227 KB
+  // two CTAs (this kernel + its PDL successor) must fit in one SM's 227 KB
+  const size_t budget = ((size_t)K * es > 16384 ? 116 : 108) * 1024;
   int ns = GEMV_MAX_STAGES;
-  while (ns > 2 && gemv_smem_bytes(K, KC, ns, max_rows, es) > budget) ns--;
-  const size_t smem = gemv_smem_bytes(K, KC, ns, max_rows, es);
+  while (ns > 2 && gemv_smem_bytes(K, KC, RS, WPR, ns, max_rows, es) > budget) ns--;
+  const size_t smem = gemv_smem_bytes(K, KC, RS, WPR, ns, max_rows, es);
   if (smem > 227 * 1024) return fail(CAKE_B200_EINVAL, "gemv: N=%d K=%d needs %zu B of shared memory", N, K, smem);
-  *p = GemvPlan{KC, ns, max_rows, grid, smem};
+  *p = GemvPlan{KC, RS, WPR, RPW, ns, max_rows, grid, smem};
   return CAKE_B200_OK;
 }
 
 template <typename T, int EPI> static int launch_gemv_T(cake_b200_ctx *c, GemvArgs a, const GemvPlan &p) {
   a.KC = p.KC;
+  a.RS = p.RS;
+  a.WPR = p.WPR;
   a.n_stages = p.n_stages;
   a.max_rows = p.max_rows;
-  return launch_pdl(c, gemv_kernel<T, EPI>, dim3(p.grid), dim3(GEMV_THREADS), p.smem, a);
+  dim3 grid(p.grid), block(GEMV_THREADS);
+  switch (p.RPW) {
+    case 1: return launch_pdl(c, gemv_kernel<T, EPI, 1>, grid, block, p.smem, a);
+    case 2: return launch_pdl(c, gemv_kernel<T, EPI, 2>, grid, block, p.smem, a);
+    default: return launch_pdl(c, gemv_kernel<T, EPI, 4>, grid, block, p.smem, a);
+  }
 }
 template <int EPI> static int launch_gemv(cake_b200_ctx *c, GemvArgs a) {
   GemvPlan p;
@@ -211,13 +224,15 @@ template <int EPI> static int launch_gemv(cake_b200_ctx *c, GemvArgs a) {
 template <typename T> static int set_smem_attrs_T() {
   const int maxs = 227 * 1024;
   // max-shared carveout so that a kernel and its programmatic-dependent successor co-reside on an SM
-#define SETA(EPI)                                                                                              \
-  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));            \
-  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#define SETA1(EPI, R)                                                                                          \
+  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));         \
+  CU(cudaFuncSetAttribute(gemv_kernel<T, EPI, R>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+#define SETA(EPI) SETA1(EPI, 1) SETA1(EPI, 2) SETA1(EPI, 4)
   SETA(EPI_PLAIN) SETA(EPI_RESIDUAL) SETA(EPI_SWIGLU) SETA(EPI_ARGMAX)
 #undef SETA
+#undef SETA1
 #define SETB(HD)                                                                                                  \
-  CU(cudaFuncSetAttribute(attn_decode_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs));         \
+  CU(cudaFuncSetAttribute(attn_decode_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs - 4096)); /* static smem counts too */         \
   CU(cudaFuncSetAttribute(attn_decode_kernel<T, HD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   SETB(16) SETB(32) SETB(64) SETB(128) SETB(256)
 #undef SETB

@@ -4,16 +4,16 @@
 // HBM streaming, not math:
 //   * persistent grid, one CTA per SM (148); each CTA owns a contiguous row range [r0,r1) so the
 //     weight bytes of a CTA are ONE contiguous stream (row-major W) — perfectly sequential DRAM pages;
-//   * a dedicated producer warp issues TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) of 8-32 KB
-//     row segments into a shared-memory ring guarded by full/empty mbarriers; ~80-100 KB in flight
+//   * a dedicated producer warp issues TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) of 14-32 KB
+//     row blocks into a shared-memory ring guarded by full/empty mbarriers; ~80-100 KB in flight
 //     per SM with zero register cost, L2 policy evict_first (each weight byte is used once per token);
 //   * the producer starts streaming BEFORE griddepcontrol.wait: weights do not depend on the previous
 //     kernel, so with programmatic dependent launch the ring is already full when the activation
 //     arrives — the kernel boundary costs no HBM idle time;
-//   * 8 consumer warps, each owning whole rows (its lanes split the columns); x (optionally
-//     RMS-normalised in-kernel, f32 sum of squares) lives in shared memory in dtype D; fp32
-//     accumulation in 4 independent chains per lane, one shuffle tree per row — a fixed order, so
-//     results are bit-deterministic run to run;
+//   * 8 consumer warps as (row slot x column slice); x (optionally RMS-normalised in-kernel, f32 sum
+//     of squares) lives in shared memory in dtype D; fp32 accumulation in 2 independent chains per
+//     row per lane, one shuffle tree per row per warp, slices summed in a fixed order — results are
+//     bit-deterministic run to run;
 //   * epilogues fuse what the reference does as separate tensor ops: +bias, +residual (transformer.rs:123,131),
 //     silu(gate)*up on row-interleaved Wgu (mlp.rs:22-28), logits + greedy argmax (text_model.rs:348-352,104-105).
 // Rounding points follow SURVEY.md Appendix A: the matmul result is rounded to D before any epilogue op.
@@ -25,7 +25,6 @@ namespace cake {
 enum { EPI_PLAIN = 0, EPI_RESIDUAL = 1, EPI_SWIGLU = 2, EPI_ARGMAX = 3 };
 
 constexpr int GEMV_CONSUMER_WARPS = 8;
-constexpr int GEMV_RS = GEMV_CONSUMER_WARPS;                  // rows per stage: one per consumer warp
 constexpr int GEMV_THREADS = (GEMV_CONSUMER_WARPS + 1) * 32;  // + 1 producer warp
 constexpr int GEMV_MAX_STAGES = 16;
 
@@ -38,9 +37,11 @@ struct GemvArgs {
   void *out;             // [N] D  ([N/2] for EPI_SWIGLU)
   float eps;
   int N, K;
-  int KC;        // columns per stage segment (divides K, multiple of 64 unless KC == K)
+  // stage geometry (host-planned, see plan_gemv): a stage holds RS row segments of KC columns; the 8
+  // consumer warps form (8/WPR) row slots x WPR column slices; a warp covers RS/(8/WPR) rows per stage.
+  int KC, RS, WPR;
   int n_stages;
-  int max_rows;  // upper bound of rows per CTA (sizes the row-sum scratch)
+  int max_rows;  // upper bound of rows per CTA (sizes the partial-sum scratch)
   // EPI_ARGMAX
   float *part_val;
   int *part_idx;
@@ -51,35 +52,35 @@ struct GemvArgs {
   int ring_cap;
 };
 
-__host__ __device__ inline size_t gemv_smem_bytes(int K, int KC, int n_stages, int max_rows, int es) {
-  size_t stage = (size_t)GEMV_RS * KC * es;
+__host__ __device__ inline size_t gemv_smem_bytes(int K, int KC, int RS, int WPR, int n_stages, int max_rows, int es) {
+  size_t stage = (size_t)RS * KC * es;
   size_t off = (size_t)n_stages * stage;                 // ring
   off += (size_t)K * es;                                 // xs
   off = (off + 15) & ~(size_t)15;
-  off += (size_t)max_rows * 4;                           // row sums
+  off += (size_t)max_rows * WPR * 4;                     // partial sums [row][slice]
   off += 64 * 4;                                         // reduction scratch
   off = (off + 7) & ~(size_t)7;
   off += (size_t)2 * GEMV_MAX_STAGES * 8;                // mbarriers
   return off + 128;                                      // alignment slack
 }
 
-// A stage holds up to GEMV_RS row segments of KC columns; consumer warp w owns segment w, i.e. a warp
-// owns whole rows: its 32 lanes split the columns, accumulate in fp32 registers across the K/KC chunks
-// of the row, and do ONE 5-step shuffle reduction per row (not per stage).
-template <typename T, int EPI>
+// Geometry chosen from measurements (bench_tools/gemv_sweep.cu, profiles/gemv_sweep_r01.txt): TMA bulk
+// copies must be large (>= 16 KB; 2 KB copies cap at 4.3 TB/s even with no math) and stages ~32 KB;
+// 2 row slots x 4 column slices keeps every lane busy with one shuffle tree per row per warp.
+template <typename T, int EPI, int RPW>
 __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int es = sizeof(T);
-  const int K = a.K, N = a.N, KC = a.KC;
+  const int K = a.K, N = a.N, KC = a.KC, RS = a.RS, WPR = a.WPR;
   const int nchunk = K / KC;
   const size_t seg_bytes = (size_t)KC * es;
-  const size_t stage_bytes = (size_t)GEMV_RS * seg_bytes;
+  const size_t stage_bytes = (size_t)RS * seg_bytes;
   unsigned char *ring = smem_raw;
   T *xs = reinterpret_cast<T *>(ring + (size_t)a.n_stages * stage_bytes);
   size_t off = (size_t)a.n_stages * stage_bytes + (size_t)K * es;
   off = (off + 15) & ~(size_t)15;
-  float *rowsum = reinterpret_cast<float *>(smem_raw + off);
-  off += (size_t)a.max_rows * 4;
+  float *partial = reinterpret_cast<float *>(smem_raw + off);
+  off += (size_t)a.max_rows * WPR * 4;
   float *scratch = reinterpret_cast<float *>(smem_raw + off);
   off += 64 * 4;
   off = (off + 7) & ~(size_t)7;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvArgs a)
   const int r0 = (int)(units * blockIdx.x / gridDim.x) * G;
   const int r1 = (int)(units * (blockIdx.x + 1) / gridDim.x) * G;
   const int nrows = r1 - r0;
-  const int ngroups = (nrows + GEMV_RS - 1) / GEMV_RS;
+  const int ngroups = (nrows + RS - 1) / RS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.n_stages; s++) {
@@ -112,13 +113,13 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvArgs a)
       int s = 0;
       uint32_t ph = 0;
       for (int g = 0; g < ngroups; g++) {
-        const int row = r0 + g * GEMV_RS;
-        const int nr = min(GEMV_RS, r1 - row);
+        const int row = r0 + g * RS;
+        const int nr = min(RS, r1 - row);
         for (int j = 0; j < nchunk; j++) {
           mbar_wait(&empty[s], ph ^ 1u);
           unsigned char *dst = ring + (size_t)s * stage_bytes;
           mbar_arrive_expect_tx(&full[s], (uint32_t)(nr * seg_bytes));
-          if (nchunk == 1) {  // whole rows: the nr rows are one contiguous block
+          if (nchunk == 1) {  // whole rows: the nr rows are one contiguous block -> ONE bulk copy
             bulk_g2s(dst, Wb + (size_t)row * K * es, (uint32_t)(nr * seg_bytes), &full[s], pol);
           } else {
             for (int r = 0; r < nr; r++)
@@ -177,45 +178,55 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvArgs a)
     named_bar_sync(1, CT);
   }
 
-  // ---- main loop: warp w consumes segment w of every stage (row r0 + g*RS + w) --------------------
+  // ---- main loop: warp (slot, ks) covers rows slot, slot+slots, .. of each stage over column slice ks
   {
-    const int nvec = KC / 8;  // 16-byte vectors per row segment
+    const int slots = GEMV_CONSUMER_WARPS / WPR;
+    const int slot = warp / WPR, ks = warp % WPR;
+    const int segv = KC / 8;           // 16-byte vectors per row segment
+    const int nvec = segv / WPR;       // ... per warp
     const uint4 *xsv = reinterpret_cast<const uint4 *>(xs);
     int s = 0;
     uint32_t ph = 0;
     for (int g = 0; g < ngroups; g++) {
-      const bool have_row = (g * GEMV_RS + warp) < nrows;
-      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+      float acc[RPW][2];
+#pragma unroll
+      for (int r = 0; r < RPW; r++) acc[r][0] = acc[r][1] = 0.f;
       for (int j = 0; j < nchunk; j++) {
         mbar_wait(&full[s], ph);
-        if (have_row) {
-          const uint4 *seg = reinterpret_cast<const uint4 *>(ring + (size_t)s * stage_bytes + (size_t)warp * seg_bytes);
-          const uint4 *xc = xsv + (size_t)j * nvec;
-#pragma unroll 4
-          for (int v = lane; v < nvec; v += 32) {
-            float xf[8], wf[8];
-            unpack8<T>(xc[v], xf);
-            unpack8<T>(seg[v], wf);
-            acc0 = fmaf(wf[0], xf[0], acc0); acc1 = fmaf(wf[1], xf[1], acc1);
-            acc2 = fmaf(wf[2], xf[2], acc2); acc3 = fmaf(wf[3], xf[3], acc3);
-            acc0 = fmaf(wf[4], xf[4], acc0); acc1 = fmaf(wf[5], xf[5], acc1);
-            acc2 = fmaf(wf[6], xf[6], acc2); acc3 = fmaf(wf[7], xf[7], acc3);
+        const uint4 *st = reinterpret_cast<const uint4 *>(ring + (size_t)s * stage_bytes);
+        const uint4 *xc = xsv + (size_t)j * segv + ks * nvec;
+#pragma unroll 2
+        for (int v = lane; v < nvec; v += 32) {
+          float xf[8];
+          unpack8<T>(xc[v], xf);
+#pragma unroll
+          for (int r = 0; r < RPW; r++) {
+            float wf[8];
+            unpack8<T>(st[(size_t)(slot + r * slots) * segv + ks * nvec + v], wf);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[r][i & 1] = fmaf(wf[i], xf[i], acc[r][i & 1]);
           }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[s]);
         if (++s == a.n_stages) { s = 0; ph ^= 1u; }
       }
-      if (have_row) {
-        const float v = warp_sum((acc0 + acc1) + (acc2 + acc3));
-        if (lane == 0) rowsum[g * GEMV_RS + warp] = v;
+#pragma unroll
+      for (int r = 0; r < RPW; r++) {
+        const float v = warp_sum(acc[r][0] + acc[r][1]);
+        const int rl = g * RS + slot + r * slots;
+        if (lane == 0 && rl < nrows) partial[rl * WPR + ks] = v;
       }
     }
   }
   named_bar_sync(1, CT);
 
   // ---- epilogue -----------------------------------------------------------------------------------
-  auto row_sum = [&](int rl) { return rnd<T>(rowsum[rl]); };  // matmul result ->D
+  auto row_sum = [&](int rl) {
+    float s = 0.f;
+    for (int w = 0; w < WPR; w++) s += partial[rl * WPR + w];  // fixed order: deterministic
+    return rnd<T>(s);                                          // matmul result ->D
+  };
   T *out = reinterpret_cast<T *>(a.out);
   if (EPI == EPI_PLAIN) {
     const T *bias = reinterpret_cast<const T *>(a.bias);
