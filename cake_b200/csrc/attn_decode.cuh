@@ -48,29 +48,34 @@ __host__ __device__ inline size_t attn_smem_bytes(int hd, int es) {
 }
 
 // RMSNorm (optional, attention.rs:202-215) + rotate-half RoPE (backends/mod.rs:444-482) of one head
-// vector by one warp, staged in shared memory as f32 (values stay D-representable).
+// vector held as f32 in shared memory (values stay D-representable), by one warp, in place.
 template <typename T, int HD>
-__device__ __forceinline__ void norm_rope_head(const T *src, float *dst_smem, const T *norm_w, float eps,
-                                               const T *cosr, const T *sinr, int rot, int lane) {
-  for (int d = lane; d < HD; d += 32) dst_smem[d] = DT<T>::to_f(src[d]);
-  __syncwarp();
+__device__ __forceinline__ void norm_rope_inplace(float *buf, const T *norm_w, float eps, const T *cosr, const T *sinr,
+                                                  int rot, int lane) {
   if (norm_w) {
     float ss = 0.f;
-    for (int d = lane; d < HD; d += 32) ss += dst_smem[d] * dst_smem[d];
+    for (int d = lane; d < HD; d += 32) ss += buf[d] * buf[d];
     ss = warp_sum(ss);
     const float inv = 1.0f / sqrtf(ss / (float)HD + eps);
-    for (int d = lane; d < HD; d += 32) dst_smem[d] = rnd<T>(dst_smem[d] * inv * DT<T>::to_f(norm_w[d]));
+    for (int d = lane; d < HD; d += 32) buf[d] = rnd<T>(buf[d] * inv * DT<T>::to_f(norm_w[d]));
     __syncwarp();
   }
   const int half = rot / 2;
   for (int i = lane; i < half; i += 32) {
     const float c = DT<T>::to_f(cosr[i]), s = DT<T>::to_f(sinr[i]);
-    const float x1 = dst_smem[i], x2 = dst_smem[i + half];
+    const float x1 = buf[i], x2 = buf[i + half];
     // per-op rounding in D (half-crate / __nv_bfloat16 operator semantics)
-    dst_smem[i] = rnd<T>(rnd<T>(x1 * c) - rnd<T>(x2 * s));
-    dst_smem[i + half] = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
+    buf[i] = rnd<T>(rnd<T>(x1 * c) - rnd<T>(x2 * s));
+    buf[i + half] = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
   }
   __syncwarp();
+}
+template <typename T, int HD>
+__device__ __forceinline__ void norm_rope_head(const T *src, float *dst_smem, const T *norm_w, float eps,
+                                               const T *cosr, const T *sinr, int rot, int lane) {
+  for (int d = lane; d < HD; d += 32) dst_smem[d] = DT<T>::to_f(src[d]);
+  __syncwarp();
+  norm_rope_inplace<T, HD>(dst_smem, norm_w, eps, cosr, sinr, rot, lane);
 }
 
 template <typename T, int HD>

@@ -15,6 +15,7 @@
 #include "../../include/cake_b200.h"
 #include "attn_decode.cuh"
 #include "common.cuh"
+#include "decode_mega.cuh"
 #include "gemv.cuh"
 #include "prefill.cuh"
 
@@ -122,6 +123,11 @@ struct cake_b200_ctx {
   long steps_done = 0;
   uint64_t launches = 0;
   bool capturing = false;
+  // persistent decode megakernel (decode_mega.cuh); CAKE_B200_PER_OP=1 selects the per-op kernels instead
+  bool use_mega = true;
+  unsigned long long *gbar = nullptr;   // [0] grid-barrier counter, [1] launch epoch
+  MkLayer *mk_tab_dev = nullptr, *mk_tab_host = nullptr, *g_tab_dev = nullptr;
+  std::vector<const void *> mk_sig;
 };
 constexpr int TOKEN_RING = 1 << 16;
 
@@ -236,6 +242,11 @@ template <typename T> static int set_smem_attrs_T() {
   CU(cudaFuncSetAttribute(attn_decode_kernel<T, HD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   SETB(16) SETB(32) SETB(64) SETB(128) SETB(256)
 #undef SETB
+#define SETC(HD)                                                                                                  \
+  CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs - 2048));  \
+  CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  SETC(16) SETC(32) SETC(64) SETC(128) SETC(256)
+#undef SETC
   return CAKE_B200_OK;
 }
 
@@ -343,6 +354,15 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
   CU(cudaMemset(c->d_step, 0, 4));
   CU(cudaMalloc(&c->token_ring, (size_t)TOKEN_RING * 4));
   CU(cudaMallocHost(&c->h_pin, 64 * 4));
+  CU(cudaMalloc(&c->gbar, 16));
+  CU(cudaMemset(c->gbar, 0, 16));
+  CU(cudaMalloc(&c->mk_tab_dev, sizeof(MkLayer) * MK_MAX_LAYERS));
+  CU(cudaMalloc(&c->g_tab_dev, sizeof(MkLayer) * MK_MAX_LAYERS));
+  CU(cudaMallocHost(&c->mk_tab_host, sizeof(MkLayer) * MK_MAX_LAYERS));
+  {
+    const char *e = getenv("CAKE_B200_PER_OP");
+    c->use_mega = !(e && e[0] == '1');
+  }
   *out = c;
   return CAKE_B200_OK;
 }
@@ -356,12 +376,14 @@ extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
   void *bufs[] = {c->cos_t, c->sin_t, c->embed, c->ln_f, c->xa, c->xb, c->qkv, c->y, c->mm, c->logits, c->ws_ml,
                   c->ws_acc, c->part_val, c->part_idx, c->d_step, c->attn_counters, c->argmax_counter, c->d_token,
-                  c->token_ring, c->d_ids, c->d_pen, c->pf_h, c->pf_qkv, c->pf_y, c->pf_x1, c->pf_gu, c->pf_mm, c->io_x};
+                  c->token_ring, c->d_ids, c->d_pen, c->pf_h, c->pf_qkv, c->pf_y, c->pf_x1, c->pf_gu, c->pf_mm, c->io_x,
+                  c->gbar, c->mk_tab_dev, c->g_tab_dev};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (c->lm_head && c->lm_head != c->embed) cudaFree(c->lm_head);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->h_pin_x) cudaFreeHost(c->h_pin_x);
+  if (c->mk_tab_host) cudaFreeHost(c->mk_tab_host);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -574,6 +596,122 @@ static int enqueue_decode_layers(cake_b200_ctx *c, cake_b200_block *const *block
   return CAKE_B200_OK;
 }
 
+// ------------------------------------------------------------------------------------------ megakernel plan + launch
+static int plan_mk_geom(const cake_b200_ctx *c, int N, int K, int G, MkGeom *g, int *partial_floats) {
+  const int es = c->es;
+  if (K % 64 != 0 || N % G != 0) return fail(CAKE_B200_EINVAL, "mega: K=%d must be a multiple of 64, N=%d of %d", K, N, G);
+  int KC = K;
+  while ((size_t)KC * es > MK_STAGE_BYTES && (KC / 2) % 64 == 0) KC /= 2;
+  const size_t seg = (size_t)KC * es;
+  if (seg > MK_STAGE_BYTES) return fail(CAKE_B200_EINVAL, "mega: K=%d cannot be staged", K);
+  int RS = 1;
+  while (RS < 64 && (size_t)(RS * 2) * seg <= MK_STAGE_BYTES) RS *= 2;
+  int WPR, RPW;
+  if (RS >= MK_CW) { WPR = 1; RPW = RS / MK_CW; }
+  else { WPR = MK_CW / RS; RPW = 1; }
+  while (WPR > 1 && ((KC / 8) % WPR != 0)) { WPR /= 2; }  // slices must divide the segment's 16-byte vectors
+  if (RS * RPW < (MK_CW / WPR) * RPW || RS != (MK_CW / WPR) * RPW)  // every row slot must map to a staged row
+    return fail(CAKE_B200_EINVAL, "mega: unsupported geometry N=%d K=%d (KC=%d RS=%d WPR=%d)", N, K, KC, RS, WPR);
+  *g = MkGeom{N, K, KC, RS, WPR, RPW};
+  const int pf = (((N / G) / c->sm_count) + 1) * G * WPR;
+  if (pf > *partial_floats) *partial_floats = pf;
+  return CAKE_B200_OK;
+}
+
+struct MkPlan {
+  MkArgs a;
+  size_t smem;
+};
+static int plan_mega(cake_b200_ctx *c, cake_b200_cache *kc, bool with_head, MkPlan *p) {
+  const cake_b200_config &f = c->cfg;
+  MkArgs &a = p->a;
+  memset(&a, 0, sizeof(a));
+  int pf = 0;
+  RC(plan_mk_geom(c, c->nqkv, f.hidden, 1, &a.g_qkv, &pf));
+  RC(plan_mk_geom(c, f.hidden, f.n_heads * f.head_dim, 1, &a.g_o, &pf));
+  RC(plan_mk_geom(c, 2 * f.inter, f.hidden, 2, &a.g_gu, &pf));
+  RC(plan_mk_geom(c, f.hidden, f.inter, 1, &a.g_down, &pf));
+  if (with_head) RC(plan_mk_geom(c, f.vocab, f.hidden, 1, &a.g_head, &pf));
+  a.partial_floats = pf;
+  a.hidden = f.hidden; a.inter = f.inter; a.n_heads = f.n_heads; a.n_kv = f.n_kv_heads; a.hd = f.head_dim;
+  a.rot = c->rot; a.cap = kc ? kc->cap : 0; a.nsplit = c->nsplit; a.eps = f.rms_eps;
+  a.scale = (float)(1.0 / sqrt((double)f.head_dim));
+  a.max_k = f.inter > f.hidden ? f.inter : f.hidden;
+  if (f.n_heads * f.head_dim > a.max_k) a.max_k = f.n_heads * f.head_dim;
+  a.xa = c->xa; a.xb = c->xb; a.qkv = c->qkv; a.y = c->y; a.mm = c->mm;
+  a.ws_ml = c->ws_ml; a.ws_acc = c->ws_acc; a.attn_counters = c->attn_counters;
+  a.cos_t = c->cos_t; a.sin_t = c->sin_t; a.d_pos = kc ? kc->d_pos : nullptr; a.d_step = c->d_step; a.gbar = c->gbar;
+  a.vocab = f.vocab; a.embed = c->embed; a.d_token = c->d_token;
+  a.ln_f = c->ln_f; a.lm_head = c->lm_head; a.logits = c->logits; a.part_val = c->part_val; a.part_idx = c->part_idx;
+  a.argmax_counter = c->argmax_counter; a.token_out = c->d_token; a.token_ring = nullptr; a.ring_cap = TOKEN_RING;
+  int ns = MK_MAX_STAGES;
+  const size_t limit = 227 * 1024 - 2048;
+  while (ns > 2 && mk_smem_bytes(a.max_k, pf, ns, c->es) > limit) ns--;
+  a.n_stages = ns;
+  p->smem = mk_smem_bytes(a.max_k, pf, ns, c->es);
+  if (p->smem > limit) return fail(CAKE_B200_EINVAL, "mega: needs %zu B of shared memory", p->smem);
+  return CAKE_B200_OK;
+}
+
+static int launch_mega(cake_b200_ctx *c, const MkPlan &p) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(c->sm_count);
+  cfg.blockDim = dim3(MK_THREADS);
+  cfg.dynamicSmemBytes = p.smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident (grid barriers inside)
+  at[0].val.cooperative = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  const MkArgs &a = p.a;
+  int rc = DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+    typedef typename decltype(tag_)::type T;
+    switch (c->cfg.head_dim) {
+      case 16: CU(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T, 16>, a)); break;
+      case 32: CU(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T, 32>, a)); break;
+      case 64: CU(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T, 64>, a)); break;
+      case 128: CU(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T, 128>, a)); break;
+      default: CU(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T, 256>, a)); break;
+    }
+    return CAKE_B200_OK;
+  });
+  RC(rc);
+  if (c->capturing) c->g_kernels++;
+  else c->launches++;
+  return CAKE_B200_OK;
+}
+
+static void fill_mk_table(MkLayer *tab, cake_b200_block *const *blocks, const int *block_idx, int n, cake_b200_cache *kc) {
+  for (int i = 0; i < n; i++) {
+    const cake_b200_block *b = blocks[i];
+    tab[i] = MkLayer{b->wqkv, b->wo, b->wgu, b->wd, b->ln1, b->ln2, b->bqkv, b->qn, b->kn, kc->k[block_idx[i]], kc->v[block_idx[i]]};
+  }
+}
+
+// x_in -> x_out through n blocks in ONE persistent kernel; position from cache->d_pos
+static int enqueue_mega_layers(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *block_idx, int n,
+                               cake_b200_cache *kc, const void *x_in, void *x_out) {
+  if (n > MK_MAX_LAYERS) return fail(CAKE_B200_EINVAL, "more than %d blocks in one call", MK_MAX_LAYERS);
+  std::vector<const void *> sig;
+  for (int i = 0; i < n; i++) { sig.push_back(blocks[i]); sig.push_back(kc->k[block_idx[i]]); }
+  if (sig != c->mk_sig) {  // (re)build the layer table; rare
+    CU(cudaStreamSynchronize(c->stream));
+    fill_mk_table(c->mk_tab_host, blocks, block_idx, n, kc);
+    CU(cudaMemcpyAsync(c->mk_tab_dev, c->mk_tab_host, sizeof(MkLayer) * n, cudaMemcpyHostToDevice, c->stream));
+    c->mk_sig = sig;
+  }
+  MkPlan p;
+  RC(plan_mega(c, kc, false, &p));
+  p.a.layers = c->mk_tab_dev;
+  p.a.n_layers = n;
+  p.a.x_in = x_in;
+  p.a.x_out = x_out;
+  p.a.has_head = 0;
+  p.a.advance = 0;
+  return launch_mega(c, p);
+}
+
 // ln_f + lm_head + greedy argmax on one hidden row -> logits_out (nullable), token -> c->d_token
 static int enqueue_head(cake_b200_ctx *c, const void *x_row, void *logits_out, bool ring) {
   GemvArgs a{};
@@ -665,7 +803,8 @@ extern "C" int cake_b200_forward_batch(cake_b200_ctx *c, cake_b200_block *const 
   if (batch == 1 && seq == 1) {
     set_int_kernel<<<1, 1, 0, c->stream>>>(kc->d_pos, index_pos);
     c->launches++;
-    RC(enqueue_decode_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev));
+    if (c->use_mega) RC(enqueue_mega_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev));
+    else RC(enqueue_decode_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev));
   } else {
     RC(enqueue_prefill_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev, batch, seq, index_pos));
   }
@@ -840,10 +979,45 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
   if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
   const size_t xbytes = (size_t)c->cfg.hidden * c->es;
   CU(cudaStreamSynchronize(c->stream));
+  if (n_blocks > MK_MAX_LAYERS) return fail(CAKE_B200_EINVAL, "more than %d blocks per shard", MK_MAX_LAYERS);
+  if (n_blocks > 0) {
+    std::vector<MkLayer> tab(n_blocks);
+    fill_mk_table(tab.data(), blocks, block_idx, n_blocks, kc);
+    CU(cudaMemcpy(c->g_tab_dev, tab.data(), sizeof(MkLayer) * n_blocks, cudaMemcpyHostToDevice));
+  }
   CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
   c->capturing = true;
   c->g_kernels = 0;
   int rc = [&]() -> int {
+    if (c->use_mega) {
+      // rank 0: [embed+layers(+head if alone)] ; world>1: layers -> send ... recv -> head.  ranks>0: recv -> layers -> send
+      MkPlan p;
+      if (rank == 0) {
+        RC(plan_mega(c, kc, world == 1, &p));
+        p.a.layers = c->g_tab_dev; p.a.n_layers = n_blocks; p.a.x_in = nullptr; p.a.x_out = c->xa;
+        p.a.has_head = (world == 1); p.a.advance = (world == 1); p.a.token_ring = c->token_ring;
+        if (n_blocks > 0 || world == 1) RC(launch_mega(c, p));
+        if (world > 1) {
+          if (n_blocks == 0) return fail(CAKE_B200_EINVAL, "rank 0 must own at least one layer");
+          RC(cake_b200_send(c, c->xa, xbytes, 1));
+          RC(cake_b200_recv(c, c->xa, xbytes, world - 1));
+          MkPlan h;
+          RC(plan_mega(c, kc, true, &h));
+          h.a.layers = c->g_tab_dev; h.a.n_layers = 0; h.a.x_in = c->xa; h.a.x_out = c->xa;
+          h.a.has_head = 1; h.a.advance = 1; h.a.token_ring = c->token_ring;
+          RC(launch_mega(c, h));
+        }
+      } else {
+        RC(cake_b200_recv(c, c->xa, xbytes, rank - 1));
+        RC(plan_mega(c, kc, false, &p));
+        p.a.layers = c->g_tab_dev; p.a.n_layers = n_blocks; p.a.x_in = c->xa; p.a.x_out = c->xa;
+        p.a.has_head = 0; p.a.advance = 1;
+        if (n_blocks > 0) RC(launch_mega(c, p));
+        else RC(launch_pdl(c, advance_kernel, dim3(1), dim3(32), 0, kc->d_pos, c->d_step));
+        RC(cake_b200_send(c, c->xa, xbytes, (rank + 1) % world));
+      }
+      return CAKE_B200_OK;
+    }
     if (rank == 0) {
       RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
       typedef typename decltype(tag_)::type T;

@@ -102,6 +102,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// scalar D load that bypasses L1 (data produced by another SM during the same kernel)
+template <typename T> __device__ __forceinline__ T ldcg_T(const T *p) {
+  const unsigned short u = __ldcg(reinterpret_cast<const unsigned short *>(p));
+  T r;
+  *reinterpret_cast<unsigned short *>(&r) = u;
+  return r;
+}
+
 __device__ __forceinline__ uint4 ld_nc_v4(const void *p) {
   uint4 r;
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"

@@ -1,0 +1,700 @@
+// decode_mega.cuh — the decode hot loop as ONE persistent kernel per shard-step.
+//
+// Why: with one kernel per op (5 per layer) every dependency between ops is a kernel boundary that
+// costs ~3 us of HBM idle time even with programmatic dependent launch (profiles/gemv_sweep_r01.txt:
+// o_proj 7.2 us streamed vs 5.1 us ideal) — 130 boundaries per token = ~0.4 ms of a 2.3 ms budget.
+// Here the whole walk  [rms_1+qkv -> rope/append/attention -> o_proj+res -> rms_2+gate_up+silu*mul ->
+// down+res] x layers (+ ln_f/lm_head/argmax on the master)  runs inside one grid of one CTA per SM:
+//   * warp 16 is the PRODUCER: it walks the same static phase list and issues TMA bulk copies of the
+//     next weight rows (32 KB stages, evict_first) and of this CTA's K/V cache tile into a 5-6 stage
+//     shared-memory ring.  It never takes part in a grid barrier, so HBM keeps streaming while the
+//     consumers synchronise — the ring (~160 KB/SM, ~24 MB chip-wide) absorbs the bubbles;
+//   * warps 0-15 are CONSUMERS: per phase they wait for the grid barrier that publishes the previous
+//     phase's output vector, stage x (RMS-normalised in-kernel), multiply-accumulate the staged rows in
+//     fp32 and run the fused epilogue;
+//   * grid barriers are a 64-bit monotonic counter in global memory (release: bar.sync + threadfence +
+//     atomicAdd; acquire: ld.acquire poll + threadfence); activations are read with ld.global.cg.
+// Arithmetic and rounding points are identical to the per-op kernels (gemv.cuh / attn_decode.cuh); only the
+// fp32 summation order within a dot product differs (tests/test_gpu_parity.py::test_megakernel_equals_per_op_kernels).
+#pragma once
+#include "common.cuh"
+#include "gemv.cuh"
+#include "attn_decode.cuh"
+
+namespace cake {
+
+constexpr int MK_CW = 16;                       // consumer warps
+constexpr int MK_CT = MK_CW * 32;               // consumer threads
+constexpr int MK_THREADS = (MK_CW + 1) * 32;    // + producer warp
+constexpr int MK_STAGE_BYTES = 32768;
+constexpr int MK_MAX_STAGES = 6;
+constexpr int MK_MAX_LAYERS = 96;
+constexpr int MK_BARS_PER_LAUNCH = 1024;        // upper bound of grid barriers in one launch
+
+struct MkLayer {
+  const void *wqkv, *wo, *wgu, *wd, *ln1, *ln2, *bqkv, *qn, *kn;
+  void *kc, *vc;
+};
+struct MkGeom {  // one decode GEMV type; a stage holds RS row segments of KC columns
+  int N, K, KC, RS, WPR, RPW;
+};
+struct MkArgs {
+  const MkLayer *layers;
+  int n_layers;
+  MkGeom g_qkv, g_o, g_gu, g_down, g_head;
+  int hidden, inter, n_heads, n_kv, hd, rot, cap, nsplit, max_k;
+  float eps, scale;
+  const void *x_in;          // input hidden state (nullptr on the master: embed row of *d_token)
+  const void *embed;
+  const uint32_t *d_token;
+  void *x_out;               // output hidden state of this shard
+  void *xa, *xb, *qkv, *y, *mm;
+  float *ws_ml, *ws_acc;
+  unsigned *attn_counters;
+  const void *cos_t, *sin_t;
+  int *d_pos, *d_step;
+  unsigned long long *gbar;      // [0] barrier counter, [1] launch epoch
+  int has_head, advance, n_stages, vocab, partial_floats;
+  const void *ln_f, *lm_head;
+  void *logits;
+  float *part_val;
+  int *part_idx;
+  unsigned *argmax_counter;
+  uint32_t *token_out, *token_ring;
+  int ring_cap;
+};
+
+__host__ __device__ inline size_t mk_xs_bytes(int max_k, int es) {
+  size_t b = (size_t)max_k * es;
+  const size_t attn = (size_t)(ATTN_MAX_G * 256 * 4) + (size_t)ATTN_MAX_G * 128 * 4 + (size_t)4 * ATTN_MAX_G * 256 * 4 / 2;
+  return b > attn ? b : attn;  // the attention phase overlays its scratch on the x buffer
+}
+__host__ __device__ inline size_t mk_smem_bytes(int max_k, int partial_floats, int n_stages, int es) {
+  size_t off = (size_t)n_stages * MK_STAGE_BYTES;
+  off += mk_xs_bytes(max_k, es);
+  off = (off + 15) & ~(size_t)15;
+  off += (size_t)partial_floats * 4;     // partial sums [row][slice]
+  off += 128 * 4;                        // scratch
+  off = (off + 7) & ~(size_t)7;
+  off += (size_t)2 * MK_MAX_STAGES * 8;  // mbarriers
+  return off + 256;
+}
+
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint4 ldcg_v4(const void *p) { return __ldcg(reinterpret_cast<const uint4 *>(p)); }
+
+struct MkRing {
+  unsigned char *ring;
+  uint64_t *full, *empty;
+  int n_stages;
+  int s;
+  uint32_t ph;
+  __device__ __forceinline__ void advance() {
+    if (++s == n_stages) { s = 0; ph ^= 1u; }
+  }
+};
+
+// rows [r0,r1) of this CTA for a GEMV over N rows with row granularity G
+__device__ __forceinline__ void mk_rows(int N, int G, int &r0, int &r1) {
+  const long units = N / G;
+  r0 = (int)(units * blockIdx.x / gridDim.x) * G;
+  r1 = (int)(units * (blockIdx.x + 1) / gridDim.x) * G;
+}
+
+// ---------------------------------------------------------------------------------------- producer
+template <typename T>
+__device__ __forceinline__ void mk_produce_gemv(MkRing &rg, const MkGeom &g, const void *W, int G, uint64_t pol) {
+  constexpr int es = sizeof(T);
+  int r0, r1;
+  mk_rows(g.N, G, r0, r1);
+  const int nchunk = g.K / g.KC;
+  const size_t seg = (size_t)g.KC * es;
+  const unsigned char *Wb = reinterpret_cast<const unsigned char *>(W);
+  for (int row = r0; row < r1; row += g.RS) {
+    const int nr = min(g.RS, r1 - row);
+    for (int j = 0; j < nchunk; j++) {
+      mbar_wait(&rg.empty[rg.s], rg.ph ^ 1u);
+      unsigned char *dst = rg.ring + (size_t)rg.s * MK_STAGE_BYTES;
+      mbar_arrive_expect_tx(&rg.full[rg.s], (uint32_t)(nr * seg));
+      if (nchunk == 1) {
+        bulk_g2s(dst, Wb + (size_t)row * g.K * es, (uint32_t)(nr * seg), &rg.full[rg.s], pol);
+      } else {
+        for (int r = 0; r < nr; r++)
+          bulk_g2s(dst + r * seg, Wb + ((size_t)(row + r) * g.K + (size_t)j * g.KC) * es, (uint32_t)seg, &rg.full[rg.s], pol);
+      }
+      rg.advance();
+    }
+  }
+}
+
+struct MkAttnItem {
+  int active, kvh, split, s0, s1, tile;
+};
+template <typename T>
+__device__ __forceinline__ MkAttnItem mk_attn_item(const MkArgs &a, int pos) {
+  MkAttnItem it;
+  const int items = a.n_kv * a.nsplit;
+  it.active = (int)blockIdx.x < items;
+  it.kvh = blockIdx.x / a.nsplit;
+  it.split = blockIdx.x % a.nsplit;
+  const int Tn = pos + 1;
+  int per = (Tn + a.nsplit - 1) / a.nsplit;
+  per = (per + 7) & ~7;
+  it.s0 = min(Tn, it.split * per);
+  it.s1 = min(Tn, it.s0 + per);
+  const int rows = MK_STAGE_BYTES / (a.hd * (int)sizeof(T));
+  it.tile = rows < ATTN_TILE ? rows : ATTN_TILE;
+  if (!it.active) it.s0 = it.s1 = 0;
+  return it;
+}
+
+template <typename T>
+__device__ __forceinline__ void mk_produce_attn(MkRing &rg, const MkArgs &a, const MkLayer &L, int pos, uint64_t pol) {
+  const MkAttnItem it = mk_attn_item<T>(a, pos);
+  const int HD = a.hd;
+  const T *kc = reinterpret_cast<const T *>(L.kc) + (size_t)it.kvh * a.cap * HD;
+  const T *vc = reinterpret_cast<const T *>(L.vc) + (size_t)it.kvh * a.cap * HD;
+  for (int t0 = it.s0; t0 < it.s1; t0 += it.tile) {
+    const int t1 = min(it.s1, t0 + it.tile);
+    const int nold = min(t1, pos) - t0;  // rows already in the cache (the appended row is handled by the consumers)
+    for (int kv = 0; kv < 2; kv++) {
+      mbar_wait(&rg.empty[rg.s], rg.ph ^ 1u);
+      if (nold > 0) {
+        const uint32_t bytes = (uint32_t)nold * HD * sizeof(T);
+        mbar_arrive_expect_tx(&rg.full[rg.s], bytes);
+        bulk_g2s(rg.ring + (size_t)rg.s * MK_STAGE_BYTES, (kv ? vc : kc) + (size_t)t0 * HD, bytes, &rg.full[rg.s], pol);
+      } else {
+        mbar_arrive(&rg.full[rg.s]);
+      }
+      rg.advance();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------- consumers
+__device__ __forceinline__ void mk_grid_sync(unsigned long long *ctr, unsigned long long target, int ct) {
+  named_bar_sync(1, MK_CT);  // every consumer thread of this CTA has issued its global writes
+  if (ct == 0) {
+    __threadfence();
+    atomicAdd(ctr, 1ULL);
+    while (ld_acquire_u64(ctr) < target) {
+    }
+    __threadfence();
+  }
+  named_bar_sync(1, MK_CT);
+}
+
+// x -> shared (D), optionally RMS-normalised.  Activations were written by other SMs: ld.global.cg.
+template <typename T>
+__device__ __forceinline__ void mk_stage_x(T *xs, const void *x, const void *norm_w, int K, float eps, float *scratch,
+                                           int ct, int warp, int lane) {
+  constexpr int es = sizeof(T);
+  uint4 *xsv = reinterpret_cast<uint4 *>(xs);
+  const int nv = K * es / 16;
+  const char *xb = reinterpret_cast<const char *>(x);
+  if (norm_w == nullptr) {
+    for (int v = ct; v < nv; v += MK_CT) xsv[v] = ldcg_v4(xb + (size_t)v * 16);
+  } else {
+    float ss = 0.f;
+    for (int v = ct; v < nv; v += MK_CT) {
+      const uint4 u = ldcg_v4(xb + (size_t)v * 16);
+      xsv[v] = u;
+      float f[8];
+      unpack8<T>(u, f);
+#pragma unroll
+      for (int i = 0; i < 8; i++) ss += f[i] * f[i];
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) scratch[warp] = ss;
+    named_bar_sync(1, MK_CT);
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < MK_CW; w++) tot += scratch[w];
+    const float inv = 1.0f / sqrtf(tot / (float)K + eps);
+    const uint4 *wg = reinterpret_cast<const uint4 *>(norm_w);
+    for (int v = ct; v < nv; v += MK_CT) {
+      float f[8], w8[8];
+      unpack8<T>(xsv[v], f);
+      unpack8<T>(wg[v], w8);
+      uint4 o;
+      o.x = pack2<T>(f[0] * inv * w8[0], f[1] * inv * w8[1]);
+      o.y = pack2<T>(f[2] * inv * w8[2], f[3] * inv * w8[3]);
+      o.z = pack2<T>(f[4] * inv * w8[4], f[5] * inv * w8[5]);
+      o.w = pack2<T>(f[6] * inv * w8[6], f[7] * inv * w8[7]);
+      xsv[v] = o;
+    }
+  }
+  named_bar_sync(1, MK_CT);
+}
+
+struct MkEpi {
+  const void *bias, *residual;
+  void *out;
+  // argmax
+  float *part_val;
+  int *part_idx;
+  unsigned *counter;
+  uint32_t *token_out, *token_ring;
+  const int *step;
+  int ring_cap;
+  // end-of-step bookkeeping done by the argmax finaliser
+  int advance;
+  int *d_pos, *d_step;
+  unsigned long long *gbar;
+  unsigned long long epoch;
+};
+
+template <typename T, int EPI>
+__device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, const T *xs, float *partial, float *scratch,
+                                                const MkEpi &e, int ct, int warp, int lane) {
+  constexpr int G = (EPI == EPI_SWIGLU) ? 2 : 1;
+  int r0, r1;
+  mk_rows(g.N, G, r0, r1);
+  const int nrows = r1 - r0, RS = g.RS, WPR = g.WPR, RPW = g.RPW;
+  const int nchunk = g.K / g.KC;
+  const int slots = MK_CW / WPR, slot = warp / WPR, ks = warp % WPR;
+  const int segv = g.KC / 8, nvec = segv / WPR;
+  const uint4 *xsv = reinterpret_cast<const uint4 *>(xs);
+  for (int g0 = 0; g0 < nrows; g0 += RS) {
+    float acc[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; r++) acc[r][0] = acc[r][1] = 0.f;
+    for (int j = 0; j < nchunk; j++) {
+      mbar_wait(&rg.full[rg.s], rg.ph);
+      const uint4 *st = reinterpret_cast<const uint4 *>(rg.ring + (size_t)rg.s * MK_STAGE_BYTES);
+      const uint4 *xc = xsv + (size_t)j * segv + ks * nvec;
+#pragma unroll 2
+      for (int v = lane; v < nvec; v += 32) {
+        float xf[8];
+        unpack8<T>(xc[v], xf);
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          if (r < RPW) {
+            float wf[8];
+            unpack8<T>(st[(size_t)(slot + r * slots) * segv + ks * nvec + v], wf);
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[r][i & 1] = fmaf(wf[i], xf[i], acc[r][i & 1]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rg.empty[rg.s]);
+      rg.advance();
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (r < RPW) {
+        const float v = warp_sum(acc[r][0] + acc[r][1]);
+        const int rl = g0 + slot + r * slots;
+        if (lane == 0 && rl < nrows) partial[rl * WPR + ks] = v;
+      }
+    }
+  }
+  named_bar_sync(1, MK_CT);
+  auto row_sum = [&](int rl) {
+    float s = 0.f;
+    for (int w = 0; w < WPR; w++) s += partial[rl * WPR + w];
+    return rnd<T>(s);
+  };
+  T *out = reinterpret_cast<T *>(e.out);
+  if (EPI == EPI_PLAIN) {
+    const T *bias = reinterpret_cast<const T *>(e.bias);
+    for (int rl = ct; rl < nrows; rl += MK_CT) {
+      float v = row_sum(rl);
+      if (bias) v = rnd<T>(v + DT<T>::to_f(bias[r0 + rl]));
+      out[r0 + rl] = DT<T>::from_f(v);
+    }
+  } else if (EPI == EPI_RESIDUAL) {
+    const T *res = reinterpret_cast<const T *>(e.residual);
+    for (int rl = ct; rl < nrows; rl += MK_CT) {
+      const float v = row_sum(rl);
+      out[r0 + rl] = DT<T>::from_f(v + DT<T>::to_f(ldcg_T<T>(res + r0 + rl)));
+    }
+  } else if (EPI == EPI_SWIGLU) {
+    for (int p = ct; p < nrows / 2; p += MK_CT) {
+      const float gte = row_sum(2 * p), up = row_sum(2 * p + 1);
+      const float sl = rnd<T>(gte / (1.0f + expf(-gte)));
+      out[r0 / 2 + p] = DT<T>::from_f(sl * up);
+    }
+  } else {
+    float best = -INFINITY;
+    int bidx = 0x7fffffff;
+    for (int rl = ct; rl < nrows; rl += MK_CT) {
+      const float v = row_sum(rl);
+      if (out) out[r0 + rl] = DT<T>::from_f(v);
+      if (v > best) { best = v; bidx = r0 + rl; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bidx, o);
+      if (ov > best || (ov == best && oi < bidx)) { best = ov; bidx = oi; }
+    }
+    int *scratch_i = reinterpret_cast<int *>(scratch + 32);
+    if (lane == 0) { scratch[warp] = best; scratch_i[warp] = bidx; }
+    named_bar_sync(1, MK_CT);
+    if (ct == 0) {
+      for (int w = 1; w < MK_CW; w++)
+        if (scratch[w] > best || (scratch[w] == best && scratch_i[w] < bidx)) { best = scratch[w]; bidx = scratch_i[w]; }
+      e.part_val[blockIdx.x] = best;
+      e.part_idx[blockIdx.x] = bidx;
+      __threadfence();
+      const unsigned ticket = atomicAdd(e.counter, 1u);
+      if (ticket == gridDim.x - 1) {
+        __threadfence();
+        float bv = -INFINITY;
+        int bi = 0x7fffffff;
+        for (unsigned c = 0; c < gridDim.x; c++) {
+          const float v = __ldcg(e.part_val + c);
+          const int i = __ldcg(e.part_idx + c);
+          if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+        }
+        *e.token_out = (uint32_t)bi;
+        if (e.token_ring) e.token_ring[*e.step % e.ring_cap] = (uint32_t)bi;
+        *e.counter = 0;
+        // end-of-step bookkeeping: this is the last CTA of the grid to finish
+        if (e.advance) { *e.d_pos += 1; *e.d_step += 1; }
+        e.gbar[1] = e.epoch + 1;
+      }
+    }
+  }
+}
+
+// Attention phase for this CTA's (kv head, split) item.  Same math as attn_decode_kernel; K/V tiles come
+// from the ring (prefetched by the producer while the qkv GEMV was still running).
+template <typename T, int HD>
+__device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, const MkLayer &L, int pos, unsigned char *scr,
+                                                int ct, int warp, int lane) {
+  constexpr int LPR = HD / 8, RPW = 32 / LPR, NW = MK_CW;
+  constexpr int NPG = (HD < MK_CT) ? MK_CT / HD : 1;
+  constexpr int DPT = (HD > MK_CT) ? HD / MK_CT : 1;
+  const MkAttnItem it = mk_attn_item<T>(a, pos);
+  const int G = a.n_heads / a.n_kv;
+  float *q_s = reinterpret_cast<float *>(scr);             // [MAX_G][HD]
+  float *sc = q_s + ATTN_MAX_G * HD;                       // [MAX_G][ATTN_TILE]
+  float *pvred = sc + ATTN_MAX_G * ATTN_TILE;              // [NPG][MAX_G][HD]
+  __shared__ float m_run[ATTN_MAX_G], l_run[ATTN_MAX_G], fac[ATTN_MAX_G];
+  __shared__ float wgt[ATTN_MAX_G][ATTN_MAX_SPLIT];
+  __shared__ int is_last;
+  if (!it.active) return;  // CTA-uniform; inactive CTAs issue no stages either
+
+  const T *qkv = reinterpret_cast<const T *>(a.qkv);
+  const T *cosr = reinterpret_cast<const T *>(a.cos_t) + (size_t)pos * (a.rot / 2);
+  const T *sinr = reinterpret_cast<const T *>(a.sin_t) + (size_t)pos * (a.rot / 2);
+  T *kc = reinterpret_cast<T *>(L.kc) + (size_t)it.kvh * a.cap * HD;
+  T *vc = reinterpret_cast<T *>(L.vc) + (size_t)it.kvh * a.cap * HD;
+  const int kvh = it.kvh, split = it.split, s0 = it.s0, s1 = it.s1, TILE = it.tile;
+  const bool owner = (pos >= s0 && pos < s1);
+
+  // q for all G heads (qkv was written by other SMs: .cg loads through a staged copy)
+  for (int g = warp; g < G; g += NW) {
+    const T *src = qkv + (size_t)(kvh * G + g) * HD;
+    float *dst = q_s + g * HD;
+    for (int d = lane; d < HD; d += 32) dst[d] = DT<T>::to_f(ldcg_T<T>(src + d));
+    __syncwarp();
+    norm_rope_inplace<T, HD>(dst, reinterpret_cast<const T *>(L.qn), a.eps, cosr, sinr, a.rot, lane);
+  }
+  float *knew = pvred;  // free until the end of the phase
+  if (owner) {
+    if (warp == NW - 1) {
+      const T *src = qkv + (size_t)(a.n_heads + kvh) * HD;
+      for (int d = lane; d < HD; d += 32) knew[d] = DT<T>::to_f(ldcg_T<T>(src + d));
+      __syncwarp();
+      norm_rope_inplace<T, HD>(knew, reinterpret_cast<const T *>(L.kn), a.eps, cosr, sinr, a.rot, lane);
+      for (int d = lane; d < HD; d += 32) kc[(size_t)pos * HD + d] = DT<T>::from_f(knew[d]);
+    } else if (warp == NW - 2) {
+      const T *vsrc = qkv + (size_t)(a.n_heads + a.n_kv + kvh) * HD;
+      for (int d = lane; d < HD; d += 32) {
+        const T vv = ldcg_T<T>(vsrc + d);
+        vc[(size_t)pos * HD + d] = vv;
+        knew[HD + d] = DT<T>::to_f(vv);
+      }
+    }
+  }
+  if (ct < ATTN_MAX_G) { m_run[ct] = -INFINITY; l_run[ct] = 0.f; }
+  named_bar_sync(1, MK_CT);
+
+  const int grp = lane / LPR, gl = lane % LPR;
+  float qreg[ATTN_MAX_G][8];
+#pragma unroll
+  for (int g = 0; g < ATTN_MAX_G; g++)
+#pragma unroll
+    for (int i = 0; i < 8; i++) qreg[g][i] = (g < G) ? q_s[g * HD + gl * 8 + i] : 0.f;
+  const int pv_d = ct % HD, pv_g = ct / HD;
+  float acc[ATTN_MAX_G][DPT];
+#pragma unroll
+  for (int g = 0; g < ATTN_MAX_G; g++)
+#pragma unroll
+    for (int i = 0; i < DPT; i++) acc[g][i] = 0.f;
+
+  for (int t0 = s0; t0 < s1; t0 += TILE) {
+    const int tn = min(TILE, s1 - t0);
+    // K tile = current stage, V tile = the next one
+    const int sk = rg.s;
+    const uint32_t phk = rg.ph;
+    rg.advance();
+    const int sv = rg.s;
+    const uint32_t phv = rg.ph;
+    rg.advance();
+    T *Ks = reinterpret_cast<T *>(rg.ring + (size_t)sk * MK_STAGE_BYTES);
+    T *Vs = reinterpret_cast<T *>(rg.ring + (size_t)sv * MK_STAGE_BYTES);
+    mbar_wait(&rg.full[sk], phk);
+    mbar_wait(&rg.full[sv], phv);
+    if (owner && pos >= t0 && pos < t0 + tn) {  // drop the appended row into its slot of the staged tiles
+      const int slot = pos - t0;
+      for (int d = ct; d < HD; d += MK_CT) {
+        Ks[(size_t)slot * HD + d] = DT<T>::from_f(knew[d]);
+        Vs[(size_t)slot * HD + d] = DT<T>::from_f(knew[HD + d]);
+      }
+    }
+    named_bar_sync(1, MK_CT);
+    for (int pb = warp * RPW; pb < tn; pb += NW * RPW) {
+      const int p = pb + grp;
+      const bool valid = p < tn;
+      float kf[8];
+      uint4 kraw = make_uint4(0u, 0u, 0u, 0u);
+      if (valid) kraw = *reinterpret_cast<const uint4 *>(Ks + (size_t)p * HD + gl * 8);
+      unpack8<T>(kraw, kf);
+#pragma unroll
+      for (int g = 0; g < ATTN_MAX_G; g++) {
+        if (g < G) {
+          float s = 0.f;
+#pragma unroll
+          for (int i = 0; i < 8; i++) s = fmaf(qreg[g][i], kf[i], s);
+#pragma unroll
+          for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+          if (gl == 0 && valid) sc[g * ATTN_TILE + p] = s * a.scale;
+        }
+      }
+    }
+    named_bar_sync(1, MK_CT);
+    for (int g = warp; g < G; g += NW) {
+      float mx = -INFINITY;
+      for (int p = lane; p < tn; p += 32) mx = fmaxf(mx, sc[g * ATTN_TILE + p]);
+      mx = warp_max(mx);
+      const float m_new = fmaxf(m_run[g], mx);
+      float sum = 0.f;
+      for (int p = lane; p < tn; p += 32) {
+        const float ev = expf(sc[g * ATTN_TILE + p] - m_new);
+        sc[g * ATTN_TILE + p] = ev;
+        sum += ev;
+      }
+      sum = warp_sum(sum);
+      if (lane == 0) {
+        const float f = (m_run[g] == -INFINITY) ? 0.f : expf(m_run[g] - m_new);
+        fac[g] = f;
+        l_run[g] = l_run[g] * f + sum;
+        m_run[g] = m_new;
+      }
+    }
+    named_bar_sync(1, MK_CT);
+#pragma unroll
+    for (int g = 0; g < ATTN_MAX_G; g++)
+      if (g < G) {
+        const float f = fac[g];
+#pragma unroll
+        for (int i = 0; i < DPT; i++) acc[g][i] *= f;
+      }
+#pragma unroll 4
+    for (int p = pv_g; p < tn; p += NPG) {
+      float vf[DPT];
+#pragma unroll
+      for (int i = 0; i < DPT; i++) vf[i] = DT<T>::to_f(Vs[(size_t)p * HD + pv_d + i * MK_CT]);
+#pragma unroll
+      for (int g = 0; g < ATTN_MAX_G; g++)
+        if (g < G) {
+          const float ev = sc[g * ATTN_TILE + p];
+#pragma unroll
+          for (int i = 0; i < DPT; i++) acc[g][i] = fmaf(ev, vf[i], acc[g][i]);
+        }
+    }
+    __syncwarp();
+    if (lane == 0) { mbar_arrive(&rg.empty[sk]); mbar_arrive(&rg.empty[sv]); }
+    named_bar_sync(1, MK_CT);
+  }
+
+  if (NPG > 1) {
+#pragma unroll
+    for (int g = 0; g < ATTN_MAX_G; g++)
+      if (g < G) pvred[((size_t)pv_g * ATTN_MAX_G + g) * HD + pv_d] = acc[g][0];
+    named_bar_sync(1, MK_CT);
+    for (int i = ct; i < G * HD; i += MK_CT) {
+      const int g = i / HD, d = i % HD;
+      float s = 0.f;
+      for (int r = 0; r < NPG; r++) s += pvred[((size_t)r * ATTN_MAX_G + g) * HD + d];
+      a.ws_acc[((size_t)(kvh * G + g) * a.nsplit + split) * HD + d] = s;
+    }
+  } else {
+#pragma unroll
+    for (int g = 0; g < ATTN_MAX_G; g++)
+      if (g < G) {
+#pragma unroll
+        for (int i = 0; i < DPT; i++) a.ws_acc[((size_t)(kvh * G + g) * a.nsplit + split) * HD + pv_d + i * MK_CT] = acc[g][i];
+      }
+  }
+  if (ct < G) {
+    a.ws_ml[((size_t)(kvh * G + ct) * a.nsplit + split) * 2 + 0] = m_run[ct];
+    a.ws_ml[((size_t)(kvh * G + ct) * a.nsplit + split) * 2 + 1] = l_run[ct];
+  }
+  __threadfence();
+  named_bar_sync(1, MK_CT);
+  if (ct == 0) {
+    const unsigned ticket = atomicAdd(&a.attn_counters[kvh], 1u);
+    is_last = (ticket == (unsigned)a.nsplit - 1);
+  }
+  named_bar_sync(1, MK_CT);
+  if (!is_last) return;
+  __threadfence();
+  for (int g = warp; g < G; g += NW) {
+    const int h = kvh * G + g;
+    float m = -INFINITY, l = 0.f;
+    if (lane < a.nsplit) {
+      m = __ldcg(a.ws_ml + ((size_t)h * a.nsplit + lane) * 2);
+      l = __ldcg(a.ws_ml + ((size_t)h * a.nsplit + lane) * 2 + 1);
+    }
+    const float M = warp_max(m);
+    const float w = (m == -INFINITY) ? 0.f : expf(m - M);
+    const float Lsum = warp_sum(w * l);
+    wgt[g][lane] = w / Lsum;
+  }
+  named_bar_sync(1, MK_CT);
+  T *y = reinterpret_cast<T *>(a.y);
+  for (int i = ct; i < G * HD; i += MK_CT) {
+    const int g = i / HD, d = i % HD, h = kvh * G + g;
+    const float *src = a.ws_acc + (size_t)h * a.nsplit * HD + d;
+    float o = 0.f;
+#pragma unroll 8
+    for (int s = 0; s < a.nsplit; s++) o = fmaf(wgt[g][s], __ldcg(src + (size_t)s * HD), o);
+    y[(size_t)h * HD + d] = DT<T>::from_f(o);
+  }
+  if (ct == 0) a.attn_counters[kvh] = 0;
+}
+
+// ---------------------------------------------------------------------------------------- the kernel
+template <typename T, int HD>
+__global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr int es = sizeof(T);
+  unsigned char *ring = smem_raw;
+  T *xs = reinterpret_cast<T *>(ring + (size_t)a.n_stages * MK_STAGE_BYTES);
+  size_t off = (size_t)a.n_stages * MK_STAGE_BYTES + mk_xs_bytes(a.max_k, es);
+  off = (off + 15) & ~(size_t)15;
+  float *partial = reinterpret_cast<float *>(smem_raw + off);
+  off += (size_t)a.partial_floats * 4;  // sized by the host: max rows x slices over all GEMV types
+  float *scratch = reinterpret_cast<float *>(smem_raw + off);
+  off += 128 * 4;
+  off = (off + 7) & ~(size_t)7;
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + off);
+  uint64_t *empty = full + MK_MAX_STAGES;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.n_stages; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], MK_CW);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int pos = *a.d_pos;
+  MkRing rg{ring, full, empty, a.n_stages, 0, 0u};
+
+  if (warp == MK_CW) {
+    // ================= producer: stream weights and K/V tiles through the whole phase list ==========
+    if (lane == 0) {
+      const uint64_t pol_w = policy_evict_first(), pol_kv = policy_evict_last();
+      for (int l = 0; l < a.n_layers; l++) {
+        const MkLayer L = a.layers[l];
+        mk_produce_gemv<T>(rg, a.g_qkv, L.wqkv, 1, pol_w);
+        mk_produce_attn<T>(rg, a, L, pos, pol_kv);
+        mk_produce_gemv<T>(rg, a.g_o, L.wo, 1, pol_w);
+        mk_produce_gemv<T>(rg, a.g_gu, L.wgu, 2, pol_w);
+        mk_produce_gemv<T>(rg, a.g_down, L.wd, 1, pol_w);
+      }
+      if (a.has_head) mk_produce_gemv<T>(rg, a.g_head, a.lm_head, 1, pol_w);
+    }
+    return;
+  }
+
+  // ================= consumers ========================================================================
+  const int ct = threadIdx.x;
+  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(a.gbar + 1);
+  const unsigned long long base = epoch * (unsigned long long)MK_BARS_PER_LAUNCH * gridDim.x;
+  unsigned nbar = 0;
+  auto gsync = [&]() {
+    nbar++;
+    mk_grid_sync(a.gbar, base + (unsigned long long)nbar * gridDim.x, ct);
+  };
+  const T *cur = reinterpret_cast<const T *>(a.x_in);
+  if (cur == nullptr) {  // master: the block input is the embedding row of the current token (text_model.rs:271)
+    uint32_t tok = *a.d_token;
+    if (tok >= (uint32_t)a.vocab) tok = 0;
+    cur = reinterpret_cast<const T *>(a.embed) + (size_t)tok * a.hidden;
+  }
+  MkEpi e{};
+  for (int l = 0; l < a.n_layers; l++) {
+    const MkLayer L = a.layers[l];
+    T *dst = reinterpret_cast<T *>((l == a.n_layers - 1) ? a.x_out : a.xa);
+    // rms_1 + qkv (+bias)
+    mk_stage_x<T>(xs, cur, L.ln1, a.hidden, a.eps, scratch, ct, warp, lane);
+    e = MkEpi{};
+    e.bias = L.bqkv;
+    e.out = a.qkv;
+    mk_consume_gemv<T, EPI_PLAIN>(rg, a.g_qkv, xs, partial, scratch, e, ct, warp, lane);
+    gsync();
+    // qk-norm, RoPE, KV append, attention
+    mk_consume_attn<T, HD>(rg, a, L, pos, reinterpret_cast<unsigned char *>(xs), ct, warp, lane);
+    gsync();
+    // o_proj + residual
+    mk_stage_x<T>(xs, a.y, nullptr, a.n_heads * a.hd, a.eps, scratch, ct, warp, lane);
+    e = MkEpi{};
+    e.residual = cur;
+    e.out = a.xb;
+    mk_consume_gemv<T, EPI_RESIDUAL>(rg, a.g_o, xs, partial, scratch, e, ct, warp, lane);
+    gsync();
+    // rms_2 + gate_up + silu*mul
+    mk_stage_x<T>(xs, a.xb, L.ln2, a.hidden, a.eps, scratch, ct, warp, lane);
+    e = MkEpi{};
+    e.out = a.mm;
+    mk_consume_gemv<T, EPI_SWIGLU>(rg, a.g_gu, xs, partial, scratch, e, ct, warp, lane);
+    gsync();
+    // down + residual
+    mk_stage_x<T>(xs, a.mm, nullptr, a.inter, a.eps, scratch, ct, warp, lane);
+    e = MkEpi{};
+    e.residual = a.xb;
+    e.out = dst;
+    mk_consume_gemv<T, EPI_RESIDUAL>(rg, a.g_down, xs, partial, scratch, e, ct, warp, lane);
+    if (l < a.n_layers - 1 || a.has_head) gsync();
+    cur = dst;
+  }
+  if (a.has_head) {
+    mk_stage_x<T>(xs, cur, a.ln_f, a.hidden, a.eps, scratch, ct, warp, lane);
+    e = MkEpi{};
+    e.out = a.logits;
+    e.part_val = a.part_val;
+    e.part_idx = a.part_idx;
+    e.counter = a.argmax_counter;
+    e.token_out = a.token_out;
+    e.token_ring = a.token_ring;
+    e.step = a.d_step;
+    e.ring_cap = a.ring_cap;
+    e.advance = a.advance;
+    e.d_pos = a.d_pos;
+    e.d_step = a.d_step;
+    e.gbar = a.gbar;
+    e.epoch = epoch;
+    mk_consume_gemv<T, EPI_ARGMAX>(rg, a.g_head, xs, partial, scratch, e, ct, warp, lane);
+  }
+  // bookkeeping without a head: CTA 0 only gets here after passing barriers that every CTA arrived at,
+  // and every CTA read *d_pos and the epoch before its first barrier.
+  if (!a.has_head && blockIdx.x == 0 && ct == 0) {
+    if (a.advance) { *a.d_pos += 1; *a.d_step += 1; }
+    a.gbar[1] = epoch + 1;
+  }
+}
+
+}  // namespace cake

@@ -274,3 +274,42 @@ def test_repeat_penalty_matches_oracle():
     assert np.array_equal(to_np(d), ref)
     assert out.value == O.argmax(ref)
     ctx.close()
+
+
+def test_megakernel_equals_per_op_kernels(monkeypatch):
+    """The persistent decode megakernel (decode_mega.cuh) and the per-op kernel chain (gemv.cuh +
+    attn_decode.cuh, CAKE_B200_PER_OP=1) implement the same arithmetic with the same rounding points; only
+    the fp32 summation order inside a dot product differs (16 vs 8 consumer warps slice K differently), so
+    outputs agree to <= 2 ulp of D and greedy tokens (peaked head) are identical."""
+    from cake_b200.model import B200Transformer, TextModelBase
+    cfg = medium_config()
+    sd = checkpoint(cfg, "bf16", seed=17, peaked=True)
+    x = rand_x((1, 40, cfg.hidden_size), "bf16", seed=3)
+    prompt = np.random.default_rng(5).integers(0, cfg.vocab_size, 11).tolist()
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("CAKE_B200_PER_OP", mode)
+        ctx = _ctx(cfg, sd, "bf16")
+        blks = [B200Transformer.load(cfg.layer_name(i), ctx) for i in range(3)]
+        batch = [(b.layer_name(), 0, i) for i, b in enumerate(blks)]
+        blks[0].forward_batch(ctx.to_device(x[:, :33]), batch, ctx, blocks=blks)
+        outs = []
+        for t in range(33, 40):
+            y = blks[0].forward_batch(ctx.to_device(x[:, t:t + 1]), [(n, t, i) for n, _, i in batch], ctx, blocks=blks)
+            ctx.sync()
+            outs.append(y.cpu())
+        k, v = ctx.cache.kv(2)
+        del blks
+        ctx.cache.clear()
+        model = TextModelBase.load(ctx)
+        model.prepare_prompt(prompt)
+        t0 = model.next_token(0).id
+        model.decode_build()
+        toks = [t0] + model.decode_greedy(t0, 8)
+        res[mode] = (outs, k, v, toks)
+        ctx.close()
+    for a, b in zip(res["0"][0], res["1"][0]):
+        assert max_ulp_err(to_np(a), to_np(b), "bf16") <= 2.0
+    assert max_ulp_err(to_np(res["0"][1]), to_np(res["1"][1]), "bf16") <= 2.0
+    assert max_ulp_err(to_np(res["0"][2]), to_np(res["1"][2]), "bf16") <= 2.0
+    assert res["0"][3] == res["1"][3]
