@@ -134,6 +134,7 @@ constexpr int TOKEN_RING = 1 << 16;
 struct cake_b200_block {
   cake_b200_ctx *ctx;
   int layer;
+  int device = 0;  // copied so that block_free never dereferences a ctx that was destroyed first
   void *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wd = nullptr, *ln1 = nullptr, *ln2 = nullptr;
   void *bqkv = nullptr, *qn = nullptr, *kn = nullptr;
 };
@@ -141,6 +142,7 @@ struct cake_b200_block {
 struct cake_b200_cache {
   cake_b200_ctx *ctx;
   int batch, cap;
+  int device = 0;
   std::vector<void *> k, v;
   std::vector<int> len;
   int *d_pos = nullptr;
@@ -415,7 +417,7 @@ extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void 
   CU(cudaSetDevice(c->device));
   const size_t es = c->es, H = c->cfg.hidden, I = c->cfg.inter, hd = c->cfg.head_dim;
   const size_t sq = (size_t)c->cfg.n_heads * hd, skv = (size_t)c->cfg.n_kv_heads * hd;
-  auto *b = new cake_b200_block{c, layer_idx};
+  auto *b = new cake_b200_block{c, layer_idx, c->device};
   // attention.rs:109-113: Wqkv = cat([q,k,v], 0)
   CU(cudaMalloc(&b->wqkv, (sq + 2 * skv) * H * es + 16));
   CU(cudaMemcpy(b->wqkv, q, sq * H * es, cudaMemcpyDefault));
@@ -445,10 +447,11 @@ extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void 
 }
 extern "C" void cake_b200_block_free(cake_b200_block *b) {
   if (!b) return;
-  cudaSetDevice(b->ctx->device);
+  cudaSetDevice(b->device);
   void *bufs[] = {b->wqkv, b->wo, b->wgu, b->wd, b->ln1, b->ln2, b->bqkv, b->qn, b->kn};
   for (void *p : bufs)
-    if (p) cudaFree(p);
+    if (p) cudaFree(p);  // cudaFree synchronises with outstanding work
+  (void)cudaGetLastError();
   delete b;
 }
 extern "C" int cake_b200_block_layer(const cake_b200_block *b) { return b->layer; }
@@ -458,7 +461,7 @@ extern "C" int cake_b200_cache_create(cake_b200_ctx *c, int batch, int max_seq, 
   if (!c || !out || batch < 1 || max_seq < 1) return fail(CAKE_B200_EINVAL, "bad cache arguments");
   if (max_seq > c->cfg.max_seq) return fail(CAKE_B200_EINVAL, "cache max_seq %d exceeds config max_seq %d (RoPE table rows)", max_seq, c->cfg.max_seq);
   CU(cudaSetDevice(c->device));
-  auto *k = new cake_b200_cache{c, batch, max_seq};
+  auto *k = new cake_b200_cache{c, batch, max_seq, c->device};
   k->k.assign(c->cfg.n_layers, nullptr);
   k->v.assign(c->cfg.n_layers, nullptr);
   k->len.assign(c->cfg.n_layers, 0);
@@ -481,13 +484,13 @@ extern "C" int cake_b200_cache_clear(cake_b200_cache *k) {
 }
 extern "C" void cake_b200_cache_free(cake_b200_cache *k) {
   if (!k) return;
-  cudaSetDevice(k->ctx->device);
-  cudaStreamSynchronize(k->ctx->stream);
+  cudaSetDevice(k->device);
   for (void *p : k->k)
     if (p) cudaFree(p);
   for (void *p : k->v)
     if (p) cudaFree(p);
   cudaFree(k->d_pos);
+  (void)cudaGetLastError();
   delete k;
 }
 extern "C" int cake_b200_cache_len(const cake_b200_cache *k, int block_idx) {

@@ -29,7 +29,6 @@ constexpr int MK_THREADS = (MK_CW + 1) * 32;    // + producer warp
 constexpr int MK_STAGE_BYTES = 32768;
 constexpr int MK_MAX_STAGES = 6;
 constexpr int MK_MAX_LAYERS = 96;
-constexpr int MK_BARS_PER_LAUNCH = 1024;        // upper bound of grid barriers in one launch
 
 struct MkLayer {
   const void *wqkv, *wo, *wgu, *wd, *ln1, *ln2, *bqkv, *qn, *kn;
@@ -53,7 +52,7 @@ struct MkArgs {
   unsigned *attn_counters;
   const void *cos_t, *sin_t;
   int *d_pos, *d_step;
-  unsigned long long *gbar;      // [0] barrier counter, [1] launch epoch
+  unsigned long long *gbar;      // [0] monotonic barrier arrival counter, [1] its value at launch start
   int has_head, advance, n_stages, vocab, partial_floats;
   const void *ln_f, *lm_head;
   void *logits;
@@ -245,7 +244,7 @@ struct MkEpi {
   int advance;
   int *d_pos, *d_step;
   unsigned long long *gbar;
-  unsigned long long epoch;
+  unsigned long long next_start;
 };
 
 template <typename T, int EPI>
@@ -358,7 +357,7 @@ __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, con
         *e.counter = 0;
         // end-of-step bookkeeping: this is the last CTA of the grid to finish
         if (e.advance) { *e.d_pos += 1; *e.d_step += 1; }
-        e.gbar[1] = e.epoch + 1;
+        e.gbar[1] = e.next_start;
       }
     }
   }
@@ -622,12 +621,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
 
   // ================= consumers ========================================================================
   const int ct = threadIdx.x;
-  const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(a.gbar + 1);
-  const unsigned long long base = epoch * (unsigned long long)MK_BARS_PER_LAUNCH * gridDim.x;
+  // gbar[0] is a monotonic arrival counter; gbar[1] holds its value at the start of this launch (written
+  // by the previous launch's last thread), so barrier k of this launch completes at start + k*grid.
+  const unsigned long long start = *reinterpret_cast<volatile unsigned long long *>(a.gbar + 1);
   unsigned nbar = 0;
   auto gsync = [&]() {
     nbar++;
-    mk_grid_sync(a.gbar, base + (unsigned long long)nbar * gridDim.x, ct);
+    mk_grid_sync(a.gbar, start + (unsigned long long)nbar * gridDim.x, ct);
   };
   const T *cur = reinterpret_cast<const T *>(a.x_in);
   if (cur == nullptr) {  // master: the block input is the embedding row of the current token (text_model.rs:271)
@@ -686,14 +686,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     e.d_pos = a.d_pos;
     e.d_step = a.d_step;
     e.gbar = a.gbar;
-    e.epoch = epoch;
+    e.next_start = start + (unsigned long long)nbar * gridDim.x;
     mk_consume_gemv<T, EPI_ARGMAX>(rg, a.g_head, xs, partial, scratch, e, ct, warp, lane);
   }
   // bookkeeping without a head: CTA 0 only gets here after passing barriers that every CTA arrived at,
   // and every CTA read *d_pos and the epoch before its first barrier.
   if (!a.has_head && blockIdx.x == 0 && ct == 0) {
     if (a.advance) { *a.d_pos += 1; *a.d_step += 1; }
-    a.gbar[1] = epoch + 1;
+    a.gbar[1] = start + (unsigned long long)nbar * gridDim.x;
   }
 }
 

@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes
 import time
+import weakref
 from abc import ABC, abstractmethod
 from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
@@ -38,6 +39,12 @@ class Cache:
         self.max_seq = max_seq or ctx.max_seq
         self.h = c_void_p()
         check(lib().cake_b200_cache_create(ctx.h, batch, self.max_seq, byref(self.h)))
+        ctx._children.append(weakref.ref(self))
+
+    def close(self):
+        if self.h:
+            lib().cake_b200_cache_free(self.h)
+            self.h = None
 
     def clear(self) -> None:  # cache.rs:247-253
         check(lib().cake_b200_cache_clear(self.h))
@@ -67,9 +74,7 @@ class Cache:
 
     def __del__(self):
         try:
-            if self.h:
-                lib().cake_b200_cache_free(self.h)
-                self.h = None
+            self.close()
         except Exception:
             pass
 
@@ -86,6 +91,7 @@ class Context:
         self.topology = topology or {}
         self.ccfg = CConfig.from_config(config, dtype, self.max_seq)
         self.h = c_void_p()
+        self._children = []  # weakrefs to caches / blocks: freed before the ctx (they point into it)
         torch.cuda.set_device(device)
         check(lib().cake_b200_ctx_create(device, byref(self.ccfg), byref(self.h)))
         self.cache: Optional[Cache] = Cache(self)
@@ -117,6 +123,12 @@ class Context:
 
     def close(self):
         if self.h:
+            self.sync()
+            for ref in self._children:
+                obj = ref()
+                if obj is not None:
+                    obj.close()
+            self._children = []
             self.cache = None
             lib().cake_b200_ctx_destroy(self.h)
             self.h = None
@@ -157,7 +169,13 @@ class B200Transformer(Forwarder):
     backed by a cake_b200_block handle."""
 
     def __init__(self, name: str, handle: c_void_p, ctx: Context):
-        self.name, self.h, self._ctx = name, handle, ctx
+        self.name, self.h = name, handle
+        ctx._children.append(weakref.ref(self))
+
+    def close(self):
+        if self.h:
+            lib().cake_b200_block_free(self.h)
+            self.h = None
 
     @classmethod
     def load(cls, name: str, ctx: Context) -> "B200Transformer":
@@ -223,9 +241,7 @@ class B200Transformer(Forwarder):
 
     def __del__(self):
         try:
-            if self.h:
-                lib().cake_b200_block_free(self.h)
-                self.h = None
+            self.close()
         except Exception:
             pass
 
