@@ -128,6 +128,7 @@ struct cake_b200_ctx {
   unsigned long long *gbar = nullptr;   // [0] grid-barrier counter, [1] launch epoch
   MkLayer *mk_tab_dev = nullptr, *mk_tab_host = nullptr, *g_tab_dev = nullptr;
   std::vector<const void *> mk_sig;
+  unsigned long long *trace = nullptr;  // CAKE_B200_MEGA_TRACE=1
 };
 constexpr int TOKEN_RING = 1 << 16;
 
@@ -364,6 +365,11 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
   {
     const char *e = getenv("CAKE_B200_PER_OP");
     c->use_mega = !(e && e[0] == '1');
+    const char *t = getenv("CAKE_B200_MEGA_TRACE");
+    if (t && t[0] == '1') {
+      CU(cudaMalloc(&c->trace, 8 * 4096));
+      CU(cudaMemset(c->trace, 0, 8 * 4096));
+    }
   }
   *out = c;
   return CAKE_B200_OK;
@@ -647,6 +653,7 @@ static int plan_mega(cake_b200_ctx *c, cake_b200_cache *kc, bool with_head, MkPl
   a.vocab = f.vocab; a.embed = c->embed; a.d_token = c->d_token;
   a.ln_f = c->ln_f; a.lm_head = c->lm_head; a.logits = c->logits; a.part_val = c->part_val; a.part_idx = c->part_idx;
   a.argmax_counter = c->argmax_counter; a.token_out = c->d_token; a.token_ring = nullptr; a.ring_cap = TOKEN_RING;
+  a.trace = c->trace;
   int ns = MK_MAX_STAGES;
   const size_t limit = 227 * 1024 - 2048;
   while (ns > 2 && mk_smem_bytes(a.max_k, pf, ns, c->es) > limit) ns--;
@@ -1157,5 +1164,15 @@ extern "C" int cake_b200_bench_kernel(cake_b200_ctx *c, cake_b200_block *const *
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *ms_per_launch = ms / (float)(reps * n_blocks);
+  return CAKE_B200_OK;
+}
+
+/* profiling aid (not in the public header): copies the megakernel's phase-boundary %globaltimer stamps of
+ * the last launch (CTA 0) to `out`; needs CAKE_B200_MEGA_TRACE=1 at ctx creation. */
+extern "C" int cake_b200_debug_trace(cake_b200_ctx *c, unsigned long long *out, int n) {
+  if (!c || !c->trace || n > 4096) return fail(CAKE_B200_ESTATE, "tracing is off (CAKE_B200_MEGA_TRACE=1)");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaMemcpy(out, c->trace, (size_t)n * 8, cudaMemcpyDeviceToHost));
   return CAKE_B200_OK;
 }

@@ -61,6 +61,7 @@ struct MkArgs {
   unsigned *argmax_counter;
   uint32_t *token_out, *token_ring;
   int ring_cap;
+  unsigned long long *trace;  // optional: %globaltimer stamps of CTA 0 at phase boundaries (profiling aid)
 };
 
 __host__ __device__ inline size_t mk_xs_bytes(int max_k, int es) {
@@ -178,13 +179,12 @@ __device__ __forceinline__ void mk_produce_attn(MkRing &rg, const MkArgs &a, con
 __device__ __forceinline__ void mk_grid_sync(unsigned long long *ctr, unsigned long long target, int ct) {
   named_bar_sync(1, MK_CT);  // every consumer thread of this CTA has issued its global writes
   if (ct == 0) {
-    __threadfence();
-    atomicAdd(ctr, 1ULL);
+    // release: publishes this CTA's writes (ordered before us by the bar.sync above); fire-and-forget
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(ctr), "l"(1ULL) : "memory");
     while (ld_acquire_u64(ctr) < target) {
     }
-    __threadfence();
   }
-  named_bar_sync(1, MK_CT);
+  named_bar_sync(1, MK_CT);  // data written by other SMs is read with ld.global.cg below (L1 is bypassed)
 }
 
 // x -> shared (D), optionally RMS-normalised.  Activations were written by other SMs: ld.global.cg.
@@ -258,6 +258,48 @@ __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, con
   const int slots = MK_CW / WPR, slot = warp / WPR, ks = warp % WPR;
   const int segv = g.KC / 8, nvec = segv / WPR;
   const uint4 *xsv = reinterpret_cast<const uint4 *>(xs);
+  if (nchunk == 1 && nvec <= 128) {
+    // Fast path (all Llama/Qwen shapes): a lane's columns are the same for every row of the phase, so its
+    // x slice is converted to fp32 ONCE into registers; per 16-byte weight vector the loop is then
+    // 1 LDS.128 + 8 converts + 8 FMA (ncu r01: re-reading/converting x per vector made the loop issue-bound).
+    float xr[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int v = lane + 32 * i;
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (v < nvec) u = xsv[ks * nvec + v];
+      unpack8<T>(u, xr[i]);
+    }
+    const bool v3 = lane + 96 < nvec, v2 = lane + 64 < nvec, v1 = lane + 32 < nvec, v0 = lane < nvec;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    for (int g0 = 0; g0 < nrows; g0 += RS) {
+      mbar_wait(&rg.full[rg.s], rg.ph);
+      const uint4 *st = reinterpret_cast<const uint4 *>(rg.ring + (size_t)rg.s * MK_STAGE_BYTES) + ks * nvec + lane;
+      for (int r = 0; r < RPW; r++) {
+        const uint4 *rowp = st + (size_t)(slot + r * slots) * segv;
+        const uint4 w0 = v0 ? rowp[0] : z, w1 = v1 ? rowp[32] : z, w2 = v2 ? rowp[64] : z, w3 = v3 ? rowp[96] : z;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, wf[8];
+        unpack8<T>(w0, wf);
+        a0 = fmaf(wf[0], xr[0][0], a0); a1 = fmaf(wf[1], xr[0][1], a1); a2 = fmaf(wf[2], xr[0][2], a2); a3 = fmaf(wf[3], xr[0][3], a3);
+        a0 = fmaf(wf[4], xr[0][4], a0); a1 = fmaf(wf[5], xr[0][5], a1); a2 = fmaf(wf[6], xr[0][6], a2); a3 = fmaf(wf[7], xr[0][7], a3);
+        unpack8<T>(w1, wf);
+        a0 = fmaf(wf[0], xr[1][0], a0); a1 = fmaf(wf[1], xr[1][1], a1); a2 = fmaf(wf[2], xr[1][2], a2); a3 = fmaf(wf[3], xr[1][3], a3);
+        a0 = fmaf(wf[4], xr[1][4], a0); a1 = fmaf(wf[5], xr[1][5], a1); a2 = fmaf(wf[6], xr[1][6], a2); a3 = fmaf(wf[7], xr[1][7], a3);
+        unpack8<T>(w2, wf);
+        a0 = fmaf(wf[0], xr[2][0], a0); a1 = fmaf(wf[1], xr[2][1], a1); a2 = fmaf(wf[2], xr[2][2], a2); a3 = fmaf(wf[3], xr[2][3], a3);
+        a0 = fmaf(wf[4], xr[2][4], a0); a1 = fmaf(wf[5], xr[2][5], a1); a2 = fmaf(wf[6], xr[2][6], a2); a3 = fmaf(wf[7], xr[2][7], a3);
+        unpack8<T>(w3, wf);
+        a0 = fmaf(wf[0], xr[3][0], a0); a1 = fmaf(wf[1], xr[3][1], a1); a2 = fmaf(wf[2], xr[3][2], a2); a3 = fmaf(wf[3], xr[3][3], a3);
+        a0 = fmaf(wf[4], xr[3][4], a0); a1 = fmaf(wf[5], xr[3][5], a1); a2 = fmaf(wf[6], xr[3][6], a2); a3 = fmaf(wf[7], xr[3][7], a3);
+        const float v = warp_sum((a0 + a1) + (a2 + a3));
+        const int rl = g0 + slot + r * slots;
+        if (lane == 0 && rl < nrows) partial[rl * WPR + ks] = v;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&rg.empty[rg.s]);
+      rg.advance();
+    }
+  } else
   for (int g0 = 0; g0 < nrows; g0 += RS) {
     float acc[4][2];
 #pragma unroll
@@ -367,7 +409,15 @@ __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, con
 // from the ring (prefetched by the producer while the qkv GEMV was still running).
 template <typename T, int HD>
 __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, const MkLayer &L, int pos, unsigned char *scr,
-                                                int ct, int warp, int lane) {
+                                                int ct, int warp, int lane, unsigned long long *tr) {
+  auto stamp = [&](int i) {
+    if (tr && ct == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      tr[i] = t;
+    }
+  };
+  stamp(0);
   constexpr int LPR = HD / 8, RPW = 32 / LPR, NW = MK_CW;
   constexpr int NPG = (HD < MK_CT) ? MK_CT / HD : 1;
   constexpr int DPT = (HD > MK_CT) ? HD / MK_CT : 1;
@@ -416,6 +466,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
   }
   if (ct < ATTN_MAX_G) { m_run[ct] = -INFINITY; l_run[ct] = 0.f; }
   named_bar_sync(1, MK_CT);
+  stamp(1);
 
   const int grp = lane / LPR, gl = lane % LPR;
   float qreg[ATTN_MAX_G][8];
@@ -443,6 +494,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     T *Vs = reinterpret_cast<T *>(rg.ring + (size_t)sv * MK_STAGE_BYTES);
     mbar_wait(&rg.full[sk], phk);
     mbar_wait(&rg.full[sv], phv);
+    stamp(2);
     if (owner && pos >= t0 && pos < t0 + tn) {  // drop the appended row into its slot of the staged tiles
       const int slot = pos - t0;
       for (int d = ct; d < HD; d += MK_CT) {
@@ -471,6 +523,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
       }
     }
     named_bar_sync(1, MK_CT);
+    stamp(3);
     for (int g = warp; g < G; g += NW) {
       float mx = -INFINITY;
       for (int p = lane; p < tn; p += 32) mx = fmaxf(mx, sc[g * ATTN_TILE + p]);
@@ -491,6 +544,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
       }
     }
     named_bar_sync(1, MK_CT);
+    stamp(4);
 #pragma unroll
     for (int g = 0; g < ATTN_MAX_G; g++)
       if (g < G) {
@@ -514,6 +568,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     __syncwarp();
     if (lane == 0) { mbar_arrive(&rg.empty[sk]); mbar_arrive(&rg.empty[sv]); }
     named_bar_sync(1, MK_CT);
+    stamp(5);
   }
 
   if (NPG > 1) {
@@ -539,6 +594,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     a.ws_ml[((size_t)(kvh * G + ct) * a.nsplit + split) * 2 + 0] = m_run[ct];
     a.ws_ml[((size_t)(kvh * G + ct) * a.nsplit + split) * 2 + 1] = l_run[ct];
   }
+  stamp(6);
   __threadfence();
   named_bar_sync(1, MK_CT);
   if (ct == 0) {
@@ -546,6 +602,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     is_last = (ticket == (unsigned)a.nsplit - 1);
   }
   named_bar_sync(1, MK_CT);
+  stamp(7);
   if (!is_last) return;
   __threadfence();
   for (int g = warp; g < G; g += NW) {
@@ -625,10 +682,21 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
   // by the previous launch's last thread), so barrier k of this launch completes at start + k*grid.
   const unsigned long long start = *reinterpret_cast<volatile unsigned long long *>(a.gbar + 1);
   unsigned nbar = 0;
+  int ntrace = 0;
+  auto stamp = [&]() {
+    if (a.trace && blockIdx.x == 0 && ct == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.trace[ntrace++] = t;
+    }
+  };
   auto gsync = [&]() {
     nbar++;
+    stamp();
     mk_grid_sync(a.gbar, start + (unsigned long long)nbar * gridDim.x, ct);
+    stamp();
   };
+  stamp();
   const T *cur = reinterpret_cast<const T *>(a.x_in);
   if (cur == nullptr) {  // master: the block input is the embedding row of the current token (text_model.rs:271)
     uint32_t tok = *a.d_token;
@@ -647,7 +715,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     mk_consume_gemv<T, EPI_PLAIN>(rg, a.g_qkv, xs, partial, scratch, e, ct, warp, lane);
     gsync();
     // qk-norm, RoPE, KV append, attention
-    mk_consume_attn<T, HD>(rg, a, L, pos, reinterpret_cast<unsigned char *>(xs), ct, warp, lane);
+    mk_consume_attn<T, HD>(rg, a, L, pos, reinterpret_cast<unsigned char *>(xs), ct, warp, lane,
+                           (a.trace && blockIdx.x == 0 && l == 1) ? a.trace + 2048 : nullptr);
     gsync();
     // o_proj + residual
     mk_stage_x<T>(xs, a.y, nullptr, a.n_heads * a.hd, a.eps, scratch, ct, warp, lane);
