@@ -87,12 +87,45 @@ def init_comm(ctx: Context, rank: int, world: int) -> None:
     check(lib().cake_b200_comm_init(ctx.h, ptr(uid), rank, world))
 
 
+class NcclTransport:
+    """Activation hand-off through the library's communicator: in-stream ncclSend/ncclRecv, no host copy."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def empty_like(self, x):
+        with torch.cuda.stream(self.ctx.torch_stream):
+            return torch.empty_like(x)
+
+    def send(self, x: torch.Tensor, peer: int) -> None:
+        check(lib().cake_b200_send(self.ctx.h, ptr(x), x.numel() * x.element_size(), peer))
+
+    def recv(self, y: torch.Tensor, peer: int) -> None:
+        check(lib().cake_b200_recv(self.ctx.h, ptr(y), y.numel() * y.element_size(), peer))
+
+
+class GlooTransport:
+    """CPU stand-in used by the world_size-2 gloo tests of the host logic (tests/test_parallel_cpu.py)."""
+
+    def empty_like(self, x):
+        return torch.empty_like(x)
+
+    def send(self, x, peer):
+        import torch.distributed as dist
+        dist.send(x.contiguous(), peer)
+
+    def recv(self, y, peer):
+        import torch.distributed as dist
+        dist.recv(y, peer)
+
+
 class Client(Forwarder):
     """A block that lives on another GPU (client.rs:13).  forward_batch ships the activation to the
     worker rank and receives the result — NCCL send/recv on the ctx stream, no host copy."""
 
-    def __init__(self, worker: str, name: str, ctx: Context):
+    def __init__(self, worker: str, name: str, ctx, transport=None):
         self.worker, self.name, self.ctx, self.peer = worker, name, ctx, rank_of(worker)
+        self.transport = transport or NcclTransport(ctx)
 
     @classmethod
     def load(cls, name, ctx):  # pragma: no cover - constructed through TextModelBase.load(make_remote=...)
@@ -105,13 +138,11 @@ class Client(Forwarder):
         import torch.distributed as dist
         b, s, _ = x.shape
         # control header == the (layer_name, index_pos, block_idx) list of Message::Batch (message.rs:191-247)
-        dist.broadcast_object_list([("batch", self.peer, b, s, batch)], src=0)
-        nbytes = x.numel() * x.element_size()
-        with torch.cuda.stream(ctx.torch_stream):
-            x = x.contiguous()
-            y = torch.empty_like(x)
-        check(lib().cake_b200_send(ctx.h, ptr(x), nbytes, self.peer))
-        check(lib().cake_b200_recv(ctx.h, ptr(y), nbytes, self.peer))
+        dist.broadcast_object_list([("batch", self.peer, b, s, list(x.shape), batch)], src=0)
+        x = x.contiguous()
+        y = self.transport.empty_like(x)
+        self.transport.send(x, self.peer)
+        self.transport.recv(y, self.peer)
         return y
 
     def goodbye(self):
@@ -130,11 +161,13 @@ class Client(Forwarder):
 class Worker:
     """worker.rs:79-597 on rank > 0: owns the blocks of its layer range and a per-session cache."""
 
-    def __init__(self, ctx: Context, rank: int, world: int):
+    def __init__(self, ctx, rank: int, world: int, block_cls=B200Transformer, transport=None):
         self.ctx, self.rank, self.world = ctx, rank, world
         names = box_topology(ctx.config, world).get(f"gpu{rank}", {"layers": []})["layers"]
-        self.blocks: Dict[str, B200Transformer] = {n: B200Transformer.load(n, ctx) for n in names}
+        self.blocks: Dict[str, Forwarder] = {n: block_cls.load(n, ctx) for n in names}
         self.names = names
+        self.transport = transport or NcclTransport(ctx)
+        self.served = 0
 
     def block_list(self) -> Tuple[List[B200Transformer], List[int]]:
         blks = [self.blocks[n] for n in self.names]
@@ -153,15 +186,18 @@ class Worker:
             if op[0] == "goodbye":  # worker.rs:364-371
                 ctx.cache.clear()
             elif op[0] == "batch":
-                _, peer, b, s, batch = op
+                _, peer, b, s, shape, batch = op
                 if peer != self.rank:
                     continue
-                x = ctx.empty(b, s, ctx.config.hidden_size)
-                nbytes = x.numel() * x.element_size()
-                check(lib().cake_b200_recv(ctx.h, ptr(x), nbytes, 0))
+                x = ctx.empty(*shape)
+                self.transport.recv(x, 0)
+                missing = [name for name, _, _ in batch if name not in self.blocks]
+                if missing:  # worker.rs:490-503: report, keep serving
+                    raise KeyError(f"worker gpu{self.rank} does not own {missing}")
                 blks = [self.blocks[name] for name, _, _ in batch]
                 y = blks[0].forward_batch(x, batch, ctx, blocks=blks)
-                check(lib().cake_b200_send(ctx.h, ptr(y), nbytes, 0))
+                self.transport.send(y, 0)
+                self.served += 1
             elif op[0] == "decode":  # graph-captured ring decode: n steps without further control traffic
                 _, n_steps, index_pos = op
                 blks, idx = self.block_list()

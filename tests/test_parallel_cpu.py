@@ -1,0 +1,169 @@
+"""Host-side logic of the sharded path on CPU: topology/range parsing (reference: cake-core/src/cake/
+sharding/topology.rs:13,134-172 and tests/unit_tests/test_topology.rs) and the master<->worker protocol
+with world_size 2 over gloo (reference: tests/protocol.rs — two tasks over loopback; here two processes).
+The CUDA blocks are replaced by a stand-in Forwarder so that no GPU is needed; the transport is GlooTransport."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cake_b200.config import llama3_8b, reference_test_config
+from cake_b200.model import Forwarder, _topology_owner
+from cake_b200.parallel import Client, GlooTransport, Worker, box_topology, expand_layers, layer_split, parse_topology
+
+
+def test_layer_range_expansion():
+    assert expand_layers(["model.layers.0-2"]) == ["model.layers.0", "model.layers.1", "model.layers.2"]
+    assert expand_layers(["model.layers.7", "model.layers.9-9"]) == ["model.layers.7", "model.layers.9"]
+    assert expand_layers(["model.language_model.layers.10-11"]) == ["model.language_model.layers.10", "model.language_model.layers.11"]
+    with pytest.raises(ValueError, match="end must be >= start"):
+        expand_layers(["model.layers.5-2"])
+
+
+def test_parse_topology_and_ownership():
+    topo = parse_topology({"w1": {"host": "10.0.0.2:10128", "layers": ["model.layers.4-7"]},
+                           "w2": {"host": "10.0.0.3:10128", "layers": ["model.layers.8-8"]}})
+    assert len(topo["w1"]["layers"]) == 4
+    assert _topology_owner(topo, "model.layers.5") == "w1"
+    assert _topology_owner(topo, "model.layers.8") == "w2"
+    assert _topology_owner(topo, "model.layers.0") is None           # unassigned layers stay on the master
+    assert _topology_owner(topo, "model.layers.80") is None          # "model.layers.8" must not match "…80"
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_layer_split_is_contiguous_and_complete(world):
+    cfg = llama3_8b()
+    parts = layer_split(cfg.num_hidden_layers, world)
+    assert [i for r in parts for i in r] == list(range(cfg.num_hidden_layers))
+    assert max(len(r) for r in parts) - min(len(r) for r in parts) <= 1
+    topo = box_topology(cfg, world)
+    assert set(topo) == {f"gpu{r}" for r in range(1, world)}
+    for r in range(1, world):
+        assert topo[f"gpu{r}"]["layers"] == [f"model.layers.{i}" for i in parts[r]]
+
+
+def test_70b_split_is_ten_layers_per_gpu():
+    from cake_b200.config import llama3_70b
+    assert [len(r) for r in layer_split(llama3_70b().num_hidden_layers, 8)] == [10] * 8
+
+
+# ---- world_size 2 over gloo -----------------------------------------------------------------------
+class _Cache:
+    def __init__(self):
+        self.cleared = 0
+
+    def clear(self):
+        self.cleared += 1
+
+
+class _Ctx:
+    """Context stand-in: config + cache + empty()."""
+
+    def __init__(self, cfg):
+        self.config, self.cache, self.topology = cfg, _Cache(), {}
+
+    def empty(self, *shape):
+        return torch.empty(shape, dtype=torch.float32)
+
+    def sync(self):
+        pass
+
+
+class _AffineBlock(Forwarder):
+    """y = 2x + (layer index + 1): order-sensitive, so a wrong layer order or a skipped layer is caught."""
+
+    def __init__(self, name):
+        self.name, self.idx = name, int(name.rsplit(".", 1)[1])
+
+    @classmethod
+    def load(cls, name, ctx):
+        return cls(name)
+
+    def forward(self, x, index_pos, block_idx, ctx):
+        assert block_idx == self.idx
+        return 2 * x + (self.idx + 1)
+
+    def forward_batch(self, x, batch, ctx, blocks=None):
+        for (name, pos, idx), blk in zip(batch, blocks or [self]):
+            assert name == blk.name
+            x = blk.forward(x, pos, idx, ctx)
+        return x
+
+    def layer_name(self):
+        return self.name
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _run(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = reference_test_config()          # 4 layers -> rank 0 owns 0-1, rank 1 owns 2-3
+    ctx = _Ctx(cfg)
+    tr = GlooTransport()
+    try:
+        if rank == 1:
+            w = Worker(ctx, 1, world, block_cls=_AffineBlock, transport=tr)
+            assert w.names == ["model.layers.2", "model.layers.3"]
+            w.serve()
+            q.put(("worker", w.served, ctx.cache.cleared))
+        else:
+            ctx.topology = box_topology(cfg, world)
+            blocks = []
+            for i in range(cfg.num_hidden_layers):
+                name = cfg.layer_name(i)
+                owner = _topology_owner(ctx.topology, name)
+                blocks.append(_AffineBlock.load(name, ctx) if owner is None else Client(owner, name, ctx, transport=tr))
+            assert [b.ident() for b in blocks] == ["local", "local", "gpu1", "gpu1"]
+
+            def forward(x, pos):  # the block walk of text_model.rs:284-332
+                i = 0
+                while i < len(blocks):
+                    j = i
+                    while j < len(blocks) and blocks[j].ident() == blocks[i].ident():
+                        j += 1
+                    batch = [(blocks[k].layer_name(), pos, k) for k in range(i, j)]
+                    x = blocks[i].forward_batch(x, batch, ctx, blocks=blocks[i:j]) if blocks[i].ident() == "local" \
+                        else blocks[i].forward_batch(x, batch, ctx)
+                    i = j
+                return x
+
+            x = torch.arange(8, dtype=torch.float32).reshape(1, 1, 8)
+            ref = x
+            for i in range(4):
+                ref = 2 * ref + (i + 1)
+            outs = [forward(x, p) for p in range(3)]                  # 3 sequential ops (protocol.rs: 10 sequential)
+            big = forward(torch.ones(1, 64, 8), 3)                     # "large tensor" case
+            dist.broadcast_object_list([("goodbye",)], src=0)         # goodbye-then-continue
+            after = forward(x, 0)
+            dist.broadcast_object_list([("shutdown",)], src=0)
+            q.put(("master", all(torch.equal(o, ref) for o in outs + [after]), tuple(big.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_master_worker_protocol_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_run, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in range(2):
+        item = q.get(timeout=120)
+        res[item[0]] = item[1:]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res["master"] == (True, (1, 64, 8))
+    assert res["worker"] == (5, 1)   # 5 batches served, cache cleared once by Goodbye
