@@ -25,6 +25,10 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# Before numpy/torch load an OpenMP runtime: pin OpenMP threads.  The CPU legs (oracle port) otherwise lose
+# >10x to thread migration between torch's and the system's libgomp (1.2 GB/s unbound vs 68 GB/s bound).
+os.environ.setdefault("OMP_PROC_BIND", "true")
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
 METRIC = "decode tok/s (Llama-3-8B bf16, bs=1, 2k ctx)"
 CTX_LEN = 2048
@@ -117,6 +121,7 @@ def cpu_reference_tok_s(cfg, n_tokens: int, budget_s: float, layers_cap=None) ->
     from cake_b200.synth import make_head, make_layer
     from oracle import oracle as O
 
+    torch.set_num_threads(1)  # torch only builds the inputs here; keep its OpenMP pool off the oracle's cores
     t_build = time.perf_counter()
     nl = cfg.num_hidden_layers
     n_sample = min(nl, layers_cap or nl)

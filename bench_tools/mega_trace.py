@@ -43,3 +43,13 @@ buf2 = (ctypes.c_ulonglong * n2)()
 check(L.cake_b200_debug_trace(ctx.h, buf2, n2))
 a = np.array(buf2[2048:2056], dtype=np.int64)
 print("attention sub-phases (layer 1, CTA 0) us:", dict(zip(["qprep", "tile_wait", "scores", "softmax", "pv", "partial_wr", "fence+ticket"], np.round(np.diff(a) / 1e3, 2))))
+
+n3 = 2560 + 148
+buf3 = (ctypes.c_ulonglong * n3)()
+check(L.cake_b200_debug_trace(ctx.h, buf3, n3))
+fin = np.array(buf3[2304:2304 + 148], dtype=np.int64) / 1e3
+rel = np.array(buf3[2560:2560 + 148], dtype=np.int64) / 1e3
+fin -= fin.min(); 
+print("gate_up(l=1) finish spread over CTAs us: p50 %.2f p90 %.2f max %.2f ; sorted tail:" % (np.percentile(fin, 50), np.percentile(fin, 90), fin.max()), np.round(np.sort(fin)[-6:], 2))
+print("barrier release after last finisher us: min %.2f max %.2f" % ((rel - rel.min()).min() , (rel.max() - (np.array(buf3[2304:2304+148],dtype=np.int64)/1e3).max())))
+print("slowest CTAs:", np.argsort(fin)[-8:])

@@ -54,6 +54,8 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
 };
 static NcclApi g_nccl;
 static int nccl_load() {
@@ -75,6 +77,8 @@ static int nccl_load() {
   SYM(Send, "ncclSend");
   SYM(Recv, "ncclRecv");
   SYM(GetErrorString, "ncclGetErrorString");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
 #undef SYM
   g_nccl.lib = h;
   return CAKE_B200_OK;
@@ -157,6 +161,9 @@ template <typename F> static inline int dispatch_T(int dtype, F &&f) {
 // usage: DISPATCH_T(dtype, [&](auto tag_) -> int { typedef typename decltype(tag_)::type T; ... })
 #define DISPATCH_T(dtype, ...) dispatch_T((dtype), __VA_ARGS__)
 #define T_LAMBDA [&](auto tag_) -> int
+
+// (head_dim, query heads per kv head) combinations the megakernel is instantiated for
+#define MK_FOR_ALL(X) X(16, 2) X(16, 4) X(64, 2) X(64, 4) X(128, 1) X(128, 2) X(128, 4) X(128, 8)
 
 // ------------------------------------------------------------------------------------------ launch helper (PDL)
 template <typename... KArgs, typename... Args>
@@ -245,10 +252,10 @@ template <typename T> static int set_smem_attrs_T() {
   CU(cudaFuncSetAttribute(attn_decode_kernel<T, HD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   SETB(16) SETB(32) SETB(64) SETB(128) SETB(256)
 #undef SETB
-#define SETC(HD)                                                                                                  \
-  CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs - 2048));  \
-  CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  SETC(16) SETC(32) SETC(64) SETC(128) SETC(256)
+#define SETC(HD, G)                                                                                                  \
+  CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs - 2048));  \
+  CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+  MK_FOR_ALL(SETC)
 #undef SETC
   return CAKE_B200_OK;
 }
@@ -631,6 +638,13 @@ struct MkPlan {
   MkArgs a;
   size_t smem;
 };
+static bool mega_supported(const cake_b200_ctx *c) {
+  const int G = c->cfg.n_heads / c->cfg.n_kv_heads;
+#define MK_CASE(HD_, G_) if (c->cfg.head_dim == HD_ && G == G_) return true;
+  MK_FOR_ALL(MK_CASE)
+#undef MK_CASE
+  return false;
+}
 static int plan_mega(cake_b200_ctx *c, cake_b200_cache *kc, bool with_head, MkPlan *p) {
   const cake_b200_config &f = c->cfg;
   MkArgs &a = p->a;
@@ -663,6 +677,18 @@ static int plan_mega(cake_b200_ctx *c, cake_b200_cache *kc, bool with_head, MkPl
   return CAKE_B200_OK;
 }
 
+template <typename T> static int launch_mega_T(cake_b200_ctx *c, cudaLaunchConfig_t *cfg, const MkArgs &a) {
+  const int G = c->cfg.n_heads / c->cfg.n_kv_heads;
+#define MK_CASE(HD_, G_)                                                \
+  if (c->cfg.head_dim == HD_ && G == G_) {                              \
+    CU(cudaLaunchKernelEx(cfg, decode_mega_kernel<T, HD_, G_>, a));     \
+    return CAKE_B200_OK;                                                \
+  }
+  MK_FOR_ALL(MK_CASE)
+#undef MK_CASE
+  return fail(CAKE_B200_EINVAL, "megakernel: head_dim %d with %d query heads per kv head is not instantiated", c->cfg.head_dim, G);
+}
+
 static int launch_mega(cake_b200_ctx *c, const MkPlan &p) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(c->sm_count);
@@ -677,14 +703,7 @@ static int launch_mega(cake_b200_ctx *c, const MkPlan &p) {
   const MkArgs &a = p.a;
   int rc = DISPATCH_T(c->cfg.dtype, T_LAMBDA {
     typedef typename decltype(tag_)::type T;
-    switch (c->cfg.head_dim) {
-      case 16: CU(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T, 16>, a)); break;
-      case 32: CU(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T, 32>, a)); break;
-      case 64: CU(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T, 64>, a)); break;
-      case 128: CU(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T, 128>, a)); break;
-      default: CU(cudaLaunchKernelEx(&cfg, decode_mega_kernel<T, 256>, a)); break;
-    }
-    return CAKE_B200_OK;
+    return launch_mega_T<T>(c, &cfg, a);
   });
   RC(rc);
   if (c->capturing) c->g_kernels++;
@@ -813,7 +832,7 @@ extern "C" int cake_b200_forward_batch(cake_b200_ctx *c, cake_b200_block *const 
   if (batch == 1 && seq == 1) {
     set_int_kernel<<<1, 1, 0, c->stream>>>(kc->d_pos, index_pos);
     c->launches++;
-    if (c->use_mega) RC(enqueue_mega_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev));
+    if (c->use_mega && mega_supported(c)) RC(enqueue_mega_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev));
     else RC(enqueue_decode_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev));
   } else {
     RC(enqueue_prefill_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev, batch, seq, index_pos));
@@ -963,6 +982,16 @@ extern "C" int cake_b200_comm_init(cake_b200_ctx *c, const void *unique_id128, i
   NC(g_nccl.CommInitRank(&c->comm, world, id, rank));
   c->rank = rank;
   c->world = world;
+  // Warm up the ring's p2p connections now: NCCL sets a peer connection up lazily on first use, which must
+  // not happen inside the CUDA-graph capture of the decode step.
+  if (world > 1) {
+    const size_t xbytes = (size_t)c->cfg.hidden * c->es;
+    NC(g_nccl.GroupStart());
+    NC(g_nccl.Send(c->xa, xbytes, ncclUint8, (rank + 1) % world, c->comm, c->stream));
+    NC(g_nccl.Recv(c->xb, xbytes, ncclUint8, (rank + world - 1) % world, c->comm, c->stream));
+    NC(g_nccl.GroupEnd());
+    CU(cudaStreamSynchronize(c->stream));
+  }
   return CAKE_B200_OK;
 }
 extern "C" int cake_b200_send(cake_b200_ctx *c, const void *x_dev, size_t bytes, int peer) {
@@ -999,7 +1028,7 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
   c->capturing = true;
   c->g_kernels = 0;
   int rc = [&]() -> int {
-    if (c->use_mega) {
+    if (c->use_mega && mega_supported(c)) {
       // rank 0: [embed+layers(+head if alone)] ; world>1: layers -> send ... recv -> head.  ranks>0: recv -> layers -> send
       MkPlan p;
       if (rank == 0) {

@@ -66,7 +66,7 @@ struct MkArgs {
 
 __host__ __device__ inline size_t mk_xs_bytes(int max_k, int es) {
   size_t b = (size_t)max_k * es;
-  const size_t attn = (size_t)(ATTN_MAX_G * 256 * 4) + (size_t)ATTN_MAX_G * 128 * 4 + (size_t)4 * ATTN_MAX_G * 256 * 4 / 2;
+  const size_t attn = (size_t)(ATTN_MAX_G * 256 * 4) + (size_t)ATTN_MAX_G * ATTN_TILE * 4 + (size_t)2 * 256 * 4;
   return b > attn ? b : attn;  // the attention phase overlays its scratch on the x buffer
 }
 __host__ __device__ inline size_t mk_smem_bytes(int max_k, int partial_floats, int n_stages, int es) {
@@ -405,9 +405,38 @@ __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, con
   }
 }
 
-// Attention phase for this CTA's (kv head, split) item.  Same math as attn_decode_kernel; K/V tiles come
-// from the ring (prefetched by the producer while the qkv GEMV was still running).
-template <typename T, int HD>
+// Sum G per-lane values over the 16 lanes of a half-warp with a halving butterfly: after log2(G) exchange
+// steps every lane owns ONE head's partial, then the remaining xor steps finish it.  G + log2(16/G) - 1
+// shuffles instead of 4*G.  Returns the sum for head `g_out` (valid on every lane of the half-warp).
+template <int G>
+__device__ __forceinline__ float reduce16_heads(float (&s)[G], int lane, int &g_out) {
+  int g = 0;
+  int bit = 8;
+#pragma unroll
+  for (int n = G; n > 1; n >>= 1) {
+    const bool upper = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; i++) {
+      const float keep = upper ? s[i + n / 2] : s[i];
+      const float send = upper ? s[i] : s[i + n / 2];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+    if (upper) g += n / 2;
+    bit >>= 1;
+  }
+  float v = s[0];
+#pragma unroll
+  for (int b2 = 8; b2 >= 1; b2 >>= 1)
+    if (b2 <= bit) v += __shfl_xor_sync(0xffffffffu, v, b2);
+  g_out = g;
+  return v;
+}
+
+// Attention phase for this CTA's (kv head, split) item.  Same math as attn_decode_kernel (f32 scores,
+// softmax and PV, one rounding of the result); K/V tiles come from the ring, prefetched by the producer while
+// the qkv GEMV was still running.  G = n_heads / n_kv_heads is a template parameter so that all per-head
+// state lives in registers.
+template <typename T, int HD, int G>
 __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, const MkLayer &L, int pos, unsigned char *scr,
                                                 int ct, int warp, int lane, unsigned long long *tr) {
   auto stamp = [&](int i) {
@@ -418,14 +447,14 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     }
   };
   stamp(0);
-  constexpr int LPR = HD / 8, RPW = 32 / LPR, NW = MK_CW;
-  constexpr int NPG = (HD < MK_CT) ? MK_CT / HD : 1;
-  constexpr int DPT = (HD > MK_CT) ? HD / MK_CT : 1;
+  constexpr int LPR = HD / 8;            // lanes per cached row (16 B each); HD in {16,64,128} -> 2, 8, 16
+  constexpr int RPWI = 32 / LPR;         // rows per warp per iteration
+  constexpr int NW = MK_CW;
+  static_assert(HD == 16 || HD == 64 || HD == 128, "head_dim");
   const MkAttnItem it = mk_attn_item<T>(a, pos);
-  const int G = a.n_heads / a.n_kv;
-  float *q_s = reinterpret_cast<float *>(scr);             // [MAX_G][HD]
-  float *sc = q_s + ATTN_MAX_G * HD;                       // [MAX_G][ATTN_TILE]
-  float *pvred = sc + ATTN_MAX_G * ATTN_TILE;              // [NPG][MAX_G][HD]
+  float *q_s = reinterpret_cast<float *>(scr);             // [G][HD]
+  float *sc = q_s + ATTN_MAX_G * 256;                      // [ATTN_TILE][G]  (position-major: one vector per position)
+  float *knew = sc + ATTN_MAX_G * ATTN_TILE;               // [2][HD] appended k / v row
   __shared__ float m_run[ATTN_MAX_G], l_run[ATTN_MAX_G], fac[ATTN_MAX_G];
   __shared__ float wgt[ATTN_MAX_G][ATTN_MAX_SPLIT];
   __shared__ int is_last;
@@ -439,7 +468,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
   const int kvh = it.kvh, split = it.split, s0 = it.s0, s1 = it.s1, TILE = it.tile;
   const bool owner = (pos >= s0 && pos < s1);
 
-  // q for all G heads (qkv was written by other SMs: .cg loads through a staged copy)
+  // q for the G heads of this kv head (qkv was written by other SMs: ld.global.cg)
   for (int g = warp; g < G; g += NW) {
     const T *src = qkv + (size_t)(kvh * G + g) * HD;
     float *dst = q_s + g * HD;
@@ -447,7 +476,6 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     __syncwarp();
     norm_rope_inplace<T, HD>(dst, reinterpret_cast<const T *>(L.qn), a.eps, cosr, sinr, a.rot, lane);
   }
-  float *knew = pvred;  // free until the end of the phase
   if (owner) {
     if (warp == NW - 1) {
       const T *src = qkv + (size_t)(a.n_heads + kvh) * HD;
@@ -468,30 +496,34 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
   named_bar_sync(1, MK_CT);
   stamp(1);
 
-  const int grp = lane / LPR, gl = lane % LPR;
-  float qreg[ATTN_MAX_G][8];
+  const int grp = lane / LPR, gl = lane % LPR;  // row group within the warp / lane within the row
+  float qreg[G][8];
 #pragma unroll
-  for (int g = 0; g < ATTN_MAX_G; g++)
+  for (int g = 0; g < G; g++)
 #pragma unroll
-    for (int i = 0; i < 8; i++) qreg[g][i] = (g < G) ? q_s[g * HD + gl * 8 + i] : 0.f;
-  const int pv_d = ct % HD, pv_g = ct / HD;
-  float acc[ATTN_MAX_G][DPT];
+    for (int i = 0; i < 8; i++) qreg[g][i] = q_s[g * HD + gl * 8 + i];
+  float acc[G][8];  // PV accumulator: dims gl*8..+8 of every head, over this half-warp's positions
 #pragma unroll
-  for (int g = 0; g < ATTN_MAX_G; g++)
+  for (int g = 0; g < G; g++)
 #pragma unroll
-    for (int i = 0; i < DPT; i++) acc[g][i] = 0.f;
+    for (int i = 0; i < 8; i++) acc[g][i] = 0.f;
 
+  T *Ks = nullptr, *Vs = nullptr;
+  int sk = 0, sv = 0;
   for (int t0 = s0; t0 < s1; t0 += TILE) {
     const int tn = min(TILE, s1 - t0);
-    // K tile = current stage, V tile = the next one
-    const int sk = rg.s;
+    if (t0 > s0) {  // release the previous tile's stages (the last tile's are kept for the final reduction)
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&rg.empty[sk]); mbar_arrive(&rg.empty[sv]); }
+    }
+    sk = rg.s;
     const uint32_t phk = rg.ph;
     rg.advance();
-    const int sv = rg.s;
+    sv = rg.s;
     const uint32_t phv = rg.ph;
     rg.advance();
-    T *Ks = reinterpret_cast<T *>(rg.ring + (size_t)sk * MK_STAGE_BYTES);
-    T *Vs = reinterpret_cast<T *>(rg.ring + (size_t)sv * MK_STAGE_BYTES);
+    Ks = reinterpret_cast<T *>(rg.ring + (size_t)sk * MK_STAGE_BYTES);
+    Vs = reinterpret_cast<T *>(rg.ring + (size_t)sv * MK_STAGE_BYTES);
     mbar_wait(&rg.full[sk], phk);
     mbar_wait(&rg.full[sv], phv);
     stamp(2);
@@ -503,36 +535,49 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
       }
     }
     named_bar_sync(1, MK_CT);
-    for (int pb = warp * RPW; pb < tn; pb += NW * RPW) {
+    // ---- scores: s[p][g] = (q_g . k_p) * scale, f32 ----------------------------------------------
+    for (int pb = warp * RPWI; pb < tn; pb += NW * RPWI) {  // warp-uniform trip count (shuffles below)
       const int p = pb + grp;
       const bool valid = p < tn;
       float kf[8];
       uint4 kraw = make_uint4(0u, 0u, 0u, 0u);
       if (valid) kraw = *reinterpret_cast<const uint4 *>(Ks + (size_t)p * HD + gl * 8);
       unpack8<T>(kraw, kf);
+      float sg[G];
 #pragma unroll
-      for (int g = 0; g < ATTN_MAX_G; g++) {
-        if (g < G) {
-          float s = 0.f;
+      for (int g = 0; g < G; g++) {
+        float sacc = 0.f;
 #pragma unroll
-          for (int i = 0; i < 8; i++) s = fmaf(qreg[g][i], kf[i], s);
+        for (int i = 0; i < 8; i++) sacc = fmaf(qreg[g][i], kf[i], sacc);
+        sg[g] = sacc;
+      }
+      if (LPR == 16) {
+        int gh;
+        const float v = reduce16_heads<G>(sg, lane, gh);
+        constexpr int FIN = (G >= 8) ? 1 : (G == 4 ? 3 : (G == 2 ? 7 : 15));  // lanes that hold a finished head
+        if (valid && (gl & FIN) == 0) sc[p * G + gh] = v * a.scale;
+      } else {
 #pragma unroll
-          for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          if (gl == 0 && valid) sc[g * ATTN_TILE + p] = s * a.scale;
+        for (int g = 0; g < G; g++) {
+          float v = sg[g];
+#pragma unroll
+          for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (gl == 0 && valid) sc[p * G + g] = v * a.scale;
         }
       }
     }
     named_bar_sync(1, MK_CT);
     stamp(3);
+    // ---- online softmax bookkeeping, one warp per head ---------------------------------------------
     for (int g = warp; g < G; g += NW) {
       float mx = -INFINITY;
-      for (int p = lane; p < tn; p += 32) mx = fmaxf(mx, sc[g * ATTN_TILE + p]);
+      for (int p = lane; p < tn; p += 32) mx = fmaxf(mx, sc[p * G + g]);
       mx = warp_max(mx);
       const float m_new = fmaxf(m_run[g], mx);
       float sum = 0.f;
       for (int p = lane; p < tn; p += 32) {
-        const float ev = expf(sc[g * ATTN_TILE + p] - m_new);
-        sc[g * ATTN_TILE + p] = ev;
+        const float ev = expf(sc[p * G + g] - m_new);
+        sc[p * G + g] = ev;
         sum += ev;
       }
       sum = warp_sum(sum);
@@ -545,59 +590,72 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     }
     named_bar_sync(1, MK_CT);
     stamp(4);
+    // ---- PV: a lane owns dims gl*8..+8 of every head; one 16-byte V load feeds 8*G FMAs ------------
 #pragma unroll
-    for (int g = 0; g < ATTN_MAX_G; g++)
-      if (g < G) {
-        const float f = fac[g];
+    for (int g = 0; g < G; g++) {
+      const float f = fac[g];
 #pragma unroll
-        for (int i = 0; i < DPT; i++) acc[g][i] *= f;
-      }
-#pragma unroll 4
-    for (int p = pv_g; p < tn; p += NPG) {
-      float vf[DPT];
-#pragma unroll
-      for (int i = 0; i < DPT; i++) vf[i] = DT<T>::to_f(Vs[(size_t)p * HD + pv_d + i * MK_CT]);
-#pragma unroll
-      for (int g = 0; g < ATTN_MAX_G; g++)
-        if (g < G) {
-          const float ev = sc[g * ATTN_TILE + p];
-#pragma unroll
-          for (int i = 0; i < DPT; i++) acc[g][i] = fmaf(ev, vf[i], acc[g][i]);
-        }
+      for (int i = 0; i < 8; i++) acc[g][i] *= f;
     }
-    __syncwarp();
-    if (lane == 0) { mbar_arrive(&rg.empty[sk]); mbar_arrive(&rg.empty[sv]); }
-    named_bar_sync(1, MK_CT);
+    for (int p = warp * RPWI + grp; p < tn; p += NW * RPWI) {
+      float vf[8];
+      unpack8<T>(*reinterpret_cast<const uint4 *>(Vs + (size_t)p * HD + gl * 8), vf);
+#pragma unroll
+      for (int g = 0; g < G; g++) {
+        const float ev = sc[p * G + g];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[g][i] = fmaf(ev, vf[i], acc[g][i]);
+      }
+    }
+    named_bar_sync(1, MK_CT);  // every warp is done with this tile's K, V and probabilities
     stamp(5);
   }
 
-  if (NPG > 1) {
+  // ---- combine the row groups: lanes of a warp first (shuffles), then the 16 warps through the (dead)
+  //      K/V stage buffers of the last tile -----------------------------------------------------------
 #pragma unroll
-    for (int g = 0; g < ATTN_MAX_G; g++)
-      if (g < G) pvred[((size_t)pv_g * ATTN_MAX_G + g) * HD + pv_d] = acc[g][0];
+  for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+    for (int g = 0; g < G; g++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) acc[g][i] += __shfl_xor_sync(0xffffffffu, acc[g][i], o);
+  const bool have_tile = (s1 > s0);
+  float *red0 = reinterpret_cast<float *>(Ks), *red1 = reinterpret_cast<float *>(Vs);  // 8 warps each: [8][G][HD] <= 32 KB
+  if (have_tile) {
+    if (lane < LPR) {
+      float *dst = (warp < 8 ? red0 : red1) + (size_t)(warp & 7) * G * HD;
+#pragma unroll
+      for (int g = 0; g < G; g++)
+#pragma unroll
+        for (int i = 0; i < 8; i++) dst[g * HD + lane * 8 + i] = acc[g][i];
+    }
     named_bar_sync(1, MK_CT);
     for (int i = ct; i < G * HD; i += MK_CT) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; w++) sum += red0[(size_t)w * G * HD + i];
+#pragma unroll
+      for (int w = 0; w < 8; w++) sum += red1[(size_t)w * G * HD + i];
       const int g = i / HD, d = i % HD;
-      float s = 0.f;
-      for (int r = 0; r < NPG; r++) s += pvred[((size_t)r * ATTN_MAX_G + g) * HD + d];
-      a.ws_acc[((size_t)(kvh * G + g) * a.nsplit + split) * HD + d] = s;
+      a.ws_acc[((size_t)(kvh * G + g) * a.nsplit + split) * HD + d] = sum;
     }
+    __syncwarp();
+    named_bar_sync(1, MK_CT);
+    if (lane == 0) { mbar_arrive(&rg.empty[sk]); mbar_arrive(&rg.empty[sv]); }
   } else {
-#pragma unroll
-    for (int g = 0; g < ATTN_MAX_G; g++)
-      if (g < G) {
-#pragma unroll
-        for (int i = 0; i < DPT; i++) a.ws_acc[((size_t)(kvh * G + g) * a.nsplit + split) * HD + pv_d + i * MK_CT] = acc[g][i];
-      }
+    for (int i = ct; i < G * HD; i += MK_CT) {
+      const int g = i / HD, d = i % HD;
+      a.ws_acc[((size_t)(kvh * G + g) * a.nsplit + split) * HD + d] = 0.f;
+    }
   }
   if (ct < G) {
     a.ws_ml[((size_t)(kvh * G + ct) * a.nsplit + split) * 2 + 0] = m_run[ct];
     a.ws_ml[((size_t)(kvh * G + ct) * a.nsplit + split) * 2 + 1] = l_run[ct];
   }
   stamp(6);
-  __threadfence();
   named_bar_sync(1, MK_CT);
   if (ct == 0) {
+    __threadfence();  // cumulative: publishes the partials every thread of this CTA wrote before the bar.sync
     const unsigned ticket = atomicAdd(&a.attn_counters[kvh], 1u);
     is_last = (ticket == (unsigned)a.nsplit - 1);
   }
@@ -624,14 +682,14 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     const float *src = a.ws_acc + (size_t)h * a.nsplit * HD + d;
     float o = 0.f;
 #pragma unroll 8
-    for (int s = 0; s < a.nsplit; s++) o = fmaf(wgt[g][s], __ldcg(src + (size_t)s * HD), o);
+    for (int s2 = 0; s2 < a.nsplit; s2++) o = fmaf(wgt[g][s2], __ldcg(src + (size_t)s2 * HD), o);
     y[(size_t)h * HD + d] = DT<T>::from_f(o);
   }
   if (ct == 0) a.attn_counters[kvh] = 0;
 }
 
 // ---------------------------------------------------------------------------------------- the kernel
-template <typename T, int HD>
+template <typename T, int HD, int G>
 __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int es = sizeof(T);
@@ -715,7 +773,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     mk_consume_gemv<T, EPI_PLAIN>(rg, a.g_qkv, xs, partial, scratch, e, ct, warp, lane);
     gsync();
     // qk-norm, RoPE, KV append, attention
-    mk_consume_attn<T, HD>(rg, a, L, pos, reinterpret_cast<unsigned char *>(xs), ct, warp, lane,
+    mk_consume_attn<T, HD, G>(rg, a, L, pos, reinterpret_cast<unsigned char *>(xs), ct, warp, lane,
                            (a.trace && blockIdx.x == 0 && l == 1) ? a.trace + 2048 : nullptr);
     gsync();
     // o_proj + residual
@@ -730,7 +788,17 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     e = MkEpi{};
     e.out = a.mm;
     mk_consume_gemv<T, EPI_SWIGLU>(rg, a.g_gu, xs, partial, scratch, e, ct, warp, lane);
+    if (a.trace && l == 1 && ct == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.trace[2304 + blockIdx.x] = t;
+    }
     gsync();
+    if (a.trace && l == 1 && ct == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.trace[2560 + blockIdx.x] = t;
+    }
     // down + residual
     mk_stage_x<T>(xs, a.mm, nullptr, a.inter, a.eps, scratch, ct, warp, lane);
     e = MkEpi{};

@@ -34,6 +34,7 @@
  *   attention core: f32 throughout, one rounding of the result (attention.rs:301-346)
  *   residual adds in D; silu -> D then mul -> D (cpu/mod.rs:87-89); logits D -> f32 -> argmax
  */
+#include <immintrin.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -106,7 +107,31 @@ static size_t esize(int dt) { return dt == ORA_F32 ? 4 : 2; }
 /* ---------------------------------------------------------------- dot / linear */
 /* 16 independent partial sums so gcc vectorises without reassociating a single chain.
  * Products of two D values are exact in f32 for bf16 (8x8 bit) and f16 (11x11 bit). */
+#if defined(__AVX2__) && defined(__FMA__)
+/* bf16 row . f32 vector with 2x8 fp32 partial sums.  The products are exact in fp32 (x holds D values), so
+ * fused multiply-add equals multiply-then-add here; only the summation order differs from the scalar loop. */
+static float dot_row_bf16_avx2(const uint16_t *w, const float *x, int K) {
+  __m256 a0 = _mm256_setzero_ps(), a1 = _mm256_setzero_ps();
+  int k = 0;
+  for (; k + 16 <= K; k += 16) {
+    const __m256i raw = _mm256_loadu_si256((const __m256i *)(w + k));
+    const __m256i lo = _mm256_slli_epi32(_mm256_cvtepu16_epi32(_mm256_castsi256_si128(raw)), 16);
+    const __m256i hi = _mm256_slli_epi32(_mm256_cvtepu16_epi32(_mm256_extracti128_si256(raw, 1)), 16);
+    a0 = _mm256_fmadd_ps(_mm256_castsi256_ps(lo), _mm256_loadu_ps(x + k), a0);
+    a1 = _mm256_fmadd_ps(_mm256_castsi256_ps(hi), _mm256_loadu_ps(x + k + 8), a1);
+  }
+  float t[8];
+  _mm256_storeu_ps(t, _mm256_add_ps(a0, a1));
+  float s = ((t[0] + t[1]) + (t[2] + t[3])) + ((t[4] + t[5]) + (t[6] + t[7]));
+  for (; k < K; k++) s += bf16_bits_to_f32(w[k]) * x[k];
+  return s;
+}
+#endif
+
 static float dot_row(const void *W, size_t off, const float *x, int K, int dt) {
+#if defined(__AVX2__) && defined(__FMA__)
+  if (dt == ORA_BF16) return dot_row_bf16_avx2((const uint16_t *)W + off, x, K);
+#endif
   float acc[16];
   for (int j = 0; j < 16; j++) acc[j] = 0.f;
   int k = 0;
