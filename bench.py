@@ -341,24 +341,20 @@ def run_cuda(args):
     nxt = c_uint32()
     check(lib().cake_b200_decode_begin(ctx.h, tok, model.index_pos))
     sync_all()
-    if world == 1:
-        t0 = time.perf_counter()
-        cur = tok
-        for _ in range(n_e2e):
-            check(lib().cake_b200_decode_step_host(ctx.h, cur, byref(nxt)))
-            cur = nxt.value
-        e2e_s = time.perf_counter() - t0
-    else:
-        # workers already enqueued n_e2e replays; rank 0 still pays H2D + launch + D2H + sync per token
-        t0 = time.perf_counter()
-        cur = tok
-        for _ in range(n_e2e):
-            check(lib().cake_b200_decode_step_host(ctx.h, cur, byref(nxt)))
-            cur = nxt.value
-        e2e_s = time.perf_counter() - t0
+    cur = tok
+    lat = []
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):  # workers (N>1) have pre-enqueued the same number of replays
+        t1 = time.perf_counter()
+        check(lib().cake_b200_decode_step_host(ctx.h, cur, byref(nxt)))
+        cur = nxt.value
+        lat.append(time.perf_counter() - t1)
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
         sync_all()
     model.index_pos += n_e2e
     e2e_tok_s = n_e2e / e2e_s
+    lat_ms = sorted(x * 1e3 for x in lat)
 
     # ---- roofline of the dominant kernel (gate_up GEMV: 54% of the bytes of a token), timed live -----
     peak, peak_src = peaks()
@@ -398,6 +394,7 @@ def run_cuda(args):
                    "l2": "inputs (15 GB of weights per step) larger than L2; no flush needed"},
         "clocks": clocks,
         "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4, "steps": n_e2e,
+                "ms_per_step_p50": lat_ms[len(lat_ms) // 2], "ms_per_step_max": lat_ms[-1],
                 "api": "cake_b200_decode_step_host (token id from host, sampled token back to host, sync per token)"},
         "gpu_launches": int(launches),
         "roofline": roof,
