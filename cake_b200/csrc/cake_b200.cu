@@ -16,6 +16,7 @@
 #include "attn_decode.cuh"
 #include "common.cuh"
 #include "decode_mega.cuh"
+#include "gemm_tc.cuh"
 #include "gemv.cuh"
 #include "prefill.cuh"
 
@@ -257,6 +258,9 @@ template <typename T> static int set_smem_attrs_T() {
   CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   MK_FOR_ALL(SETC)
 #undef SETC
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, TCE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, TCE_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, TCE_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   return CAKE_B200_OK;
 }
 
@@ -751,6 +755,48 @@ static int enqueue_head(cake_b200_ctx *c, const void *x_row, void *logits_out, b
   return launch_gemv<EPI_ARGMAX>(c, a);
 }
 
+// ------------------------------------------------------------------------------------------ TMA tensor maps (driver entry point, no -lcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+static int tmap_init() {
+  if (g_encode_tiled) return CAKE_B200_OK;
+  void *fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn || q != cudaDriverEntryPointSuccess) return fail(CAKE_B200_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  g_encode_tiled = (EncodeTiledFn)fn;
+  return CAKE_B200_OK;
+}
+// [rows, K] row-major matrix of D -> 2-D map with a (64 x box_rows) box and 128-byte swizzle
+static int make_tmap(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t K, int dtype, uint32_t box_rows) {
+  RC(tmap_init());
+  const cuuint64_t gdim[2] = {K, rows};
+  const cuuint64_t gstride[1] = {K * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = g_encode_tiled(m, dtype == CAKE_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                                    const_cast<void *>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CAKE_B200_ECUDA, "cuTensorMapEncodeTiled(rows=%llu, K=%llu) -> CUresult %d", (unsigned long long)rows, (unsigned long long)K, (int)r);
+  return CAKE_B200_OK;
+}
+
+static bool tc_gemm_ok(int M, int N, int K) { return M >= 1 && N % TC_BN == 0 && K % TC_BK == 0; }
+
+// C = epi(A[M,K] W[N,K]^T) on the tensor cores (gemm_tc.cuh)
+template <typename T, int EPI>
+static int gemm_tc_T(cake_b200_ctx *c, const void *A, const void *W, const void *bias, const void *res, void *C, int M, int N, int K) {
+  CUtensorMap ma, mb;
+  RC(make_tmap(&ma, A, (uint64_t)M, (uint64_t)K, c->cfg.dtype, TC_BM));
+  RC(make_tmap(&mb, W, (uint64_t)N, (uint64_t)K, c->cfg.dtype, TC_BN));
+  TcParams p{bias, res, C, M, N, K};
+  const int tiles = ((M + TC_BM - 1) / TC_BM) * (N / TC_BN);
+  dim3 grid(tiles < c->sm_count ? tiles : c->sm_count), block(TC_THREADS);
+  return launch_pdl(c, gemm_tc_kernel<T, EPI>, grid, block, (size_t)TC_SMEM_BYTES, ma, mb, p);
+}
+
 // ------------------------------------------------------------------------------------------ prefill path (any batch / seq)
 static int pf_reserve(cake_b200_ctx *c, size_t rows) {
   if (rows <= c->pf_rows) return CAKE_B200_OK;
@@ -783,6 +829,8 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
   const cake_b200_config &f = c->cfg;
   const int H = f.hidden, I = f.inter, hd = f.head_dim, sq = f.n_heads * hd, M = B * S;
   RC(pf_reserve(c, (size_t)M));
+  const char *env_tc = getenv("CAKE_B200_NO_TC");
+  const bool use_tc = !(env_tc && env_tc[0] == '1');  // CAKE_B200_NO_TC=1: CUDA-core GEMM (A/B testing aid)
   return DISPATCH_T(f.dtype, T_LAMBDA {
       typedef typename decltype(tag_)::type T;
     const void *cur = x_in;
@@ -790,7 +838,8 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
       const cake_b200_block *b = blocks[i];
       const int l = block_idx[i];
       RC(launch_pdl(c, rmsnorm_rows_kernel<T>, dim3(M), dim3(256), 0, (const T *)cur, (const T *)b->ln1, (T *)c->pf_h, H, f.rms_eps));
-      RC(gemm_T<T>(c, c->pf_h, b->wqkv, b->bqkv, nullptr, c->pf_qkv, M, c->nqkv, H));
+      if (use_tc && tc_gemm_ok(M, c->nqkv, H)) RC((gemm_tc_T<T, TCE_PLAIN>(c, c->pf_h, b->wqkv, b->bqkv, nullptr, c->pf_qkv, M, c->nqkv, H)));
+      else RC(gemm_T<T>(c, c->pf_h, b->wqkv, b->bqkv, nullptr, c->pf_qkv, M, c->nqkv, H));
       {
         const long items = (long)M * (f.n_heads + 2 * f.n_kv_heads);
         RC(launch_pdl(c, rope_append_kernel<T>, dim3((unsigned)((items + 3) / 4)), dim3(128), (size_t)4 * hd * 4,
@@ -803,11 +852,17 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
                       (const T *)kc->k[l], (const T *)kc->v[l], (T *)c->pf_y, B, S, f.n_heads, f.n_kv_heads, hd, kc->cap,
                       pos0, (float)(1.0 / sqrt((double)hd))));
       }
-      RC(gemm_T<T>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq));
+      if (use_tc && tc_gemm_ok(M, H, sq)) RC((gemm_tc_T<T, TCE_RESIDUAL>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq)));
+      else RC(gemm_T<T>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq));
       RC(launch_pdl(c, rmsnorm_rows_kernel<T>, dim3(M), dim3(256), 0, (const T *)c->pf_x1, (const T *)b->ln2, (T *)c->pf_h, H, f.rms_eps));
-      RC(gemm_T<T>(c, c->pf_h, b->wgu, nullptr, nullptr, c->pf_gu, M, 2 * I, H));
-      RC(launch_pdl(c, swiglu_rows_kernel<T>, dim3(c->sm_count * 4), dim3(256), 0, (const T *)c->pf_gu, (T *)c->pf_mm, (size_t)M * I));
-      RC(gemm_T<T>(c, c->pf_mm, b->wd, nullptr, c->pf_x1, x_out, M, H, I));
+      if (use_tc && tc_gemm_ok(M, 2 * I, H)) {
+        RC((gemm_tc_T<T, TCE_SWIGLU>(c, c->pf_h, b->wgu, nullptr, nullptr, c->pf_mm, M, 2 * I, H)));
+      } else {
+        RC(gemm_T<T>(c, c->pf_h, b->wgu, nullptr, nullptr, c->pf_gu, M, 2 * I, H));
+        RC(launch_pdl(c, swiglu_rows_kernel<T>, dim3(c->sm_count * 4), dim3(256), 0, (const T *)c->pf_gu, (T *)c->pf_mm, (size_t)M * I));
+      }
+      if (use_tc && tc_gemm_ok(M, H, I)) RC((gemm_tc_T<T, TCE_RESIDUAL>(c, c->pf_mm, b->wd, nullptr, c->pf_x1, x_out, M, H, I)));
+      else RC(gemm_T<T>(c, c->pf_mm, b->wd, nullptr, c->pf_x1, x_out, M, H, I));
       cur = x_out;
     }
     return CAKE_B200_OK;
