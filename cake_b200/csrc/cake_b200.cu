@@ -14,6 +14,7 @@
 
 #include "../../include/cake_b200.h"
 #include "attn_decode.cuh"
+#include "attn_prefill.cuh"
 #include "common.cuh"
 #include "decode_mega.cuh"
 #include "gemm_tc.cuh"
@@ -134,6 +135,7 @@ struct cake_b200_ctx {
   MkLayer *mk_tab_dev = nullptr, *mk_tab_host = nullptr, *g_tab_dev = nullptr;
   std::vector<const void *> mk_sig;
   unsigned long long *trace = nullptr;  // CAKE_B200_MEGA_TRACE=1
+  unsigned *tickets = nullptr;          // per-phase work-claim counters of the megakernel
 };
 constexpr int TOKEN_RING = 1 << 16;
 
@@ -258,6 +260,8 @@ template <typename T> static int set_smem_attrs_T() {
   CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   MK_FOR_ALL(SETC)
 #undef SETC
+  CU(cudaFuncSetAttribute(attn_prefill_mma_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * FA_BN * 128 * 2));
+  CU(cudaFuncSetAttribute(attn_prefill_mma_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * FA_BN * 64 * 2));
   CU(cudaFuncSetAttribute(gemm_tc_kernel<T, TCE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tc_kernel<T, TCE_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
   CU(cudaFuncSetAttribute(gemm_tc_kernel<T, TCE_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
@@ -370,6 +374,7 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
   CU(cudaMallocHost(&c->h_pin, 64 * 4));
   CU(cudaMalloc(&c->gbar, 16));
   CU(cudaMemset(c->gbar, 0, 16));
+  CU(cudaMalloc(&c->tickets, sizeof(unsigned) * (4 * MK_MAX_LAYERS + 4)));
   CU(cudaMalloc(&c->mk_tab_dev, sizeof(MkLayer) * MK_MAX_LAYERS));
   CU(cudaMalloc(&c->g_tab_dev, sizeof(MkLayer) * MK_MAX_LAYERS));
   CU(cudaMallocHost(&c->mk_tab_host, sizeof(MkLayer) * MK_MAX_LAYERS));
@@ -396,7 +401,7 @@ extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
   void *bufs[] = {c->cos_t, c->sin_t, c->embed, c->ln_f, c->xa, c->xb, c->qkv, c->y, c->mm, c->logits, c->ws_ml,
                   c->ws_acc, c->part_val, c->part_idx, c->d_step, c->attn_counters, c->argmax_counter, c->d_token,
                   c->token_ring, c->d_ids, c->d_pen, c->pf_h, c->pf_qkv, c->pf_y, c->pf_x1, c->pf_gu, c->pf_mm, c->io_x,
-                  c->gbar, c->mk_tab_dev, c->g_tab_dev};
+                  c->gbar, c->mk_tab_dev, c->g_tab_dev, c->tickets};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (c->lm_head && c->lm_head != c->embed) cudaFree(c->lm_head);
@@ -617,7 +622,7 @@ static int enqueue_decode_layers(cake_b200_ctx *c, cake_b200_block *const *block
 }
 
 // ------------------------------------------------------------------------------------------ megakernel plan + launch
-static int plan_mk_geom(const cake_b200_ctx *c, int N, int K, int G, MkGeom *g, int *partial_floats) {
+static int plan_mk_geom(const cake_b200_ctx *c, int N, int K, int G, MkGeom *g, int *partial_floats, int *max_groups) {
   const int es = c->es;
   if (K % 64 != 0 || N % G != 0) return fail(CAKE_B200_EINVAL, "mega: K=%d must be a multiple of 64, N=%d of %d", K, N, G);
   int KC = K;
@@ -633,8 +638,14 @@ static int plan_mk_geom(const cake_b200_ctx *c, int N, int K, int G, MkGeom *g, 
   if (RS * RPW < (MK_CW / WPR) * RPW || RS != (MK_CW / WPR) * RPW)  // every row slot must map to a staged row
     return fail(CAKE_B200_EINVAL, "mega: unsupported geometry N=%d K=%d (KC=%d RS=%d WPR=%d)", N, K, KC, RS, WPR);
   *g = MkGeom{N, K, KC, RS, WPR, RPW};
-  const int pf = (((N / G) / c->sm_count) + 1) * G * WPR;
-  if (pf > *partial_floats) *partial_floats = pf;
+  // per-CTA cap of row groups in one phase: twice the even share (dynamic claiming, decode_mega.cuh mk_split)
+  const int n_groups = (N + RS - 1) / RS;
+  const int cap = 2 * ((n_groups + c->sm_count - 1) / c->sm_count) + 4;
+  if (cap > *max_groups) *max_groups = cap;
+  // *partial_floats collects max(RS*WPR) here and the static-path need; plan_mega multiplies by the global cap
+  if (RS * WPR > *partial_floats % 65536) *partial_floats = (*partial_floats / 65536) * 65536 + RS * WPR;
+  const int pf_static = (((N / G) / c->sm_count) + 1) * G * WPR;
+  if (pf_static > *partial_floats / 65536) *partial_floats = pf_static * 65536 + *partial_floats % 65536;
   return CAKE_B200_OK;
 }
 
@@ -653,13 +664,19 @@ static int plan_mega(cake_b200_ctx *c, cake_b200_cache *kc, bool with_head, MkPl
   const cake_b200_config &f = c->cfg;
   MkArgs &a = p->a;
   memset(&a, 0, sizeof(a));
-  int pf = 0;
-  RC(plan_mk_geom(c, c->nqkv, f.hidden, 1, &a.g_qkv, &pf));
-  RC(plan_mk_geom(c, f.hidden, f.n_heads * f.head_dim, 1, &a.g_o, &pf));
-  RC(plan_mk_geom(c, 2 * f.inter, f.hidden, 2, &a.g_gu, &pf));
-  RC(plan_mk_geom(c, f.hidden, f.inter, 1, &a.g_down, &pf));
-  if (with_head) RC(plan_mk_geom(c, f.vocab, f.hidden, 1, &a.g_head, &pf));
+  int pf = 0, mg = 0;
+  RC(plan_mk_geom(c, c->nqkv, f.hidden, 1, &a.g_qkv, &pf, &mg));
+  RC(plan_mk_geom(c, f.hidden, f.n_heads * f.head_dim, 1, &a.g_o, &pf, &mg));
+  RC(plan_mk_geom(c, 2 * f.inter, f.hidden, 2, &a.g_gu, &pf, &mg));
+  RC(plan_mk_geom(c, f.hidden, f.inter, 1, &a.g_down, &pf, &mg));
+  if (with_head) RC(plan_mk_geom(c, f.vocab, f.hidden, 1, &a.g_head, &pf, &mg));
+  {  // partial-sum scratch: every phase may use up to `mg` groups of its own RS*WPR floats (dynamic), or its static rows
+    const int dyn_need = mg * (pf % 65536), static_need = pf / 65536;
+    pf = dyn_need > static_need ? dyn_need : static_need;
+  }
   a.partial_floats = pf;
+  a.max_groups = mg;
+  a.tickets = c->tickets;
   a.hidden = f.hidden; a.inter = f.inter; a.n_heads = f.n_heads; a.n_kv = f.n_kv_heads; a.hd = f.head_dim;
   a.rot = c->rot; a.cap = kc ? kc->cap : 0; a.nsplit = c->nsplit; a.eps = f.rms_eps;
   a.scale = (float)(1.0 / sqrt((double)f.head_dim));
@@ -674,9 +691,9 @@ static int plan_mega(cake_b200_ctx *c, cake_b200_cache *kc, bool with_head, MkPl
   a.trace = c->trace;
   int ns = MK_MAX_STAGES;
   const size_t limit = 227 * 1024 - 2048;
-  while (ns > 2 && mk_smem_bytes(a.max_k, pf, ns, c->es) > limit) ns--;
+  while (ns > 2 && mk_smem_bytes(a.max_k, pf, mg, ns, c->es) > limit) ns--;
   a.n_stages = ns;
-  p->smem = mk_smem_bytes(a.max_k, pf, ns, c->es);
+  p->smem = mk_smem_bytes(a.max_k, pf, mg, ns, c->es);
   if (p->smem > limit) return fail(CAKE_B200_EINVAL, "mega: needs %zu B of shared memory", p->smem);
   return CAKE_B200_OK;
 }
@@ -705,6 +722,7 @@ static int launch_mega(cake_b200_ctx *c, const MkPlan &p) {
   cfg.attrs = at;
   cfg.numAttrs = 1;
   const MkArgs &a = p.a;
+  CU(cudaMemsetAsync(c->tickets, 0, sizeof(unsigned) * (4 * (size_t)a.n_layers + 4), c->stream));  // a memset node in the graph
   int rc = DISPATCH_T(c->cfg.dtype, T_LAMBDA {
     typedef typename decltype(tag_)::type T;
     return launch_mega_T<T>(c, &cfg, a);
@@ -846,7 +864,16 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
                       (T *)c->pf_qkv, (T *)kc->k[l], (T *)kc->v[l], (const T *)c->cos_t, (const T *)c->sin_t,
                       (const T *)b->qn, (const T *)b->kn, B, S, f.n_heads, f.n_kv_heads, hd, c->rot, kc->cap, pos0, f.rms_eps));
       }
-      {
+      if (use_tc && (hd == 64 || hd == 128)) {  // tensor-core flash attention (attn_prefill.cuh)
+        dim3 grid((S + FA_BM - 1) / FA_BM, f.n_heads, B), block(FA_THREADS);
+        const float sc = (float)(1.0 / sqrt((double)hd));
+        if (hd == 128)
+          RC(launch_pdl(c, attn_prefill_mma_kernel<T, 128>, grid, block, (size_t)5 * FA_BN * 128 * 2, (const T *)c->pf_qkv,
+                        (const T *)kc->k[l], (const T *)kc->v[l], (T *)c->pf_y, S, f.n_heads, f.n_kv_heads, kc->cap, pos0, sc));
+        else
+          RC(launch_pdl(c, attn_prefill_mma_kernel<T, 64>, grid, block, (size_t)5 * FA_BN * 64 * 2, (const T *)c->pf_qkv,
+                        (const T *)kc->k[l], (const T *)kc->v[l], (T *)c->pf_y, S, f.n_heads, f.n_kv_heads, kc->cap, pos0, sc));
+      } else {
         const long items = (long)M * f.n_heads;
         RC(launch_pdl(c, attn_prefill_v0_kernel<T>, dim3((unsigned)((items + 3) / 4)), dim3(128), 0, (const T *)c->pf_qkv,
                       (const T *)kc->k[l], (const T *)kc->v[l], (T *)c->pf_y, B, S, f.n_heads, f.n_kv_heads, hd, kc->cap,

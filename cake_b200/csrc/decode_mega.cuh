@@ -61,6 +61,8 @@ struct MkArgs {
   unsigned *argmax_counter;
   uint32_t *token_out, *token_ring;
   int ring_cap;
+  unsigned *tickets;          // [phase] work-claim counters, zeroed before every launch
+  int max_groups;             // per-CTA cap of row groups in one phase (sizes the partial-sum scratch)
   unsigned long long *trace;  // optional: %globaltimer stamps of CTA 0 at phase boundaries (profiling aid)
 };
 
@@ -69,14 +71,16 @@ __host__ __device__ inline size_t mk_xs_bytes(int max_k, int es) {
   const size_t attn = (size_t)(ATTN_MAX_G * 256 * 4) + (size_t)ATTN_MAX_G * ATTN_TILE * 4 + (size_t)2 * 256 * 4;
   return b > attn ? b : attn;  // the attention phase overlays its scratch on the x buffer
 }
-__host__ __device__ inline size_t mk_smem_bytes(int max_k, int partial_floats, int n_stages, int es) {
+__host__ __device__ inline size_t mk_smem_bytes(int max_k, int partial_floats, int max_groups, int n_stages, int es) {
   size_t off = (size_t)n_stages * MK_STAGE_BYTES;
   off += mk_xs_bytes(max_k, es);
   off = (off + 15) & ~(size_t)15;
   off += (size_t)partial_floats * 4;     // partial sums [row][slice]
+  off += (size_t)max_groups * 4;         // first row of each locally processed group
   off += 128 * 4;                        // scratch
   off = (off + 7) & ~(size_t)7;
   off += (size_t)2 * MK_MAX_STAGES * 8;  // mbarriers
+  off += (size_t)MK_MAX_STAGES * 4;      // stage_row
   return off + 256;
 }
 
@@ -90,6 +94,7 @@ __device__ __forceinline__ uint4 ldcg_v4(const void *p) { return __ldcg(reinterp
 struct MkRing {
   unsigned char *ring;
   uint64_t *full, *empty;
+  int *stage_row;  // first weight row held by a stage, or -1 = end-of-phase marker (dynamic phases)
   int n_stages;
   int s;
   uint32_t ph;
@@ -105,7 +110,57 @@ __device__ __forceinline__ void mk_rows(int N, int G, int &r0, int &r1) {
   r1 = (int)(units * (blockIdx.x + 1) / gridDim.x) * G;
 }
 
-// ---------------------------------------------------------------------------------------- producer
+// Dynamic phases: the N/RS row groups of a GEMV are split into a static part (75 %: CTA c owns groups
+// [c*sg, (c+1)*sg)) and a pool claimed one group at a time through an atomic ticket.  Per-SM HBM bandwidth is
+// not uniform (measured: the slowest CTA of the gate_up phase finished 5.5 us after the fastest with static
+// rows), so fast SMs take more pool groups and all CTAs reach the grid barrier together.  A row's dot product
+// is computed by one CTA with a fixed lane/warp mapping whichever CTA it is -> results stay bit-deterministic.
+struct MkSplit {
+  int n_groups, sg, pool_start;
+};
+__device__ __forceinline__ MkSplit mk_split(const MkGeom &g) {
+  MkSplit sp;
+  sp.n_groups = (g.N + g.RS - 1) / g.RS;
+  sp.sg = (int)(((long)sp.n_groups * 3 / 4) / gridDim.x);
+  sp.pool_start = sp.sg * gridDim.x;
+  return sp;
+}
+__device__ __forceinline__ bool mk_is_dynamic(const MkGeom &g) { return g.K == g.KC && (g.KC / 8) / g.WPR <= 128; }
+
+template <typename T>
+__device__ __forceinline__ void mk_produce_gemv_dyn(MkRing &rg, const MkGeom &g, const void *W, unsigned *ticket, int max_groups,
+                                                    uint64_t pol) {
+  constexpr int es = sizeof(T);
+  const MkSplit sp = mk_split(g);
+  const size_t rowb = (size_t)g.K * es;
+  const unsigned char *Wb = reinterpret_cast<const unsigned char *>(W);
+  int issued = 0;
+  auto issue = [&](int grp) {
+    const int row = grp * g.RS, nr = min(g.RS, g.N - row);
+    mbar_wait(&rg.empty[rg.s], rg.ph ^ 1u);
+    rg.stage_row[rg.s] = row;
+    mbar_arrive_expect_tx(&rg.full[rg.s], (uint32_t)(nr * rowb));
+    bulk_g2s(rg.ring + (size_t)rg.s * MK_STAGE_BYTES, Wb + (size_t)row * rowb, (uint32_t)(nr * rowb), &rg.full[rg.s], pol);
+    rg.advance();
+    issued++;
+  };
+  for (int grp = blockIdx.x * sp.sg; grp < (int)(blockIdx.x + 1) * sp.sg; grp++) issue(grp);
+  if (sp.pool_start < sp.n_groups && issued < max_groups) {
+    unsigned next = atomicAdd(ticket, 1u);
+    while (sp.pool_start + (int)next < sp.n_groups) {
+      const int cur = sp.pool_start + (int)next;
+      const bool more = issued + 1 < max_groups;  // a claimed group is never dropped: claim only what fits
+      if (more) next = atomicAdd(ticket, 1u);     // claim ahead: the round trip overlaps the wait for a free stage
+      issue(cur);
+      if (!more) break;
+    }
+  }
+  mbar_wait(&rg.empty[rg.s], rg.ph ^ 1u);  // end-of-phase marker
+  rg.stage_row[rg.s] = -1;
+  mbar_arrive(&rg.full[rg.s]);
+  rg.advance();
+}
+
 template <typename T>
 __device__ __forceinline__ void mk_produce_gemv(MkRing &rg, const MkGeom &g, const void *W, int G, uint64_t pol) {
   constexpr int es = sizeof(T);
@@ -248,20 +303,20 @@ struct MkEpi {
 };
 
 template <typename T, int EPI>
-__device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, const T *xs, float *partial, float *scratch,
-                                                const MkEpi &e, int ct, int warp, int lane) {
+__device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, const T *xs, float *partial, int *loc_row,
+                                                float *scratch, const MkEpi &e, int ct, int warp, int lane) {
   constexpr int G = (EPI == EPI_SWIGLU) ? 2 : 1;
-  int r0, r1;
-  mk_rows(g.N, G, r0, r1);
-  const int nrows = r1 - r0, RS = g.RS, WPR = g.WPR, RPW = g.RPW;
+  const int RS = g.RS, WPR = g.WPR, RPW = g.RPW, N = g.N;
   const int nchunk = g.K / g.KC;
   const int slots = MK_CW / WPR, slot = warp / WPR, ks = warp % WPR;
   const int segv = g.KC / 8, nvec = segv / WPR;
   const uint4 *xsv = reinterpret_cast<const uint4 *>(xs);
-  if (nchunk == 1 && nvec <= 128) {
-    // Fast path (all Llama/Qwen shapes): a lane's columns are the same for every row of the phase, so its
-    // x slice is converted to fp32 ONCE into registers; per 16-byte weight vector the loop is then
-    // 1 LDS.128 + 8 converts + 8 FMA (ncu r01: re-reading/converting x per vector made the loop issue-bound).
+  const bool dyn = mk_is_dynamic(g);
+  int r0 = 0, nrows = 0, nloc = 0;
+  if (dyn) {
+    // A lane's columns are the same for every row of the phase, so its x slice is converted to fp32 ONCE into
+    // registers; per 16-byte weight vector the loop is 1 LDS.128 + 8 converts + 8 FMA (ncu r01: re-reading and
+    // re-converting x per vector made the loop issue-bound).  Stages arrive with their row in stage_row[].
     float xr[4][8];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
@@ -272,102 +327,122 @@ __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, con
     }
     const bool v3 = lane + 96 < nvec, v2 = lane + 64 < nvec, v1 = lane + 32 < nvec, v0 = lane < nvec;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    for (int g0 = 0; g0 < nrows; g0 += RS) {
+    while (true) {
       mbar_wait(&rg.full[rg.s], rg.ph);
-      const uint4 *st = reinterpret_cast<const uint4 *>(rg.ring + (size_t)rg.s * MK_STAGE_BYTES) + ks * nvec + lane;
-      for (int r = 0; r < RPW; r++) {
-        const uint4 *rowp = st + (size_t)(slot + r * slots) * segv;
-        const uint4 w0 = v0 ? rowp[0] : z, w1 = v1 ? rowp[32] : z, w2 = v2 ? rowp[64] : z, w3 = v3 ? rowp[96] : z;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, wf[8];
-        unpack8<T>(w0, wf);
-        a0 = fmaf(wf[0], xr[0][0], a0); a1 = fmaf(wf[1], xr[0][1], a1); a2 = fmaf(wf[2], xr[0][2], a2); a3 = fmaf(wf[3], xr[0][3], a3);
-        a0 = fmaf(wf[4], xr[0][4], a0); a1 = fmaf(wf[5], xr[0][5], a1); a2 = fmaf(wf[6], xr[0][6], a2); a3 = fmaf(wf[7], xr[0][7], a3);
-        unpack8<T>(w1, wf);
-        a0 = fmaf(wf[0], xr[1][0], a0); a1 = fmaf(wf[1], xr[1][1], a1); a2 = fmaf(wf[2], xr[1][2], a2); a3 = fmaf(wf[3], xr[1][3], a3);
-        a0 = fmaf(wf[4], xr[1][4], a0); a1 = fmaf(wf[5], xr[1][5], a1); a2 = fmaf(wf[6], xr[1][6], a2); a3 = fmaf(wf[7], xr[1][7], a3);
-        unpack8<T>(w2, wf);
-        a0 = fmaf(wf[0], xr[2][0], a0); a1 = fmaf(wf[1], xr[2][1], a1); a2 = fmaf(wf[2], xr[2][2], a2); a3 = fmaf(wf[3], xr[2][3], a3);
-        a0 = fmaf(wf[4], xr[2][4], a0); a1 = fmaf(wf[5], xr[2][5], a1); a2 = fmaf(wf[6], xr[2][6], a2); a3 = fmaf(wf[7], xr[2][7], a3);
-        unpack8<T>(w3, wf);
-        a0 = fmaf(wf[0], xr[3][0], a0); a1 = fmaf(wf[1], xr[3][1], a1); a2 = fmaf(wf[2], xr[3][2], a2); a3 = fmaf(wf[3], xr[3][3], a3);
-        a0 = fmaf(wf[4], xr[3][4], a0); a1 = fmaf(wf[5], xr[3][5], a1); a2 = fmaf(wf[6], xr[3][6], a2); a3 = fmaf(wf[7], xr[3][7], a3);
-        const float v = warp_sum((a0 + a1) + (a2 + a3));
-        const int rl = g0 + slot + r * slots;
-        if (lane == 0 && rl < nrows) partial[rl * WPR + ks] = v;
+      const int row = rg.stage_row[rg.s];
+      if (row >= 0) {
+        const uint4 *st = reinterpret_cast<const uint4 *>(rg.ring + (size_t)rg.s * MK_STAGE_BYTES) + ks * nvec + lane;
+        for (int r = 0; r < RPW; r++) {
+          const uint4 *rowp = st + (size_t)(slot + r * slots) * segv;
+          const uint4 w0 = v0 ? rowp[0] : z, w1 = v1 ? rowp[32] : z, w2 = v2 ? rowp[64] : z, w3 = v3 ? rowp[96] : z;
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, wf[8];
+          unpack8<T>(w0, wf);
+          a0 = fmaf(wf[0], xr[0][0], a0); a1 = fmaf(wf[1], xr[0][1], a1); a2 = fmaf(wf[2], xr[0][2], a2); a3 = fmaf(wf[3], xr[0][3], a3);
+          a0 = fmaf(wf[4], xr[0][4], a0); a1 = fmaf(wf[5], xr[0][5], a1); a2 = fmaf(wf[6], xr[0][6], a2); a3 = fmaf(wf[7], xr[0][7], a3);
+          unpack8<T>(w1, wf);
+          a0 = fmaf(wf[0], xr[1][0], a0); a1 = fmaf(wf[1], xr[1][1], a1); a2 = fmaf(wf[2], xr[1][2], a2); a3 = fmaf(wf[3], xr[1][3], a3);
+          a0 = fmaf(wf[4], xr[1][4], a0); a1 = fmaf(wf[5], xr[1][5], a1); a2 = fmaf(wf[6], xr[1][6], a2); a3 = fmaf(wf[7], xr[1][7], a3);
+          unpack8<T>(w2, wf);
+          a0 = fmaf(wf[0], xr[2][0], a0); a1 = fmaf(wf[1], xr[2][1], a1); a2 = fmaf(wf[2], xr[2][2], a2); a3 = fmaf(wf[3], xr[2][3], a3);
+          a0 = fmaf(wf[4], xr[2][4], a0); a1 = fmaf(wf[5], xr[2][5], a1); a2 = fmaf(wf[6], xr[2][6], a2); a3 = fmaf(wf[7], xr[2][7], a3);
+          unpack8<T>(w3, wf);
+          a0 = fmaf(wf[0], xr[3][0], a0); a1 = fmaf(wf[1], xr[3][1], a1); a2 = fmaf(wf[2], xr[3][2], a2); a3 = fmaf(wf[3], xr[3][3], a3);
+          a0 = fmaf(wf[4], xr[3][4], a0); a1 = fmaf(wf[5], xr[3][5], a1); a2 = fmaf(wf[6], xr[3][6], a2); a3 = fmaf(wf[7], xr[3][7], a3);
+          const float v = warp_sum((a0 + a1) + (a2 + a3));
+          if (lane == 0) partial[((size_t)nloc * RS + slot + r * slots) * WPR + ks] = v;  // rows past N: never read
+        }
+        if (ct == 0) loc_row[nloc] = row;
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&rg.empty[rg.s]);
       rg.advance();
+      if (row < 0) break;
+      nloc++;
     }
-  } else
-  for (int g0 = 0; g0 < nrows; g0 += RS) {
-    float acc[4][2];
+  } else {
+    int r1;
+    mk_rows(N, G, r0, r1);
+    nrows = r1 - r0;
+    for (int g0 = 0; g0 < nrows; g0 += RS) {
+      float acc[4][2];
 #pragma unroll
-    for (int r = 0; r < 4; r++) acc[r][0] = acc[r][1] = 0.f;
-    for (int j = 0; j < nchunk; j++) {
-      mbar_wait(&rg.full[rg.s], rg.ph);
-      const uint4 *st = reinterpret_cast<const uint4 *>(rg.ring + (size_t)rg.s * MK_STAGE_BYTES);
-      const uint4 *xc = xsv + (size_t)j * segv + ks * nvec;
+      for (int r = 0; r < 4; r++) acc[r][0] = acc[r][1] = 0.f;
+      for (int j = 0; j < nchunk; j++) {
+        mbar_wait(&rg.full[rg.s], rg.ph);
+        const uint4 *st = reinterpret_cast<const uint4 *>(rg.ring + (size_t)rg.s * MK_STAGE_BYTES);
+        const uint4 *xc = xsv + (size_t)j * segv + ks * nvec;
 #pragma unroll 2
-      for (int v = lane; v < nvec; v += 32) {
-        float xf[8];
-        unpack8<T>(xc[v], xf);
+        for (int v = lane; v < nvec; v += 32) {
+          float xf[8];
+          unpack8<T>(xc[v], xf);
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
-          if (r < RPW) {
-            float wf[8];
-            unpack8<T>(st[(size_t)(slot + r * slots) * segv + ks * nvec + v], wf);
+          for (int r = 0; r < 4; r++) {
+            if (r < RPW) {
+              float wf[8];
+              unpack8<T>(st[(size_t)(slot + r * slots) * segv + ks * nvec + v], wf);
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[r][i & 1] = fmaf(wf[i], xf[i], acc[r][i & 1]);
+              for (int i = 0; i < 8; i++) acc[r][i & 1] = fmaf(wf[i], xf[i], acc[r][i & 1]);
+            }
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&rg.empty[rg.s]);
+        rg.advance();
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&rg.empty[rg.s]);
-      rg.advance();
-    }
 #pragma unroll
-    for (int r = 0; r < 4; r++) {
-      if (r < RPW) {
-        const float v = warp_sum(acc[r][0] + acc[r][1]);
-        const int rl = g0 + slot + r * slots;
-        if (lane == 0 && rl < nrows) partial[rl * WPR + ks] = v;
+      for (int r = 0; r < 4; r++) {
+        if (r < RPW) {
+          const float v = warp_sum(acc[r][0] + acc[r][1]);
+          const int rl = g0 + slot + r * slots;
+          if (lane == 0 && rl < nrows) partial[rl * WPR + ks] = v;
+        }
       }
     }
   }
   named_bar_sync(1, MK_CT);
-  auto row_sum = [&](int rl) {
-    float s = 0.f;
-    for (int w = 0; w < WPR; w++) s += partial[rl * WPR + w];
-    return rnd<T>(s);
+  // local row index li -> global row (dynamic: group list; static: contiguous range)
+  const int n_local = dyn ? nloc * RS : nrows;
+  auto row_of = [&](int li) { return dyn ? loc_row[li / RS] + li % RS : r0 + li; };
+  auto row_sum = [&](int li) {
+    float sum = 0.f;
+    for (int w = 0; w < WPR; w++) sum += partial[(size_t)li * WPR + w];
+    return rnd<T>(sum);
   };
   T *out = reinterpret_cast<T *>(e.out);
   if (EPI == EPI_PLAIN) {
     const T *bias = reinterpret_cast<const T *>(e.bias);
-    for (int rl = ct; rl < nrows; rl += MK_CT) {
-      float v = row_sum(rl);
-      if (bias) v = rnd<T>(v + DT<T>::to_f(bias[r0 + rl]));
-      out[r0 + rl] = DT<T>::from_f(v);
+    for (int li = ct; li < n_local; li += MK_CT) {
+      const int row = row_of(li);
+      if (row >= N) continue;
+      float v = row_sum(li);
+      if (bias) v = rnd<T>(v + DT<T>::to_f(bias[row]));
+      out[row] = DT<T>::from_f(v);
     }
   } else if (EPI == EPI_RESIDUAL) {
     const T *res = reinterpret_cast<const T *>(e.residual);
-    for (int rl = ct; rl < nrows; rl += MK_CT) {
-      const float v = row_sum(rl);
-      out[r0 + rl] = DT<T>::from_f(v + DT<T>::to_f(ldcg_T<T>(res + r0 + rl)));
+    for (int li = ct; li < n_local; li += MK_CT) {
+      const int row = row_of(li);
+      if (row >= N) continue;
+      const float v = row_sum(li);
+      out[row] = DT<T>::from_f(v + DT<T>::to_f(ldcg_T<T>(res + row)));
     }
   } else if (EPI == EPI_SWIGLU) {
-    for (int p = ct; p < nrows / 2; p += MK_CT) {
+    for (int p = ct; p < n_local / 2; p += MK_CT) {
+      const int row = row_of(2 * p);
+      if (row >= N) continue;
       const float gte = row_sum(2 * p), up = row_sum(2 * p + 1);
       const float sl = rnd<T>(gte / (1.0f + expf(-gte)));
-      out[r0 / 2 + p] = DT<T>::from_f(sl * up);
+      out[row / 2] = DT<T>::from_f(sl * up);
     }
   } else {
     float best = -INFINITY;
     int bidx = 0x7fffffff;
-    for (int rl = ct; rl < nrows; rl += MK_CT) {
-      const float v = row_sum(rl);
-      if (out) out[r0 + rl] = DT<T>::from_f(v);
-      if (v > best) { best = v; bidx = r0 + rl; }
+    for (int li = ct; li < n_local; li += MK_CT) {
+      const int row = row_of(li);
+      if (row >= N) continue;
+      const float v = row_sum(li);
+      if (out) out[row] = DT<T>::from_f(v);
+      if (v > best || (v == best && row < bidx)) { best = v; bidx = row; }  // first maximum wins
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -699,11 +774,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
   off = (off + 15) & ~(size_t)15;
   float *partial = reinterpret_cast<float *>(smem_raw + off);
   off += (size_t)a.partial_floats * 4;  // sized by the host: max rows x slices over all GEMV types
+  int *loc_row = reinterpret_cast<int *>(smem_raw + off);
+  off += (size_t)a.max_groups * 4;
   float *scratch = reinterpret_cast<float *>(smem_raw + off);
   off += 128 * 4;
   off = (off + 7) & ~(size_t)7;
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + off);
   uint64_t *empty = full + MK_MAX_STAGES;
+  int *stage_row = reinterpret_cast<int *>(empty + MK_MAX_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -715,21 +793,25 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
   }
   __syncthreads();
   const int pos = *a.d_pos;
-  MkRing rg{ring, full, empty, a.n_stages, 0, 0u};
+  MkRing rg{ring, full, empty, stage_row, a.n_stages, 0, 0u};
 
   if (warp == MK_CW) {
     // ================= producer: stream weights and K/V tiles through the whole phase list ==========
     if (lane == 0) {
       const uint64_t pol_w = policy_evict_first(), pol_kv = policy_evict_last();
+      auto produce = [&](const MkGeom &g, const void *W, int G, int phase) {
+        if (mk_is_dynamic(g)) mk_produce_gemv_dyn<T>(rg, g, W, a.tickets + phase, a.max_groups, pol_w);
+        else mk_produce_gemv<T>(rg, g, W, G, pol_w);
+      };
       for (int l = 0; l < a.n_layers; l++) {
         const MkLayer L = a.layers[l];
-        mk_produce_gemv<T>(rg, a.g_qkv, L.wqkv, 1, pol_w);
+        produce(a.g_qkv, L.wqkv, 1, 4 * l + 0);
         mk_produce_attn<T>(rg, a, L, pos, pol_kv);
-        mk_produce_gemv<T>(rg, a.g_o, L.wo, 1, pol_w);
-        mk_produce_gemv<T>(rg, a.g_gu, L.wgu, 2, pol_w);
-        mk_produce_gemv<T>(rg, a.g_down, L.wd, 1, pol_w);
+        produce(a.g_o, L.wo, 1, 4 * l + 1);
+        produce(a.g_gu, L.wgu, 2, 4 * l + 2);
+        produce(a.g_down, L.wd, 1, 4 * l + 3);
       }
-      if (a.has_head) mk_produce_gemv<T>(rg, a.g_head, a.lm_head, 1, pol_w);
+      if (a.has_head) produce(a.g_head, a.lm_head, 1, 4 * a.n_layers);
     }
     return;
   }
@@ -770,7 +852,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     e = MkEpi{};
     e.bias = L.bqkv;
     e.out = a.qkv;
-    mk_consume_gemv<T, EPI_PLAIN>(rg, a.g_qkv, xs, partial, scratch, e, ct, warp, lane);
+    mk_consume_gemv<T, EPI_PLAIN>(rg, a.g_qkv, xs, partial, loc_row, scratch, e, ct, warp, lane);
     gsync();
     // qk-norm, RoPE, KV append, attention
     mk_consume_attn<T, HD, G>(rg, a, L, pos, reinterpret_cast<unsigned char *>(xs), ct, warp, lane,
@@ -781,13 +863,13 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     e = MkEpi{};
     e.residual = cur;
     e.out = a.xb;
-    mk_consume_gemv<T, EPI_RESIDUAL>(rg, a.g_o, xs, partial, scratch, e, ct, warp, lane);
+    mk_consume_gemv<T, EPI_RESIDUAL>(rg, a.g_o, xs, partial, loc_row, scratch, e, ct, warp, lane);
     gsync();
     // rms_2 + gate_up + silu*mul
     mk_stage_x<T>(xs, a.xb, L.ln2, a.hidden, a.eps, scratch, ct, warp, lane);
     e = MkEpi{};
     e.out = a.mm;
-    mk_consume_gemv<T, EPI_SWIGLU>(rg, a.g_gu, xs, partial, scratch, e, ct, warp, lane);
+    mk_consume_gemv<T, EPI_SWIGLU>(rg, a.g_gu, xs, partial, loc_row, scratch, e, ct, warp, lane);
     if (a.trace && l == 1 && ct == 0) {
       unsigned long long t;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -804,7 +886,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     e = MkEpi{};
     e.residual = a.xb;
     e.out = dst;
-    mk_consume_gemv<T, EPI_RESIDUAL>(rg, a.g_down, xs, partial, scratch, e, ct, warp, lane);
+    mk_consume_gemv<T, EPI_RESIDUAL>(rg, a.g_down, xs, partial, loc_row, scratch, e, ct, warp, lane);
     if (l < a.n_layers - 1 || a.has_head) gsync();
     cur = dst;
   }
@@ -824,7 +906,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     e.d_step = a.d_step;
     e.gbar = a.gbar;
     e.next_start = start + (unsigned long long)nbar * gridDim.x;
-    mk_consume_gemv<T, EPI_ARGMAX>(rg, a.g_head, xs, partial, scratch, e, ct, warp, lane);
+    mk_consume_gemv<T, EPI_ARGMAX>(rg, a.g_head, xs, partial, loc_row, scratch, e, ct, warp, lane);
   }
   // bookkeeping without a head: CTA 0 only gets here after passing barriers that every CTA arrived at,
   // and every CTA read *d_pos and the epoch before its first barrier.
