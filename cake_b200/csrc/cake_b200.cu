@@ -677,6 +677,10 @@ static int plan_mega(cake_b200_ctx *c, cake_b200_cache *kc, bool with_head, MkPl
   a.partial_floats = pf;
   a.max_groups = mg;
   a.tickets = c->tickets;
+  {
+    const char *e = getenv("CAKE_B200_L2_PREFETCH");
+    a.l2_prefetch = (e && e[0] >= '1' && e[0] <= '2') ? e[0] - '0' : 0;
+  }
   a.hidden = f.hidden; a.inter = f.inter; a.n_heads = f.n_heads; a.n_kv = f.n_kv_heads; a.hd = f.head_dim;
   a.rot = c->rot; a.cap = kc ? kc->cap : 0; a.nsplit = c->nsplit; a.eps = f.rms_eps;
   a.scale = (float)(1.0 / sqrt((double)f.head_dim));

@@ -63,6 +63,7 @@ struct MkArgs {
   int ring_cap;
   unsigned *tickets;          // [phase] work-claim counters, zeroed before every launch
   int max_groups;             // per-CTA cap of row groups in one phase (sizes the partial-sum scratch)
+  int l2_prefetch;            // experimental (CAKE_B200_L2_PREFETCH=1): producer prefetches its future rows into L2
   unsigned long long *trace;  // optional: %globaltimer stamps of CTA 0 at phase boundaries (profiling aid)
 };
 
@@ -127,9 +128,65 @@ __device__ __forceinline__ MkSplit mk_split(const MkGeom &g) {
 }
 __device__ __forceinline__ bool mk_is_dynamic(const MkGeom &g) { return g.K == g.KC && (g.KC / 8) / g.WPR <= 128; }
 
+// L2 prefetch cursor.  HBM idles whenever the consumers sit in a grid barrier or in the attention phase and the
+// shared-memory ring is full (~20 us per layer).  The producer therefore also walks its OWN future static row
+// groups — across phase and layer boundaries — MK_PF_AHEAD groups ahead of the load cursor and issues
+// cp.async.bulk.prefetch.L2 for them: the bytes stream into the 126 MB L2 during those windows and the later
+// TMA loads hit L2.  ~14 x 32 KB x 148 CTAs = 66 MB in flight.
+constexpr int MK_PF_AHEAD = 14;
+struct MkPrefetch {
+  const MkArgs *a;
+  int l, ph, grp;  // layer, phase within the layer (0 qkv, 1 o, 2 gate_up, 3 down; l == n_layers: head), next group
+  int es;
+  __device__ __forceinline__ bool phase(const MkGeom *&g, const void *&W) const {
+    if (l < a->n_layers) {
+      const MkLayer &L = a->layers[l];
+      g = ph == 0 ? &a->g_qkv : ph == 1 ? &a->g_o : ph == 2 ? &a->g_gu : &a->g_down;
+      W = ph == 0 ? L.wqkv : ph == 1 ? L.wo : ph == 2 ? L.wgu : L.wd;
+      return true;
+    }
+    if (l == a->n_layers && a->has_head && ph == 0) { g = &a->g_head; W = a->lm_head; return true; }
+    return false;
+  }
+  __device__ __forceinline__ void step() {  // prefetch one more static group of this CTA, if any is left
+    while (true) {
+      const MkGeom *g;
+      const void *W;
+      if (!phase(g, W)) return;
+      if (mk_is_dynamic(*g)) {
+        const MkSplit sp = mk_split(*g);
+        if (grp < sp.sg) {
+          const int row = ((int)blockIdx.x * sp.sg + grp) * g->RS;
+          const size_t rowb = (size_t)g->K * es;
+          const unsigned bytes = (unsigned)(min(g->RS, g->N - row) * rowb);
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char *>(W) + (size_t)row * rowb), "r"(bytes) : "memory");
+          grp++;
+          return;
+        }
+      }
+      grp = 0;
+      if (l < a->n_layers && ph < 3) ph++;
+      else { l++; ph = 0; }
+    }
+  }
+};
+
+// Targeted variant (l2_prefetch == 2): only while HBM is otherwise idle — right after the attention K/V tiles were
+// issued — pull this CTA's static rows of the following GEMV phases into L2.
+__device__ __forceinline__ void mk_prefetch_static(const MkGeom &g, const void *W, int es, int first, int count) {
+  if (!mk_is_dynamic(g)) return;
+  const MkSplit sp = mk_split(g);
+  const size_t rowb = (size_t)g.K * es;
+  for (int i = first; i < sp.sg && i < first + count; i++) {
+    const int row = ((int)blockIdx.x * sp.sg + i) * g.RS;
+    const unsigned bytes = (unsigned)(min(g.RS, g.N - row) * rowb);
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const unsigned char *>(W) + (size_t)row * rowb), "r"(bytes) : "memory");
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void mk_produce_gemv_dyn(MkRing &rg, const MkGeom &g, const void *W, unsigned *ticket, int max_groups,
-                                                    uint64_t pol) {
+                                                    uint64_t pol, MkPrefetch &pf) {
   constexpr int es = sizeof(T);
   const MkSplit sp = mk_split(g);
   const size_t rowb = (size_t)g.K * es;
@@ -144,7 +201,10 @@ __device__ __forceinline__ void mk_produce_gemv_dyn(MkRing &rg, const MkGeom &g,
     rg.advance();
     issued++;
   };
-  for (int grp = blockIdx.x * sp.sg; grp < (int)(blockIdx.x + 1) * sp.sg; grp++) issue(grp);
+  for (int grp = blockIdx.x * sp.sg; grp < (int)(blockIdx.x + 1) * sp.sg; grp++) {
+    issue(grp);
+    if (pf.a->l2_prefetch == 1) pf.step();  // keep the L2 prefetch MK_PF_AHEAD static groups ahead of the load cursor
+  }
   if (sp.pool_start < sp.n_groups && issued < max_groups) {
     unsigned next = atomicAdd(ticket, 1u);
     while (sp.pool_start + (int)next < sp.n_groups) {
@@ -799,14 +859,20 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     // ================= producer: stream weights and K/V tiles through the whole phase list ==========
     if (lane == 0) {
       const uint64_t pol_w = policy_evict_first(), pol_kv = policy_evict_last();
+      MkPrefetch pf{&a, 0, 0, 0, (int)sizeof(T)};
+      if (a.l2_prefetch == 1) for (int i = 0; i < MK_PF_AHEAD; i++) pf.step();
       auto produce = [&](const MkGeom &g, const void *W, int G, int phase) {
-        if (mk_is_dynamic(g)) mk_produce_gemv_dyn<T>(rg, g, W, a.tickets + phase, a.max_groups, pol_w);
+        if (mk_is_dynamic(g)) mk_produce_gemv_dyn<T>(rg, g, W, a.tickets + phase, a.max_groups, pol_w, pf);
         else mk_produce_gemv<T>(rg, g, W, G, pol_w);
       };
       for (int l = 0; l < a.n_layers; l++) {
         const MkLayer L = a.layers[l];
         produce(a.g_qkv, L.wqkv, 1, 4 * l + 0);
         mk_produce_attn<T>(rg, a, L, pos, pol_kv);
+        if (a.l2_prefetch == 2) {
+          mk_prefetch_static(a.g_o, L.wo, (int)sizeof(T), 0, 1 << 20);
+          mk_prefetch_static(a.g_gu, L.wgu, (int)sizeof(T), 0, 10);
+        }
         produce(a.g_o, L.wo, 1, 4 * l + 1);
         produce(a.g_gu, L.wgu, 2, 4 * l + 2);
         produce(a.g_down, L.wd, 1, 4 * l + 3);
