@@ -28,7 +28,9 @@ def _nccl_include() -> str:
 
 def sources():
     d = os.path.join(HERE, "csrc")
+    h = os.path.join(HERE, "host")
     return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cu", ".cuh"))] + \
+           [os.path.join(h, f) for f in sorted(os.listdir(h)) if f.endswith((".cc", ".hpp"))] + \
            [os.path.join(ROOT, "include", "cake_b200.h")]
 
 
@@ -51,7 +53,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     subprocess.check_call(cmd)
+    build_host()
     return SO
+
+
+def build_host() -> str:
+    """The C++ host side (cake_b200/host/cake_host.hpp) + its `cake_run` driver, linked against the C ABI."""
+    out = os.path.join(HERE, "host", "cake_run")
+    src = os.path.join(HERE, "host", "cake_run.cc")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-o", out, src, "-I", os.path.join(ROOT, "include"),
+                           "-L", HERE, "-lcake_b200", "-Wl,-rpath,$ORIGIN/.."])
+    return out
 
 
 if __name__ == "__main__":

@@ -24,6 +24,8 @@ SYMBOLS = [
     ("cake_b200_sync", _I, [_VP]),
     ("cake_b200_stream", _VP, [_VP]),
     ("cake_b200_launch_count", _I, [_VP, POINTER(c_uint64)]),
+    ("cake_b200_dev_alloc", _I, [_VP, c_size_t, POINTER(_VP)]),
+    ("cake_b200_dev_free", _I, [_VP, _VP]),
     ("cake_b200_block_load", _I, [_VP, _I] + [_VP] * 14 + [POINTER(_VP)]),
     ("cake_b200_block_free", None, [_VP]),
     ("cake_b200_block_layer", _I, [_VP]),

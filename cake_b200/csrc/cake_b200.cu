@@ -422,6 +422,20 @@ extern "C" int cake_b200_launch_count(cake_b200_ctx *c, uint64_t *k) {
   return CAKE_B200_OK;
 }
 
+extern "C" int cake_b200_dev_alloc(cake_b200_ctx *c, size_t bytes, void **out) {
+  if (!c || !out) return fail(CAKE_B200_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaMalloc(out, bytes ? bytes : 16));
+  return CAKE_B200_OK;
+}
+extern "C" int cake_b200_dev_free(cake_b200_ctx *c, void *p) {
+  if (!c) return fail(CAKE_B200_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  CU(cudaFree(p));
+  return CAKE_B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------ blocks
 static int upload(void **dst, const void *src, size_t bytes) {
   CU(cudaMalloc(dst, bytes + 16));

@@ -861,9 +861,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
       const uint64_t pol_w = policy_evict_first(), pol_kv = policy_evict_last();
       MkPrefetch pf{&a, 0, 0, 0, (int)sizeof(T)};
       if (a.l2_prefetch == 1) for (int i = 0; i < MK_PF_AHEAD; i++) pf.step();
-      auto produce = [&](const MkGeom &g, const void *W, int G, int phase) {
+      auto produce = [&](const MkGeom &g, const void *W, int gran, int phase) {
         if (mk_is_dynamic(g)) mk_produce_gemv_dyn<T>(rg, g, W, a.tickets + phase, a.max_groups, pol_w, pf);
-        else mk_produce_gemv<T>(rg, g, W, G, pol_w);
+        else mk_produce_gemv<T>(rg, g, W, gran, pol_w);
       };
       for (int l = 0; l < a.n_layers; l++) {
         const MkLayer L = a.layers[l];

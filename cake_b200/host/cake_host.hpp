@@ -1,0 +1,493 @@
+// cake_host.hpp — C++ host side above the C ABI (include/cake_b200.h), mirroring the reference's interface for the
+// block-forward path with the reference's names, argument meaning and error behaviour:
+//
+//   Forwarder        cake-core/src/cake/mod.rs:510-556      load / forward / forward_mut / forward_batch / goodbye /
+//                                                            layer_name / ident
+//   Transformer      models/common/transformer.rs:14-150    the local block (here backed by a cake_b200_block)
+//   Cache            models/common/cache.rs:9-254           clear / as_new
+//   Context          cake/mod.rs:41-65                      config, dtype, device, var_builder, cache
+//   VarBuilder       utils/mod.rs:255-384                   mmapped safetensors (single file or index.json shards)
+//   TextModelBase    models/common/text_model.rs:133-530    load / forward / prepare_prompt / next_token / reset
+//   Master           cake/sharding/master.rs:14-191         generate_text and its tok/s definition
+//
+// cake is Rust and no Rust toolchain exists in the authoring environment, so the compiled host side is C++.
+// Errors are exceptions carrying cake_b200_last_error() (the reference returns anyhow::Result with context).
+#pragma once
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/cake_b200.h"
+
+namespace cake_host {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+inline void check(int rc, const std::string &what) {
+  if (rc != CAKE_B200_OK) throw Error(what + ": " + cake_b200_last_error());
+}
+
+// ---------------------------------------------------------------------------------------------- tiny JSON
+struct Json {
+  enum Kind { Null, Bool, Num, Str, Arr, Obj } kind = Null;
+  double num = 0;
+  bool b = false;
+  std::string str;
+  std::vector<Json> arr;
+  std::vector<std::pair<std::string, Json>> obj;
+  const Json *get(const std::string &k) const {
+    for (auto &kv : obj)
+      if (kv.first == k) return &kv.second;
+    return nullptr;
+  }
+  double number(const std::string &k, double dflt) const {
+    const Json *j = get(k);
+    return (j && j->kind == Num) ? j->num : dflt;
+  }
+  bool boolean(const std::string &k, bool dflt) const {
+    const Json *j = get(k);
+    return (j && j->kind == Bool) ? j->b : dflt;
+  }
+};
+class JsonParser {
+  const char *p, *e;
+  void ws() { while (p < e && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r')) p++; }
+  [[noreturn]] void fail(const char *m) { throw Error(std::string("json: ") + m); }
+  std::string string() {
+    if (*p != '"') fail("expected string");
+    p++;
+    std::string s;
+    while (p < e && *p != '"') {
+      if (*p == '\\' && p + 1 < e) {
+        p++;
+        s += (*p == 'n') ? '\n' : (*p == 't') ? '\t' : *p;
+      } else s += *p;
+      p++;
+    }
+    p++;
+    return s;
+  }
+ public:
+  JsonParser(const char *b, size_t n) : p(b), e(b + n) {}
+  Json value() {
+    ws();
+    Json j;
+    if (p >= e) fail("eof");
+    if (*p == '{') {
+      j.kind = Json::Obj;
+      p++;
+      ws();
+      while (*p != '}') {
+        ws();
+        std::string k = string();
+        ws();
+        if (*p != ':') fail("expected ':'");
+        p++;
+        j.obj.emplace_back(k, value());
+        ws();
+        if (*p == ',') p++;
+        ws();
+      }
+      p++;
+    } else if (*p == '[') {
+      j.kind = Json::Arr;
+      p++;
+      ws();
+      while (*p != ']') {
+        j.arr.push_back(value());
+        ws();
+        if (*p == ',') p++;
+        ws();
+      }
+      p++;
+    } else if (*p == '"') {
+      j.kind = Json::Str;
+      j.str = string();
+    } else if (!strncmp(p, "true", 4)) { j.kind = Json::Bool; j.b = true; p += 4;
+    } else if (!strncmp(p, "false", 5)) { j.kind = Json::Bool; p += 5;
+    } else if (!strncmp(p, "null", 4)) { p += 4;
+    } else {
+      char *end;
+      j.kind = Json::Num;
+      j.num = strtod(p, &end);
+      if (end == p) fail("bad number");
+      p = end;
+    }
+    return j;
+  }
+};
+inline std::string slurp(const std::string &path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) throw Error("can't read " + path);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return ss.str();
+}
+
+// ---------------------------------------------------------------------------------------------- config
+// models/common/config.rs:87-150 via LlamaConfig / Qwen3Config::into_config (llama3/config.rs:62-98, qwen3/config.rs:55-93)
+struct Config {
+  cake_b200_config c{};
+  std::string model_prefix = "model";
+  std::vector<uint32_t> eos;
+  std::string arch;
+  static Config from_path(const std::string &path, int dtype, int max_seq_override = 0) {
+    std::string txt = slurp(path);
+    Json j = JsonParser(txt.data(), txt.size()).value();
+    Config k;
+    if (const Json *a = j.get("architectures"))
+      if (!a->arr.empty()) k.arch = a->arr[0].str;  // config.rs detect_text_model_arch
+    if (!(k.arch.empty() || k.arch == "LlamaForCausalLM" || k.arch == "Qwen3ForCausalLM"))
+      throw Error("architecture " + k.arch + " is outside the block-forward path built here");
+    auto &c = k.c;
+    c.hidden = (int)j.number("hidden_size", 0);
+    c.inter = (int)j.number("intermediate_size", 0);
+    c.vocab = (int)j.number("vocab_size", 0);
+    c.n_layers = (int)j.number("num_hidden_layers", 0);
+    c.n_heads = (int)j.number("num_attention_heads", 0);
+    c.n_kv_heads = (int)j.number("num_key_value_heads", c.n_heads);
+    c.head_dim = (int)j.number("head_dim", c.n_heads ? c.hidden / c.n_heads : 0);
+    c.rms_eps = (float)j.number("rms_norm_eps", 1e-5);
+    c.rope_theta = (float)j.number("rope_theta", 10000.0);
+    c.partial_rotary = 1.0f;
+    c.max_seq = max_seq_override ? max_seq_override : (int)j.number("max_position_embeddings", 4096);
+    c.tie_embeddings = j.boolean("tie_word_embeddings", false);
+    c.qk_norm = (k.arch == "Qwen3ForCausalLM");
+    c.qkv_bias = 0;
+    c.dtype = dtype;
+    c.rope_factor = 1.f; c.rope_low = 1.f; c.rope_high = 4.f;
+    if (const Json *rs = j.get("rope_scaling")) {
+      if (rs->kind == Json::Obj) {
+        const Json *t = rs->get("rope_type");
+        const int orig = (int)rs->number("original_max_position_embeddings", 0);
+        if (t && t->str == "llama3" && orig > 0) {  // cache.rs:49-80
+          c.rope_llama3 = 1;
+          c.rope_factor = (float)rs->number("factor", 1.0);
+          c.rope_low = (float)rs->number("low_freq_factor", 1.0);
+          c.rope_high = (float)rs->number("high_freq_factor", 4.0);
+          c.rope_orig_max = orig;
+        }
+      }
+    }
+    if (const Json *e = j.get("eos_token_id")) {  // config.rs:6-19 EosTokenId single | array
+      if (e->kind == Json::Num) k.eos.push_back((uint32_t)e->num);
+      for (auto &x : e->arr) k.eos.push_back((uint32_t)x.num);
+    }
+    return k;
+  }
+  bool is_eos(uint32_t t) const {
+    for (auto x : eos)
+      if (x == t) return true;
+    return false;
+  }
+  std::string layer_name(int i) const { return model_prefix + ".layers." + std::to_string(i); }  // text_model.rs:205
+};
+
+// ---------------------------------------------------------------------------------------------- VarBuilder
+// mmapped safetensors: 8-byte little-endian header length, JSON {name: {dtype, shape, data_offsets}}, raw data
+// (utils/mod.rs:255-272 single file; :333-384 model.safetensors.index.json -> the shards that hold the names).
+struct TensorView {
+  const void *data = nullptr;
+  std::string dtype;
+  std::vector<int64_t> shape;
+  size_t bytes = 0;
+};
+class VarBuilder {
+  struct Map { void *p; size_t n; };
+  std::vector<Map> maps_;
+  std::map<std::string, TensorView> t_;
+  void add_file(const std::string &path) {
+    int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) throw Error("can't open " + path);
+    struct stat st;
+    fstat(fd, &st);
+    void *p = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) throw Error("mmap failed for " + path);
+    maps_.push_back({p, (size_t)st.st_size});
+    uint64_t hl;
+    memcpy(&hl, p, 8);
+    const char *hdr = (const char *)p + 8;
+    Json j = JsonParser(hdr, (size_t)hl).value();
+    const char *base = hdr + hl;
+    for (auto &kv : j.obj) {
+      if (kv.first == "__metadata__") continue;
+      TensorView v;
+      v.dtype = kv.second.get("dtype")->str;
+      for (auto &d : kv.second.get("shape")->arr) v.shape.push_back((int64_t)d.num);
+      const auto &off = kv.second.get("data_offsets")->arr;
+      v.data = base + (size_t)off[0].num;
+      v.bytes = (size_t)(off[1].num - off[0].num);
+      t_[kv.first] = v;
+    }
+  }
+ public:
+  explicit VarBuilder(const std::string &dir) {
+    const std::string idx = dir + "/model.safetensors.index.json";
+    if (access(idx.c_str(), R_OK) == 0) {
+      std::string txt = slurp(idx);
+      Json j = JsonParser(txt.data(), txt.size()).value();
+      std::map<std::string, bool> files;
+      if (const Json *wm = j.get("weight_map"))
+        for (auto &kv : wm->obj) files[kv.second.str] = true;
+      for (auto &f : files) add_file(dir + "/" + f.first);
+    } else {
+      add_file(dir + "/model.safetensors");
+    }
+  }
+  ~VarBuilder() {
+    for (auto &m : maps_) munmap(m.p, m.n);
+  }
+  VarBuilder(const VarBuilder &) = delete;
+  const TensorView *find(const std::string &name) const {
+    auto it = t_.find(name);
+    return it == t_.end() ? nullptr : &it->second;
+  }
+  const void *get(const std::string &name, const std::string &want_dtype) const {
+    const TensorView *v = find(name);
+    if (!v) throw Error("cannot find tensor " + name);  // candle VarBuilder error text
+    if (v->dtype != want_dtype) throw Error("tensor " + name + " is " + v->dtype + ", expected " + want_dtype);
+    return v->data;
+  }
+  const void *get_opt(const std::string &name, const std::string &want_dtype) const { return find(name) ? get(name, want_dtype) : nullptr; }
+};
+
+// ---------------------------------------------------------------------------------------------- Cache / Context
+struct Context;
+class Cache {  // cache.rs:9
+ public:
+  cake_b200_cache *h = nullptr;
+  cake_b200_ctx *ctx;
+  int batch, max_seq;
+  Cache(cake_b200_ctx *c, int b, int ms) : ctx(c), batch(b), max_seq(ms) { check(cake_b200_cache_create(c, b, ms, &h), "cache"); }
+  ~Cache() { cake_b200_cache_free(h); }
+  Cache(const Cache &) = delete;
+  void clear() { check(cake_b200_cache_clear(h), "cache.clear"); }                          // cache.rs:247-253
+  std::unique_ptr<Cache> as_new() const { return std::make_unique<Cache>(ctx, batch, max_seq); }  // cache.rs:241-245
+  int len(int block_idx) const { return cake_b200_cache_len(h, block_idx); }
+};
+
+struct Context {  // cake/mod.rs:41-65
+  Config config;
+  std::unique_ptr<VarBuilder> var_builder;
+  cake_b200_ctx *h = nullptr;
+  std::unique_ptr<Cache> cache;
+  std::string dtype_name;
+  Context(const std::string &model_dir, int device, int dtype, int max_seq = 0)
+      : config(Config::from_path(model_dir + "/config.json", dtype, max_seq)), var_builder(new VarBuilder(model_dir)) {
+    dtype_name = dtype == CAKE_B200_BF16 ? "BF16" : "F16";
+    check(cake_b200_ctx_create(device, &config.c, &h), "ctx_create");
+    cache.reset(new Cache(h, 1, config.c.max_seq));
+  }
+  ~Context() {
+    cache.reset();
+    if (h) cake_b200_ctx_destroy(h);
+  }
+  Context(const Context &) = delete;
+};
+
+// ---------------------------------------------------------------------------------------------- Forwarder
+class Forwarder {  // cake/mod.rs:510-556
+ public:
+  virtual ~Forwarder() = default;
+  // x, y: host buffers (batch, seq, hidden) in the model dtype; the _dev variants take device pointers
+  virtual void forward(const void *x_host, void *y_host, int batch, int seq, size_t index_pos, size_t block_idx, Context &ctx) = 0;
+  virtual void forward_mut(const void *x_host, void *y_host, int batch, int seq, size_t index_pos, size_t block_idx, Context &ctx) {
+    forward(x_host, y_host, batch, seq, index_pos, block_idx, ctx);
+  }
+  virtual void goodbye() {}
+  virtual const std::string &layer_name() const = 0;
+  virtual std::string ident() const { return "local"; }
+  virtual cake_b200_block *handle() const { return nullptr; }
+};
+
+class Transformer : public Forwarder {  // transformer.rs:14-150, backed by the CUDA block
+  std::string name_;
+  cake_b200_block *h_ = nullptr;
+ public:
+  static std::unique_ptr<Transformer> load(const std::string &name, Context &ctx) {  // transformer.rs:79-101
+    const VarBuilder &vb = *ctx.var_builder;
+    const std::string &dt = ctx.dtype_name;
+    auto g = [&](const char *s) { return vb.get(name + "." + s, dt); };
+    auto o = [&](const char *s) { return vb.get_opt(name + "." + s, dt); };
+    int layer = std::stoi(name.substr(name.rfind('.') + 1));
+    auto t = std::unique_ptr<Transformer>(new Transformer());
+    t->name_ = name;
+    check(cake_b200_block_load(ctx.h, layer, g("self_attn.q_proj.weight"), g("self_attn.k_proj.weight"), g("self_attn.v_proj.weight"),
+                               g("self_attn.o_proj.weight"), g("mlp.gate_proj.weight"), g("mlp.up_proj.weight"), g("mlp.down_proj.weight"),
+                               g("input_layernorm.weight"), g("post_attention_layernorm.weight"),
+                               ctx.config.c.qkv_bias ? g("self_attn.q_proj.bias") : nullptr, ctx.config.c.qkv_bias ? g("self_attn.k_proj.bias") : nullptr,
+                               ctx.config.c.qkv_bias ? g("self_attn.v_proj.bias") : nullptr,
+                               ctx.config.c.qk_norm ? g("self_attn.q_norm.weight") : o("self_attn.q_norm.weight"),
+                               ctx.config.c.qk_norm ? g("self_attn.k_norm.weight") : o("self_attn.k_norm.weight"), &t->h_),
+          name);
+    return t;
+  }
+  ~Transformer() override { cake_b200_block_free(h_); }
+  void forward(const void *x, void *y, int batch, int seq, size_t index_pos, size_t block_idx, Context &ctx) override {
+    if (!ctx.cache) throw Error("No cache specified");  // transformer.rs:120
+    cake_b200_block *blocks[1] = {h_};
+    int idx[1] = {(int)block_idx};
+    check(cake_b200_forward_batch_host(ctx.h, blocks, idx, 1, ctx.cache->h, x, y, batch, seq, (int)index_pos), "attention/mlp " + name_);
+  }
+  const std::string &layer_name() const override { return name_; }
+  cake_b200_block *handle() const override { return h_; }
+};
+
+// ---------------------------------------------------------------------------------------------- TextModelBase / Master
+struct Token {
+  uint32_t id;
+  bool is_end_of_stream;
+};
+
+class TextModelBase {  // text_model.rs:133-530 for token-id prompts
+ public:
+  Context &ctx;
+  std::vector<std::unique_ptr<Forwarder>> blocks;
+  std::vector<uint32_t> tokens;
+  size_t index_pos = 0, generated = 0, prompt_len = 0;
+  float repeat_penalty = 1.0f;
+  size_t repeat_last_n = 128;
+  bool graph_ready = false;
+
+  explicit TextModelBase(Context &c) : ctx(c) {}
+  static std::unique_ptr<TextModelBase> load(Context &ctx) {  // text_model.rs:150-264 (all layers local)
+    auto m = std::make_unique<TextModelBase>(ctx);
+    const VarBuilder &vb = *ctx.var_builder;
+    const std::string p = ctx.config.model_prefix, &dt = ctx.dtype_name;
+    check(cake_b200_head_load(ctx.h, vb.get(p + ".embed_tokens.weight", dt), vb.get(p + ".norm.weight", dt),
+                              ctx.config.c.tie_embeddings ? nullptr : vb.get("lm_head.weight", dt)),
+          "head_load");
+    for (int i = 0; i < ctx.config.c.n_layers; i++) m->blocks.push_back(Transformer::load(ctx.config.layer_name(i), ctx));
+    return m;
+  }
+  std::vector<cake_b200_block *> handles() const {
+    std::vector<cake_b200_block *> v;
+    for (auto &b : blocks) v.push_back(b->handle());
+    return v;
+  }
+  void prepare_prompt(const std::vector<uint32_t> &ids) {  // text_model.rs:371-395
+    tokens = ids;
+    ctx.cache->clear();
+    index_pos = 0;
+    prompt_len = ids.size();
+    graph_ready = false;
+  }
+  // text_model.rs:397-495.  index 0: whole prompt at position 0 through the block walk (prefill kernels);
+  // index > 0: the greedy path replays the decode graph (one persistent kernel), other settings go through logits.
+  Token next_token(size_t index) {
+    const auto &c = ctx.config.c;
+    uint32_t next = 0;
+    if (index == 0 || repeat_penalty != 1.0f) {
+      std::vector<uint32_t> in = (index > 0) ? std::vector<uint32_t>{tokens.back()} : tokens;
+      const size_t pos = (index > 0) ? index_pos : 0;
+      if (in.empty()) throw Error("empty prompt");
+      (void)c;
+      // embed -> contiguous local blocks -> ln_f / lm_head, all on the device (text_model.rs:266-352)
+      check(cake_b200_embed(ctx.h, in.data(), 1, (int)in.size(), scratch(in.size())), "embedding");
+      auto hs = handles();
+      std::vector<int> idx(hs.size());
+      for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+      check(cake_b200_forward_batch(ctx.h, hs.data(), idx.data(), (int)hs.size(), ctx.cache->h, scratch(in.size()), scratch(in.size()), 1,
+                                    (int)in.size(), (int)pos),
+            "forward");
+      index_pos += in.size();
+      if (repeat_penalty == 1.0f) {
+        check(cake_b200_logits(ctx.h, scratch(in.size()), 1, (int)in.size(), nullptr, &next), "lm_head");
+      } else {
+        check(cake_b200_logits(ctx.h, scratch(in.size()), 1, (int)in.size(), logits_dev(), nullptr), "lm_head");
+        const size_t ngen = tokens.size() - prompt_len, start = ngen > repeat_last_n ? ngen - repeat_last_n : 0;  // :435-452
+        check(cake_b200_repeat_penalty_argmax(ctx.h, logits_dev(), repeat_penalty, tokens.data() + prompt_len + start, (int)(ngen - start), &next),
+              "sample");
+      }
+    } else {
+      if (!graph_ready) {
+        auto hs = handles();
+        std::vector<int> idx(hs.size());
+        for (size_t i = 0; i < idx.size(); i++) idx[i] = (int)i;
+        check(cake_b200_decode_build(ctx.h, hs.data(), idx.data(), (int)hs.size(), ctx.cache->h, 0, 1), "decode_build");
+        check(cake_b200_decode_begin(ctx.h, tokens.back(), (int)index_pos), "decode_begin");
+        graph_ready = true;
+      }
+      check(cake_b200_decode_step_host(ctx.h, tokens.back(), &next), "decode_step");
+      index_pos += 1;
+    }
+    generated++;
+    tokens.push_back(next);
+    return Token{next, ctx.config.is_eos(next)};
+  }
+  void reset() {  // text_model.rs:497-515
+    tokens.clear();
+    ctx.cache->clear();
+    index_pos = generated = prompt_len = 0;
+    graph_ready = false;
+  }
+  void goodbye() {
+    for (auto &b : blocks) b->goodbye();
+  }
+  ~TextModelBase() { release_scratch(); }
+
+ private:
+  // device scratch for (seq, hidden) activations and (vocab) logits
+  void *scratch_ = nullptr, *logits_ = nullptr;
+  size_t scratch_rows_ = 0;
+  void *scratch(size_t rows) {
+    if (rows > scratch_rows_) {
+      check(cake_b200_sync(ctx.h), "sync");
+      if (scratch_) cake_b200_dev_free(ctx.h, scratch_);
+      check(cake_b200_dev_alloc(ctx.h, rows * (size_t)ctx.config.c.hidden * 2, &scratch_), "dev_alloc");
+      scratch_rows_ = rows;
+    }
+    return scratch_;
+  }
+  void *logits_dev() {
+    if (!logits_) check(cake_b200_dev_alloc(ctx.h, (size_t)ctx.config.c.vocab * 2, &logits_), "dev_alloc");
+    return logits_;
+  }
+  void release_scratch() {
+    if (scratch_) cake_b200_dev_free(ctx.h, scratch_);
+    if (logits_) cake_b200_dev_free(ctx.h, logits_);
+  }
+};
+
+class Master {  // sharding/master.rs:14-191
+ public:
+  TextModelBase &model;
+  explicit Master(TextModelBase &m) : model(m) {}
+  struct Result {
+    std::vector<uint32_t> tokens;
+    double tok_s;
+  };
+  // master.rs:109-168: tok/s = (generated - 1) / time since the first generated token
+  Result generate_text(const std::vector<uint32_t> &prompt, size_t sample_len, const std::function<void(const Token &)> &stream = nullptr) {
+    model.prepare_prompt(prompt);
+    Result r;
+    auto start = std::chrono::steady_clock::now();
+    for (size_t index = 0; index < sample_len; index++) {
+      if (index == 1) start = std::chrono::steady_clock::now();
+      Token t = model.next_token(index);
+      if (t.is_end_of_stream) break;
+      r.tokens.push_back(t.id);
+      if (stream) stream(t);
+    }
+    const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    r.tok_s = model.generated > 1 ? (double)(model.generated - 1) / dt : 0.0;
+    return r;
+  }
+};
+
+}  // namespace cake_host

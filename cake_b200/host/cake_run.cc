@@ -1,0 +1,50 @@
+// cake_run — minimal `cake run` for the block-forward path on a B200, built on cake_host.hpp (the C++ mirror of
+// cake's interface) and libcake_b200.so.  It takes token ids instead of text (tokenizer / chat template are outside
+// the path):   cake_run <model_dir> --prompt-ids 1,2,3 [-n 32] [--dtype bf16|f16] [--repeat-penalty 1.0]
+// <model_dir> holds config.json + model.safetensors (or model.safetensors.index.json + shards), HF layout.
+// Prints one line:  tokens: t0 t1 ...   and   tok/s as the reference defines it (master.rs:160-166).
+#include <cstdio>
+#include <cstdlib>
+
+#include "cake_host.hpp"
+
+using namespace cake_host;
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    fprintf(stderr, "usage: %s <model_dir> --prompt-ids a,b,c [-n N] [--dtype bf16|f16] [--repeat-penalty P] [--max-seq S]\n", argv[0]);
+    return 2;
+  }
+  std::string dir = argv[1];
+  std::vector<uint32_t> prompt;
+  size_t n = 32;
+  int dtype = CAKE_B200_BF16, max_seq = 0;
+  float rp = 1.0f;
+  for (int i = 2; i < argc; i++) {
+    std::string a = argv[i];
+    auto next = [&]() -> std::string { return i + 1 < argc ? std::string(argv[++i]) : std::string(); };
+    if (a == "--prompt-ids") {
+      std::stringstream ss(next());
+      std::string t;
+      while (std::getline(ss, t, ',')) prompt.push_back((uint32_t)std::stoul(t));
+    } else if (a == "-n") n = std::stoul(next());
+    else if (a == "--dtype") dtype = (next() == "f16") ? CAKE_B200_F16 : CAKE_B200_BF16;
+    else if (a == "--repeat-penalty") rp = std::stof(next());
+    else if (a == "--max-seq") max_seq = std::stoi(next());
+  }
+  try {
+    Context ctx(dir, 0, dtype, max_seq);
+    auto model = TextModelBase::load(ctx);
+    model->repeat_penalty = rp;
+    Master master(*model);
+    auto r = master.generate_text(prompt, n);
+    printf("tokens:");
+    for (auto t : r.tokens) printf(" %u", t);
+    printf("\ntok/s: %.2f\n", r.tok_s);
+    model.reset();
+  } catch (const std::exception &e) {
+    fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}

@@ -75,6 +75,10 @@ int cake_b200_sync(cake_b200_ctx *);              /* cudaStreamSynchronize(ctx s
 void *cake_b200_stream(cake_b200_ctx *);          /* the cudaStream_t everything is enqueued on */
 int cake_b200_launch_count(cake_b200_ctx *, uint64_t *kernels); /* kernels of this library launched so far (graph replays included) */
 
+/* Device buffers for hosts that have no allocator of their own (the C++ host, tests); synchronous. */
+int cake_b200_dev_alloc(cake_b200_ctx *, size_t bytes, void **out);
+int cake_b200_dev_free(cake_b200_ctx *, void *p);
+
 /* ---- blocks ----------------------------------------------------------------------------------- */
 /* Pointers are HF-layout [out,in] row-major tensors in dtype D, in host OR device memory (copied
  * with cudaMemcpyDefault).  bias / norm pointers may be NULL when the config does not use them.
