@@ -121,7 +121,7 @@ def cpu_reference_tok_s(cfg, n_tokens: int, budget_s: float, layers_cap=None) ->
     from cake_b200.synth import make_head, make_layer
     from oracle import oracle as O
 
-    torch.set_num_threads(1)  # torch only builds the inputs here; keep its OpenMP pool off the oracle's cores
+    O.lib().ora_set_num_threads(len(os.sched_getaffinity(0)))  # all host cores this process may use
     t_build = time.perf_counter()
     nl = cfg.num_hidden_layers
     n_sample = min(nl, layers_cap or nl)

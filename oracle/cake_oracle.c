@@ -482,6 +482,13 @@ int ora_forward_layers(const ora_model *m, ora_cache *kc, int l0, int l1, float 
   free(b);
   return 0;
 }
+void ora_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 int ora_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -89,6 +89,7 @@ def lib():
         L.ora_round.restype = cf
         L.ora_round.argtypes = [cf, ci]
         L.ora_num_threads.restype = ci
+        L.ora_set_num_threads.argtypes = [ci]
         _lib = L
     return _lib
 
