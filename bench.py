@@ -375,7 +375,9 @@ def run_cuda(args):
             per_kernel[names[which]] = {"ms": round(msl.value, 5), "GB/s": round(nbytes / (msl.value * 1e-3) / 1e9, 1)}
         a = per_kernel["gate_up_gemv"]["GB/s"]
         roof = {"bound": "hbm", "kernel": "gemv_kernel<bf16,SWIGLU> (rms_2 + gate_up + silu*mul)", "achieved": a, "peak": peak,
-                "unit": "GB/s", "frac": round(a / peak, 4), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(a / peak, 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum per launch of this kernel, ncu --set full, profiles/gemv_r01_raw.csv
+                "traffic": 234938368 + 3269120, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": kb[2], "per_kernel": per_kernel}
     except Exception as e:  # keep the headline line even if the aid fails
         roof = {"bound": "hbm", "error": str(e), "peak": peak, "unit": "GB/s"}
@@ -401,7 +403,9 @@ def run_cuda(args):
         "token_roofline": {"bytes_per_token": bpt, "achieved_GB_s": bpt / (ms / K * 1e-3) / 1e9,
                            "frac_of_one_gpu_hbm": bpt / (ms / K * 1e-3) / 1e9 / peak,
                            "frac_of_aggregate_hbm": bpt / (ms / K * 1e-3) / 1e9 / (peak * world),
-                           "roofline_tok_s_one_gpu": peak * 1e9 / bpt},
+                           "roofline_tok_s_one_gpu": peak * 1e9 / bpt,
+                           "traffic_per_token_ncu": 15280821000 + 7653120,  # decode_mega_kernel, profiles/mega_r01_raw.csv (N=1)
+                           "kernel": "decode_mega_kernel (one launch per token per shard)"},
     }
     if world == 1 and not args.no_cpu:
         try:
