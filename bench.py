@@ -27,8 +27,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 # Before numpy/torch load an OpenMP runtime: pin OpenMP threads.  The CPU legs (oracle port) otherwise lose
 # >10x to thread migration between torch's and the system's libgomp (1.2 GB/s unbound vs 68 GB/s bound).
+NCORES = len(os.sched_getaffinity(0))  # read before an OpenMP runtime pins the main thread to one core
 os.environ.setdefault("OMP_PROC_BIND", "true")
 os.environ.setdefault("OMP_WAIT_POLICY", "passive")
+os.environ.setdefault("OMP_NUM_THREADS", str(NCORES))
 
 METRIC = "decode tok/s (Llama-3-8B bf16, bs=1, 2k ctx)"
 CTX_LEN = 2048
@@ -109,7 +111,7 @@ def host_info() -> dict:
                     break
     except Exception:
         pass
-    return {"cpu": model, "logical_cores": len(os.sched_getaffinity(0))}
+    return {"cpu": model, "logical_cores": NCORES}
 
 
 def cpu_reference_tok_s(cfg, n_tokens: int, budget_s: float, layers_cap=None) -> dict:
@@ -121,7 +123,7 @@ def cpu_reference_tok_s(cfg, n_tokens: int, budget_s: float, layers_cap=None) ->
     from cake_b200.synth import make_head, make_layer
     from oracle import oracle as O
 
-    O.lib().ora_set_num_threads(len(os.sched_getaffinity(0)))  # all host cores this process may use
+    O.lib().ora_set_num_threads(NCORES)  # all host cores this process may use
     t_build = time.perf_counter()
     nl = cfg.num_hidden_layers
     n_sample = min(nl, layers_cap or nl)
