@@ -216,6 +216,8 @@ def run_cuda(args):
         if args.gpus > 1 and world == 1:
             raise SystemExit("launch with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N ...")
     torch.cuda.set_device(local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     cfg = llama3_8b(max_seq=4096)
@@ -395,6 +397,7 @@ def run_cuda(args):
                    "kv_len_start": CTX_LEN + W, "kv_cache": "synthetic fill to 2048 positions (prefill is outside the metric, master.rs:131-134)",
                    "weights": "random-init N(0,0.02) bf16, HF layout, seed 1234", "greedy": True,
                    "parallelism": f"pp{world}" if world > 1 else "single",
+                   "handoff": (os.environ.get("CAKE_B200_RING", "p2p") + (" (fused into the decode kernel over NVLink peer memory)" if os.environ.get("CAKE_B200_RING", "p2p") == "p2p" else " (ncclSend/ncclRecv graph nodes)")) if world > 1 else None,
                    "l2": "inputs (15 GB of weights per step) larger than L2; no flush needed"},
         "clocks": clocks,
         "e2e": {"value": e2e_tok_s, "unit": "tok/s", "h2d_bytes_per_step": 4, "d2h_bytes_per_step": 4, "steps": n_e2e,

@@ -45,6 +45,8 @@ SYMBOLS = [
     ("cake_b200_comm_init", _I, [_VP, _VP, _I, _I]),
     ("cake_b200_send", _I, [_VP, _VP, c_size_t, _I]),
     ("cake_b200_recv", _I, [_VP, _VP, c_size_t, _I]),
+    ("cake_b200_ring_export", _I, [_VP, _VP]),
+    ("cake_b200_ring_import", _I, [_VP, _VP]),
     ("cake_b200_decode_build", _I, [_VP, POINTER(_VP), POINTER(_I), _I, _VP, _I, _I]),
     ("cake_b200_decode_begin", _I, [_VP, c_uint32, _I]),
     ("cake_b200_decode_run", _I, [_VP, _I]),

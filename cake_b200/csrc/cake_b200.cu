@@ -136,6 +136,9 @@ struct cake_b200_ctx {
   std::vector<const void *> mk_sig;
   unsigned long long *trace = nullptr;  // CAKE_B200_MEGA_TRACE=1
   unsigned *tickets = nullptr;          // per-phase work-claim counters of the megakernel
+  // ring hand-off over NVLink peer memory: inbox = {counter (u64), pad, x[hidden]} in our memory, written by rank-1
+  unsigned char *inbox = nullptr, *peer_inbox = nullptr;
+  unsigned long long *ring_seq = nullptr;
 };
 constexpr int TOKEN_RING = 1 << 16;
 
@@ -375,6 +378,8 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
   CU(cudaMalloc(&c->gbar, 16));
   CU(cudaMemset(c->gbar, 0, 16));
   CU(cudaMalloc(&c->tickets, sizeof(unsigned) * (4 * MK_MAX_LAYERS + 4)));
+  CU(cudaMalloc(&c->ring_seq, 8));
+  CU(cudaMemset(c->ring_seq, 0, 8));
   CU(cudaMalloc(&c->mk_tab_dev, sizeof(MkLayer) * MK_MAX_LAYERS));
   CU(cudaMalloc(&c->g_tab_dev, sizeof(MkLayer) * MK_MAX_LAYERS));
   CU(cudaMallocHost(&c->mk_tab_host, sizeof(MkLayer) * MK_MAX_LAYERS));
@@ -398,10 +403,11 @@ extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
   if (c->gexec) cudaGraphExecDestroy(c->gexec);
   if (c->graph) cudaGraphDestroy(c->graph);
   if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+  if (c->peer_inbox) cudaIpcCloseMemHandle(c->peer_inbox);
   void *bufs[] = {c->cos_t, c->sin_t, c->embed, c->ln_f, c->xa, c->xb, c->qkv, c->y, c->mm, c->logits, c->ws_ml,
                   c->ws_acc, c->part_val, c->part_idx, c->d_step, c->attn_counters, c->argmax_counter, c->d_token,
                   c->token_ring, c->d_ids, c->d_pen, c->pf_h, c->pf_qkv, c->pf_y, c->pf_x1, c->pf_gu, c->pf_mm, c->io_x,
-                  c->gbar, c->mk_tab_dev, c->g_tab_dev, c->tickets};
+                  c->gbar, c->mk_tab_dev, c->g_tab_dev, c->tickets, c->ring_seq, c->inbox};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (c->lm_head && c->lm_head != c->embed) cudaFree(c->lm_head);
@@ -1105,6 +1111,33 @@ extern "C" int cake_b200_recv(cake_b200_ctx *c, void *x_dev, size_t bytes, int p
   return CAKE_B200_OK;
 }
 
+// Ring hand-off over NVLink peer memory.  Each rank owns an inbox {u64 arrivals, pad to 128 B, x[hidden]} that the
+// previous rank's decode kernel writes directly (st.global over NVLink) and releases with one red.release.sys per CTA.
+constexpr size_t INBOX_X_OFF = 128;
+extern "C" int cake_b200_ring_export(cake_b200_ctx *c, void *handle64) {
+  if (!c || !handle64) return fail(CAKE_B200_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (!c->inbox) {
+    CU(cudaMalloc(&c->inbox, INBOX_X_OFF + (size_t)c->cfg.hidden * c->es + 128));
+    CU(cudaMemset(c->inbox, 0, INBOX_X_OFF + (size_t)c->cfg.hidden * c->es + 128));
+  }
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  CU(cudaIpcGetMemHandle(&h, c->inbox));
+  memcpy(handle64, &h, 64);
+  return CAKE_B200_OK;
+}
+extern "C" int cake_b200_ring_import(cake_b200_ctx *c, const void *next_rank_handle64) {
+  if (!c || !next_rank_handle64) return fail(CAKE_B200_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  cudaIpcMemHandle_t h;
+  memcpy(&h, next_rank_handle64, 64);
+  void *p = nullptr;
+  CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  c->peer_inbox = (unsigned char *)p;
+  return CAKE_B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------ decode loop (one CUDA graph per shard)
 extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *block_idx,
                                       int n_blocks, cake_b200_cache *kc, int rank, int world) {
@@ -1131,29 +1164,37 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
     if (c->use_mega && mega_supported(c)) {
       // rank 0: [embed+layers(+head if alone)] ; world>1: layers -> send ... recv -> head.  ranks>0: recv -> layers -> send
       MkPlan p;
+      const bool p2p = world > 1 && c->inbox && c->peer_inbox;  // hand-off fused into the kernels (no NCCL node)
+      unsigned long long *inbox_ctr = (unsigned long long *)c->inbox, *peer_ctr = (unsigned long long *)c->peer_inbox;
+      void *inbox_x = c->inbox ? c->inbox + INBOX_X_OFF : nullptr, *peer_x = c->peer_inbox ? c->peer_inbox + INBOX_X_OFF : nullptr;
       if (rank == 0) {
         RC(plan_mega(c, kc, world == 1, &p));
         p.a.layers = c->g_tab_dev; p.a.n_layers = n_blocks; p.a.x_in = nullptr; p.a.x_out = c->xa;
         p.a.has_head = (world == 1); p.a.advance = (world == 1); p.a.token_ring = c->token_ring;
+        if (p2p) { p.a.x_out = peer_x; p.a.peer_ctr = peer_ctr; p.a.ring_seq = c->ring_seq; }
         if (n_blocks > 0 || world == 1) RC(launch_mega(c, p));
         if (world > 1) {
           if (n_blocks == 0) return fail(CAKE_B200_EINVAL, "rank 0 must own at least one layer");
-          RC(cake_b200_send(c, c->xa, xbytes, 1));
-          RC(cake_b200_recv(c, c->xa, xbytes, world - 1));
+          if (!p2p) {
+            RC(cake_b200_send(c, c->xa, xbytes, 1));
+            RC(cake_b200_recv(c, c->xa, xbytes, world - 1));
+          }
           MkPlan h;
           RC(plan_mega(c, kc, true, &h));
-          h.a.layers = c->g_tab_dev; h.a.n_layers = 0; h.a.x_in = c->xa; h.a.x_out = c->xa;
+          h.a.layers = c->g_tab_dev; h.a.n_layers = 0; h.a.x_in = p2p ? inbox_x : c->xa; h.a.x_out = c->xa;
           h.a.has_head = 1; h.a.advance = 1; h.a.token_ring = c->token_ring;
+          if (p2p) { h.a.inbox_ctr = inbox_ctr; h.a.ring_seq = c->ring_seq; }
           RC(launch_mega(c, h));
         }
       } else {
-        RC(cake_b200_recv(c, c->xa, xbytes, rank - 1));
+        if (!p2p) RC(cake_b200_recv(c, c->xa, xbytes, rank - 1));
         RC(plan_mega(c, kc, false, &p));
-        p.a.layers = c->g_tab_dev; p.a.n_layers = n_blocks; p.a.x_in = c->xa; p.a.x_out = c->xa;
+        p.a.layers = c->g_tab_dev; p.a.n_layers = n_blocks; p.a.x_in = p2p ? inbox_x : c->xa; p.a.x_out = p2p ? peer_x : c->xa;
         p.a.has_head = 0; p.a.advance = 1;
+        if (p2p) { p.a.inbox_ctr = inbox_ctr; p.a.peer_ctr = peer_ctr; p.a.ring_seq = c->ring_seq; }
         if (n_blocks > 0) RC(launch_mega(c, p));
-        else RC(launch_pdl(c, advance_kernel, dim3(1), dim3(32), 0, kc->d_pos, c->d_step));
-        RC(cake_b200_send(c, c->xa, xbytes, (rank + 1) % world));
+        else return fail(CAKE_B200_EINVAL, "every rank must own at least one layer");
+        if (!p2p) RC(cake_b200_send(c, c->xa, xbytes, (rank + 1) % world));
       }
       return CAKE_B200_OK;
     }

@@ -61,6 +61,12 @@ struct MkArgs {
   unsigned *argmax_counter;
   uint32_t *token_out, *token_ring;
   int ring_cap;
+  // shard-to-shard hand-off over NVLink peer memory (fused into this kernel; no NCCL kernel in the step):
+  //   inbox_ctr != nullptr: wait until the previous shard has delivered step *ring_seq into our inbox (x_in)
+  //   peer_ctr  != nullptr: x_out is the next shard's inbox; signal it when every CTA has written its rows
+  const unsigned long long *inbox_ctr;
+  unsigned long long *peer_ctr;
+  unsigned long long *ring_seq;   // hand-offs received so far (device-resident, never reset)
   unsigned *tickets;          // [phase] work-claim counters, zeroed before every launch
   int max_groups;             // per-CTA cap of row groups in one phase (sizes the partial-sum scratch)
   int l2_prefetch;            // experimental (CAKE_B200_L2_PREFETCH=1): producer prefetches its future rows into L2
@@ -360,6 +366,7 @@ struct MkEpi {
   int *d_pos, *d_step;
   unsigned long long *gbar;
   unsigned long long next_start;
+  unsigned long long *ring_seq;  // non-null when this launch consumed an inbox hand-off
 };
 
 template <typename T, int EPI>
@@ -534,6 +541,7 @@ __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, con
         *e.counter = 0;
         // end-of-step bookkeeping: this is the last CTA of the grid to finish
         if (e.advance) { *e.d_pos += 1; *e.d_step += 1; }
+        if (e.ring_seq) *e.ring_seq += 1ULL;
         e.gbar[1] = e.next_start;
       }
     }
@@ -903,6 +911,16 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     stamp();
   };
   stamp();
+  if (a.inbox_ctr) {  // ring hand-off: the previous shard pushes our input over NVLink and bumps the counter once per CTA
+    if (ct == 0) {
+      const unsigned long long want = (*reinterpret_cast<volatile unsigned long long *>(a.ring_seq) + 1ULL) * gridDim.x;
+      unsigned long long v;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.inbox_ctr) : "memory");
+      } while (v < want);
+    }
+    named_bar_sync(1, MK_CT);
+  }
   const T *cur = reinterpret_cast<const T *>(a.x_in);
   if (cur == nullptr) {  // master: the block input is the embedding row of the current token (text_model.rs:271)
     uint32_t tok = *a.d_token;
@@ -972,12 +990,21 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     e.d_step = a.d_step;
     e.gbar = a.gbar;
     e.next_start = start + (unsigned long long)nbar * gridDim.x;
+    e.ring_seq = a.inbox_ctr ? a.ring_seq : nullptr;
     mk_consume_gemv<T, EPI_ARGMAX>(rg, a.g_head, xs, partial, loc_row, scratch, e, ct, warp, lane);
   }
+  if (a.peer_ctr && !a.has_head) {  // our rows of x_out are in the next shard's inbox: release them, one arrival per CTA
+    named_bar_sync(1, MK_CT);
+    if (ct == 0) {
+      __threadfence_system();
+      asm volatile("red.release.sys.global.add.u64 [%0], %1;" ::"l"(a.peer_ctr), "l"(1ULL) : "memory");
+    }
+  }
   // bookkeeping without a head: CTA 0 only gets here after passing barriers that every CTA arrived at,
-  // and every CTA read *d_pos and the epoch before its first barrier.
+  // and every CTA read *d_pos, *ring_seq and the barrier start value before its first barrier.
   if (!a.has_head && blockIdx.x == 0 && ct == 0) {
     if (a.advance) { *a.d_pos += 1; *a.d_step += 1; }
+    if (a.inbox_ctr) *a.ring_seq += 1ULL;
     a.gbar[1] = start + (unsigned long long)nbar * gridDim.x;
   }
 }

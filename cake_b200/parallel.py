@@ -12,6 +12,7 @@ touch the host.
 """
 from __future__ import annotations
 
+import os
 import re
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -85,6 +86,15 @@ def init_comm(ctx: Context, rank: int, world: int) -> None:
     else:
         dist.broadcast(uid, 0)
     check(lib().cake_b200_comm_init(ctx.h, ptr(uid), rank, world))
+    if os.environ.get("CAKE_B200_RING", "p2p") == "p2p":
+        # fused hand-off: exchange the IPC handles of the inboxes; rank r writes the inbox of rank (r+1) % world
+        mine = torch.zeros(64, dtype=torch.uint8)
+        check(lib().cake_b200_ring_export(ctx.h, ptr(mine)))
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(mine.numpy().tobytes()))
+        nxt = torch.frombuffer(bytearray(handles[(rank + 1) % world]), dtype=torch.uint8)
+        check(lib().cake_b200_ring_import(ctx.h, ptr(nxt)))
+        dist.barrier()
 
 
 class NcclTransport:

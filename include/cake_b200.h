@@ -131,6 +131,13 @@ int cake_b200_comm_init(cake_b200_ctx *, const void *unique_id128, int rank, int
 int cake_b200_send(cake_b200_ctx *, const void *x_dev, size_t bytes, int peer);
 int cake_b200_recv(cake_b200_ctx *, void *x_dev, size_t bytes, int peer);
 
+/* Optional, after comm_init: hand-off fused into the decode kernels over NVLink peer memory instead of NCCL kernels.
+ * Every rank exports a 64-byte IPC handle of its inbox and imports the handle of rank (r+1) % world; decode_build then
+ * makes the last kernel of a shard write the next shard's inbox directly and release it (red.release.sys), and the
+ * first kernel of a shard acquire its own inbox.  Without these calls the decode graph uses ncclSend/ncclRecv. */
+int cake_b200_ring_export(cake_b200_ctx *, void *handle64);
+int cake_b200_ring_import(cake_b200_ctx *, const void *next_rank_handle64);
+
 /* ---- the decode hot loop (master.rs:131-155), one CUDA graph per shard ------------------------- */
 /* Builds the per-token step for this rank's contiguous layer range (batch 1, seq 1):
  *   rank 0          : embed(token) -> its blocks -> [send -> ... -> recv from last rank] -> ln_f/lm_head/argmax -> token
