@@ -115,6 +115,35 @@ def host_info() -> dict:
     return {"cpu": model, "logical_cores": NCORES}
 
 
+_BEST_THREADS = None
+
+
+def pick_threads() -> int:
+    """Thread count for the CPU legs: the fastest of {all, 1/2, 1/4} logical cores on a short GEMV probe (on a
+    2-socket box with SMT, all logical cores can be several times slower than one thread per physical core)."""
+    global _BEST_THREADS
+    if _BEST_THREADS is not None:
+        return _BEST_THREADS
+    import numpy as np
+    import torch
+    from oracle import oracle as O
+    W = torch.randn(16384, 4096).to(torch.bfloat16)  # 128 MB
+    x = O.round_to(np.random.default_rng(0).standard_normal((1, 4096)).astype(np.float32), "bf16")
+    best, best_t = NCORES, float("inf")
+    for n in sorted({NCORES, max(1, NCORES // 2), max(1, NCORES // 4)}, reverse=True):
+        O.lib().ora_set_num_threads(n)
+        O.linear(x, W, None, "bf16")
+        t0 = time.perf_counter()
+        for _ in range(4):
+            O.linear(x, W, None, "bf16")
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    O.lib().ora_set_num_threads(best)
+    _BEST_THREADS = best
+    return best
+
+
 def cpu_reference_tok_s(cfg, n_tokens: int, budget_s: float, layers_cap=None) -> dict:
     """The reference's CPU path (oracle port, all host threads) on the same workload: bs=1 decode at KV
     length CTX_LEN.  Bounded sample: `n_tokens` tokens over `n_sample` of the 32 layers (+ the full
@@ -124,7 +153,7 @@ def cpu_reference_tok_s(cfg, n_tokens: int, budget_s: float, layers_cap=None) ->
     from cake_b200.synth import make_head, make_layer
     from oracle import oracle as O
 
-    O.lib().ora_set_num_threads(NCORES)  # all host cores this process may use
+    pick_threads()  # the best-performing thread count on this host (of all / half / quarter of the logical cores)
     t_build = time.perf_counter()
     nl = cfg.num_hidden_layers
     n_sample = min(nl, layers_cap or nl)
