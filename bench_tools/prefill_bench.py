@@ -33,3 +33,6 @@ for rep in range(3):
     print(f"rep {rep}: {ms:.3f} ms/layer  B={B} S={S}  linear {flop_lin / ms / 1e9:.1f} TFLOP/s-equivalent (linears only), "
           f"{B * S / (ms * cfg.num_hidden_layers if False else ms) :.0f} tok/s/layer", flush=True)
 print("finite:", bool(torch.isfinite(y.float()).all()))
+tot = flop_lin + flop_att
+print(f"B={B} S={S}: {ms:.3f} ms/layer -> {32 * ms / 1e3:.3f} s for 32 layers = {B * S / (32 * ms / 1e3):.0f} prefill tok/s ; "
+      f"{tot / ms / 1e9:.0f} TFLOP/s (linears {flop_lin / 1e12:.2f} + causal attention {flop_att / 1e12:.3f} TFLOP per layer)")

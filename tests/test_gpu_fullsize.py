@@ -126,3 +126,29 @@ def test_qwen3_0_6b_config0_f16_greedy_against_oracle():
 def _ctx_dtype(cfg, sd, dtype, max_seq):
     from cake_b200.model import Context
     return Context(cfg, sd, dtype, device=0, max_seq=max_seq)
+
+
+def test_llama3_70b_layer_geometry_matches_oracle():
+    """BASELINE.json configs[3] layer dimensions (H=8192, I=28672, 64/8 heads of 128 -> G=8): rows of 16 KB / 56 KB,
+    i.e. the 2-row and the split-row (2 x 28 KB) stage geometries of the megakernel, and 8 query heads per kv head."""
+    from cake_b200.config import llama3_70b
+    from cake_b200.model import B200Transformer
+    cfg = llama3_70b(max_seq=128)
+    cfg.num_hidden_layers = 1
+    sd = make_layer(cfg, 0, "bf16", seed=70)
+    om = O.OracleModel(cfg, sd, "bf16", max_seq=128)
+    oc = om.new_cache(128)
+    ctx = _ctx(cfg, sd, 128)
+    blk = B200Transformer.load(cfg.layer_name(0), ctx)
+    x = rand_x((1, 20, cfg.hidden_size), "bf16", seed=3)
+    y_ref = om.block_forward(0, x[0, :17].float().numpy(), 0, oc)
+    y = blk.forward(ctx.to_device(x[:, :17]), 0, 0, ctx)
+    ctx.sync()
+    assert max_ulp_err(to_np(y[0]), y_ref, "bf16") <= 4.0
+    for t in range(17, 20):
+        y_ref = om.block_forward(0, x[0, t:t + 1].float().numpy(), t, oc)
+        y = blk.forward(ctx.to_device(x[:, t:t + 1]), t, 0, ctx)
+        ctx.sync()
+        e = max_ulp_err(to_np(y[0]), y_ref, "bf16")
+        assert e <= 4.0, f"decode @{t}: {e} ulp"
+    ctx.close()
