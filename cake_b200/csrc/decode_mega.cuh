@@ -575,13 +575,34 @@ __device__ __forceinline__ float reduce16_heads(float (&s)[G], int lane, int &g_
   return v;
 }
 
+// norm_rope_inplace with the position's cos/sin row already staged in shared memory as fp32 (D values)
+template <typename T, int HD>
+__device__ __forceinline__ void mk_norm_rope(float *buf, const T *norm_w, float eps, const float *cs, const float *sn, int rot, int lane) {
+  if (norm_w) {
+    float ss = 0.f;
+    for (int d = lane; d < HD; d += 32) ss += buf[d] * buf[d];
+    ss = warp_sum(ss);
+    const float inv = 1.0f / sqrtf(ss / (float)HD + eps);
+    for (int d = lane; d < HD; d += 32) buf[d] = rnd<T>(buf[d] * inv * DT<T>::to_f(norm_w[d]));
+    __syncwarp();
+  }
+  const int half = rot / 2;
+  for (int i = lane; i < half; i += 32) {
+    const float c = cs[i], s = sn[i];
+    const float x1 = buf[i], x2 = buf[i + half];
+    buf[i] = rnd<T>(rnd<T>(x1 * c) - rnd<T>(x2 * s));
+    buf[i + half] = rnd<T>(rnd<T>(x2 * c) + rnd<T>(x1 * s));
+  }
+  __syncwarp();
+}
+
 // Attention phase for this CTA's (kv head, split) item.  Same math as attn_decode_kernel (f32 scores,
 // softmax and PV, one rounding of the result); K/V tiles come from the ring, prefetched by the producer while
 // the qkv GEMV was still running.  G = n_heads / n_kv_heads is a template parameter so that all per-head
 // state lives in registers.
 template <typename T, int HD, int G>
 __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, const MkLayer &L, int pos, unsigned char *scr,
-                                                int ct, int warp, int lane, unsigned long long *tr) {
+                                                const float *rope_cs, int ct, int warp, int lane, unsigned long long *tr) {
   auto stamp = [&](int i) {
     if (tr && ct == 0) {
       unsigned long long t;
@@ -604,8 +625,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
   if (!it.active) return;  // CTA-uniform; inactive CTAs issue no stages either
 
   const T *qkv = reinterpret_cast<const T *>(a.qkv);
-  const T *cosr = reinterpret_cast<const T *>(a.cos_t) + (size_t)pos * (a.rot / 2);
-  const T *sinr = reinterpret_cast<const T *>(a.sin_t) + (size_t)pos * (a.rot / 2);
+  const float *cosr = rope_cs, *sinr = rope_cs + 128;  // this step's cos/sin row, staged once per launch
   T *kc = reinterpret_cast<T *>(L.kc) + (size_t)it.kvh * a.cap * HD;
   T *vc = reinterpret_cast<T *>(L.vc) + (size_t)it.kvh * a.cap * HD;
   const int kvh = it.kvh, split = it.split, s0 = it.s0, s1 = it.s1, TILE = it.tile;
@@ -617,14 +637,14 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     float *dst = q_s + g * HD;
     for (int d = lane; d < HD; d += 32) dst[d] = DT<T>::to_f(ldcg_T<T>(src + d));
     __syncwarp();
-    norm_rope_inplace<T, HD>(dst, reinterpret_cast<const T *>(L.qn), a.eps, cosr, sinr, a.rot, lane);
+    mk_norm_rope<T, HD>(dst, reinterpret_cast<const T *>(L.qn), a.eps, cosr, sinr, a.rot, lane);
   }
   if (owner) {
     if (warp == NW - 1) {
       const T *src = qkv + (size_t)(a.n_heads + kvh) * HD;
       for (int d = lane; d < HD; d += 32) knew[d] = DT<T>::to_f(ldcg_T<T>(src + d));
       __syncwarp();
-      norm_rope_inplace<T, HD>(knew, reinterpret_cast<const T *>(L.kn), a.eps, cosr, sinr, a.rot, lane);
+      mk_norm_rope<T, HD>(knew, reinterpret_cast<const T *>(L.kn), a.eps, cosr, sinr, a.rot, lane);
       for (int d = lane; d < HD; d += 32) kc[(size_t)pos * HD + d] = DT<T>::from_f(knew[d]);
     } else if (warp == NW - 2) {
       const T *vsrc = qkv + (size_t)(a.n_heads + a.n_kv + kvh) * HD;
@@ -798,14 +818,15 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
   stamp(6);
   named_bar_sync(1, MK_CT);
   if (ct == 0) {
-    __threadfence();  // cumulative: publishes the partials every thread of this CTA wrote before the bar.sync
-    const unsigned ticket = atomicAdd(&a.attn_counters[kvh], 1u);
+    // acq_rel at gpu scope: releases the partials every thread of this CTA wrote before the bar.sync (cumulative)
+    // and, for the last arriver, acquires the other splits' partials
+    unsigned ticket;
+    asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(ticket) : "l"(&a.attn_counters[kvh]) : "memory");
     is_last = (ticket == (unsigned)a.nsplit - 1);
   }
   named_bar_sync(1, MK_CT);
   stamp(7);
   if (!is_last) return;
-  __threadfence();
   for (int g = warp; g < G; g += NW) {
     const int h = kvh * G + g;
     float m = -INFINITY, l = 0.f;
@@ -892,6 +913,14 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
 
   // ================= consumers ========================================================================
   const int ct = threadIdx.x;
+  __shared__ float rope_cs[256];  // cos (first 128) and sin (last 128) row of this step's position, as fp32
+  {
+    const int half = a.rot / 2;
+    const T *cr = reinterpret_cast<const T *>(a.cos_t) + (size_t)pos * half, *sr = reinterpret_cast<const T *>(a.sin_t) + (size_t)pos * half;
+    if (ct < half) rope_cs[ct] = DT<T>::to_f(cr[ct]);
+    else if (ct >= 128 && ct - 128 < half) rope_cs[ct] = DT<T>::to_f(sr[ct - 128]);
+    // visibility: the first named barrier of the first phase orders these writes before any use
+  }
   // gbar[0] is a monotonic arrival counter; gbar[1] holds its value at the start of this launch (written
   // by the previous launch's last thread), so barrier k of this launch completes at start + k*grid.
   const unsigned long long start = *reinterpret_cast<volatile unsigned long long *>(a.gbar + 1);
@@ -939,7 +968,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     mk_consume_gemv<T, EPI_PLAIN>(rg, a.g_qkv, xs, partial, loc_row, scratch, e, ct, warp, lane);
     gsync();
     // qk-norm, RoPE, KV append, attention
-    mk_consume_attn<T, HD, G>(rg, a, L, pos, reinterpret_cast<unsigned char *>(xs), ct, warp, lane,
+    mk_consume_attn<T, HD, G>(rg, a, L, pos, reinterpret_cast<unsigned char *>(xs), rope_cs, ct, warp, lane,
                            (a.trace && blockIdx.x == 0 && l == 1) ? a.trace + 2048 : nullptr);
     gsync();
     // o_proj + residual

@@ -152,3 +152,34 @@ def test_llama3_70b_layer_geometry_matches_oracle():
         e = max_ulp_err(to_np(y[0]), y_ref, "bf16")
         assert e <= 4.0, f"decode @{t}: {e} ulp"
     ctx.close()
+
+
+def test_llama3_8b_decode_at_2500_context_multi_tile_attention():
+    """Decode at KV length 2500+ (beyond 18 splits x 128 rows): every flash-decoding split walks more than one K/V
+    tile, the online-softmax rescaling between tiles is exercised, and the appended row lands in a later tile.  The
+    cache is filled with the library's synthetic pattern, read back, and handed to the oracle."""
+    from cake_b200.model import B200Transformer, Cache
+    cfg = llama3_8b(max_seq=2600)
+    cfg.num_hidden_layers = 1
+    sd = make_layer(cfg, 0, "bf16", seed=31)
+    ctx = _ctx(cfg, sd, 2600)
+    ctx.cache = Cache(ctx, 1, 2600)
+    blk = B200Transformer.load(cfg.layer_name(0), ctx)
+    L0 = 2500
+    ctx.cache.fill_synthetic([0], L0, seed=11)
+    ctx.sync()
+    k, v = ctx.cache.kv(0)
+    om = O.OracleModel(cfg, sd, "bf16", max_seq=2600)
+    oc = om.new_cache(2600)
+    ko, vo = oc.kv(0)
+    ko[:, :L0] = k[0].float().numpy()
+    vo[:, :L0] = v[0].float().numpy()
+    oc.set_len(0, L0)
+    x = rand_x((1, 3, cfg.hidden_size), "bf16", seed=8)
+    for i in range(3):
+        y_ref = om.block_forward(0, x[0, i:i + 1].float().numpy(), L0 + i, oc)
+        y = blk.forward(ctx.to_device(x[:, i:i + 1]), L0 + i, 0, ctx)
+        ctx.sync()
+        e = max_ulp_err(to_np(y[0]), y_ref, "bf16")
+        assert e <= 4.0, f"decode @{L0 + i}: {e} ulp"
+    ctx.close()
