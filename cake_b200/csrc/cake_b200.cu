@@ -259,7 +259,7 @@ template <typename T> static int set_smem_attrs_T() {
   SETB(16) SETB(32) SETB(64) SETB(128) SETB(256)
 #undef SETB
 #define SETC(HD, G)                                                                                                  \
-  CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs - 2048));  \
+  CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, maxs - 4096));  \
   CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   MK_FOR_ALL(SETC)
 #undef SETC
@@ -714,7 +714,7 @@ static int plan_mega(cake_b200_ctx *c, cake_b200_cache *kc, bool with_head, MkPl
   a.argmax_counter = c->argmax_counter; a.token_out = c->d_token; a.token_ring = nullptr; a.ring_cap = TOKEN_RING;
   a.trace = c->trace;
   int ns = MK_MAX_STAGES;
-  const size_t limit = 227 * 1024 - 2048;
+  const size_t limit = 227 * 1024 - 4096;  // the kernel also has ~2.2 KB of static shared memory
   while (ns > 2 && mk_smem_bytes(a.max_k, pf, mg, ns, c->es) > limit) ns--;
   a.n_stages = ns;
   p->smem = mk_smem_bytes(a.max_k, pf, mg, ns, c->es);
