@@ -5,7 +5,7 @@
 // flash-style kernel: S never leaves registers.  Numerics stay those of the f32 branch:
 //   * q,k are D values, so q.k products are exact in fp32; mma.sync (D inputs, fp32 accumulate) == f32 matmul up
 //     to summation order;
-//   * softmax in fp32 (expf, max-subtracted, online rescaling);
+//   * softmax in fp32 (max-subtracted, online rescaling; __expf = MUFU ex2, ~2 ulp fp32);
 //   * P (fp32) is split into two D halves, P = P_hi + P_lo, and both are multiplied with V on the tensor cores:
 //     ~16 mantissa bits, far below the final rounding to D (an FA2-style single bf16 P would lose 8 bits);
 //   * one rounding of the result to D.
@@ -148,7 +148,7 @@ attn_prefill_mma_kernel(const T *__restrict__ qkv, const T *__restrict__ kcache,
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
       const float mn = fmaxf(m_run[r], mx[r]);
-      fac[r] = (m_run[r] == -INFINITY) ? 0.f : expf(m_run[r] - mn);
+      fac[r] = (m_run[r] == -INFINITY) ? 0.f : __expf(m_run[r] - mn);
       m_run[r] = mn;
     }
 #pragma unroll
@@ -156,7 +156,8 @@ attn_prefill_mma_kernel(const T *__restrict__ qkv, const T *__restrict__ kcache,
 #pragma unroll
       for (int e = 0; e < 4; e++) {
         const float mn = m_run[e >> 1];
-        const float p = (mn == -INFINITY) ? 0.f : expf(s[nt][e] - mn);  // fully masked row (cannot happen for valid rows)
+        // MUFU ex2-based exp (~2 ulp in fp32, far below the D rounding of the result): S*T/2 of these per head
+        const float p = (mn == -INFINITY) ? 0.f : __expf(s[nt][e] - mn);
         s[nt][e] = p;
         rs[e >> 1] += p;
       }
