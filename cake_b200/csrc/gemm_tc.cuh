@@ -36,6 +36,18 @@ struct TcParams {
   int M, N, K;
 };
 
+// Tile rasterisation: groups of TC_GM m-tiles (16 x 128 rows = 16 MB of A at K=4096) are walked n-major, so the A
+// group stays in the 126 MB L2 while each W tile streams once per group.  With plain m-fastest order a 1 GB A
+// (bs=32 x 4k) is re-read for every W tile column: measured 815 TFLOP/s, HBM-bound (profiles/README.md).
+constexpr int TC_GM = 16;
+__device__ __forceinline__ void tc_tile(int t, int tiles_m, int tiles_n, int &m0, int &n0) {
+  const int per_group = TC_GM * tiles_n;
+  const int mg = t / per_group, r = t % per_group;
+  const int gm = min(TC_GM, tiles_m - mg * TC_GM);
+  m0 = (mg * TC_GM + r % gm) * TC_BM;
+  n0 = (r / gm) * TC_BN;
+}
+
 // ---- PTX wrappers ------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
   asm volatile(
@@ -125,7 +137,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int m0 = (t % tiles_m) * TC_BM, n0 = (t / tiles_m) * TC_BN;  // m fastest: a W tile is reused from L2
+        int m0, n0;
+        tc_tile(t, tiles_m, tiles_n, m0, n0);
         for (int kb = 0; kb < kblocks; kb++) {
           mbar_wait(&empty[s], ph ^ 1u);
           unsigned char *st = smem + (size_t)s * TC_STAGE_BYTES;
@@ -173,7 +186,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
       const int a = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      const int m0 = (t % tiles_m) * TC_BM, n0 = (t / tiles_m) * TC_BN;
+      int m0, n0;
+      tc_tile(t, tiles_m, tiles_n, m0, n0);
       const int row = m0 + wq * 32 + lane;
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
