@@ -323,6 +323,10 @@ def run_cuda(args):
             e0.record(ctx.torch_stream)
             check(lib().cake_b200_decode_run(ctx.h, n))
             e1.record(ctx.torch_stream)
+            # sleep-poll instead of a spinning cudaStreamSynchronize: with N-1 worker processes spinning next to
+            # rank 0's per-token sync the host-stepped leg showed 100 ms stalls at N=8 (CPU contention / quota)
+            while not e1.query():
+                time.sleep(0.0005)
             sync_all()
             return e0.elapsed_time(e1)
         _, bidx = worker.block_list()
