@@ -28,9 +28,7 @@ def _nccl_include() -> str:
 
 def sources():
     d = os.path.join(HERE, "csrc")
-    h = os.path.join(HERE, "host")
     return [os.path.join(d, f) for f in sorted(os.listdir(d)) if f.endswith((".cu", ".cuh"))] + \
-           [os.path.join(h, f) for f in sorted(os.listdir(h)) if f.endswith((".cc", ".hpp"))] + \
            [os.path.join(ROOT, "include", "cake_b200.h")]
 
 
@@ -43,6 +41,7 @@ def stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
+        build_host()
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -53,14 +52,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     subprocess.check_call(cmd)
-    build_host()
+    build_host(force=True)
     return SO
 
 
-def build_host() -> str:
+def build_host(force: bool = False) -> str:
     """The C++ host side (cake_b200/host/cake_host.hpp) + its `cake_run` driver, linked against the C ABI."""
     out = os.path.join(HERE, "host", "cake_run")
     src = os.path.join(HERE, "host", "cake_run.cc")
+    deps = [src, os.path.join(HERE, "host", "cake_host.hpp"), os.path.join(ROOT, "include", "cake_b200.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
     subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-o", out, src, "-I", os.path.join(ROOT, "include"),
                            "-L", HERE, "-lcake_b200", "-Wl,-rpath,$ORIGIN/.."])
     return out

@@ -1,9 +1,11 @@
 """Model configuration for the block-forward path.
 
 Mirrors the reference's generalized ``Config`` (cake-core/src/models/common/config.rs:87-150) for the
-fields the dense Llama-family block path reads, and the two HF ``config.json`` mappings that are in
-scope: ``LlamaConfig::into_config`` (models/llama3/config.rs:62-98) and ``Qwen3Config::into_config``
-(models/qwen3/config.rs:55-93).  Field names follow the reference.
+fields the dense Llama-family block path reads, and the HF ``config.json`` mappings of the architectures
+whose blocks are exactly that path: ``LlamaConfig::into_config`` (models/llama3/config.rs:62-98),
+``Qwen3Config`` (qwen3/config.rs:55-93), ``Qwen2Config`` (qwen2/config.rs:69-105, q/k/v bias),
+``MistralConfig`` (mistral/config.rs:56-93, without an active sliding window) and ``Falcon3Config``
+(falcon3/config.rs:53-90).  Field names follow the reference.
 """
 from __future__ import annotations
 
@@ -44,6 +46,7 @@ class Config:
     partial_rotary_factor: float = 1.0
     use_qk_norm: bool = False
     eos_token_id: list = field(default_factory=list)
+    sliding_window: Optional[int] = None
 
     @property
     def hd(self) -> int:
@@ -63,9 +66,36 @@ class Config:
         return f"{self.model_prefix}.layers.{i}"
 
     # ---- HF config.json mappings -------------------------------------------------------------
+    # arch -> (default rope_theta, default max_position_embeddings, fixed flags): the serde defaults and the
+    # constants each ``into_config`` hard-wires.  Strings the reference does not know fall back to Llama
+    # (cake/mod.rs:81-109); architectures it knows but whose block is not this path are refused here.
+    _ARCHS = {
+        "LlamaForCausalLM": (500000.0, 4096, dict()),
+        "Qwen2ForCausalLM": (1000000.0, 32768, dict(use_qkv_bias=True)),
+        "Qwen3ForCausalLM": (1000000.0, 40960, dict(use_qk_norm=True, _head_dim=True)),
+        "MistralForCausalLM": (1000000.0, 131072, dict(_head_dim=True, _sliding_window=True)),
+        "FalconForCausalLM": (500000.0, 131072, dict(_head_dim=True)),
+    }
+    _OTHER_BLOCKS = ("Qwen3_5ForConditionalGeneration", "Qwen3MoeForCausalLM", "Qwen3_5MoeForConditionalGeneration",
+                     "Phi3ForCausalLM", "Phi4ForCausalLM", "Gemma3ForCausalLM", "OLMo2ForCausalLM",
+                     "Olmo2ForCausalLM", "ExaoneForCausalLM", "LuxTTSForTextToSpeech")
+
+    @staticmethod
+    def detect_arch(d: dict) -> str:
+        """config.rs:175-190 detect_text_model_arch: the first *string* entry of ``architectures``, else ""."""
+        archs = d.get("architectures")
+        if isinstance(archs, list):
+            for a in archs:
+                if isinstance(a, str):
+                    return a
+        return ""
+
     @staticmethod
     def from_hf(d: dict) -> "Config":
-        arch = (d.get("architectures") or [""])[0]  # config.rs detect_text_model_arch
+        arch = Config.detect_arch(d)
+        if arch in Config._OTHER_BLOCKS:
+            raise ValueError(f"architecture {arch!r} is outside the block-forward path built here")
+        rope_default, max_default, flags = Config._ARCHS.get(arch, Config._ARCHS["LlamaForCausalLM"])
         rs = d.get("rope_scaling")
         rope = None
         if rs:
@@ -78,7 +108,7 @@ class Config:
             )
         eos = d.get("eos_token_id")
         eos = [] if eos is None else (list(eos) if isinstance(eos, (list, tuple)) else [eos])
-        common = dict(
+        return Config(
             hidden_size=d["hidden_size"],
             intermediate_size=d["intermediate_size"],
             vocab_size=d["vocab_size"],
@@ -86,17 +116,16 @@ class Config:
             num_attention_heads=d["num_attention_heads"],
             num_key_value_heads=d.get("num_key_value_heads") or d["num_attention_heads"],
             rms_norm_eps=d["rms_norm_eps"],
-            rope_theta=float(d.get("rope_theta", 10000.0)),
+            rope_theta=float(d.get("rope_theta") or rope_default),
             rope_scaling=rope,
             tie_word_embeddings=bool(d.get("tie_word_embeddings", False)),
-            max_seq_len=int(d.get("max_position_embeddings", 4096)),
+            max_seq_len=int(d.get("max_position_embeddings") or max_default),
             eos_token_id=eos,
+            use_qkv_bias=bool(flags.get("use_qkv_bias", False)),
+            use_qk_norm=bool(flags.get("use_qk_norm", False)),
+            head_dim=d.get("head_dim") if flags.get("_head_dim") else None,
+            sliding_window=d.get("sliding_window") if flags.get("_sliding_window") else None,
         )
-        if arch == "Qwen3ForCausalLM":
-            return Config(**common, head_dim=d.get("head_dim"), use_qk_norm=True)
-        if arch in ("LlamaForCausalLM", ""):
-            return Config(**common)
-        raise ValueError(f"architecture {arch!r} is outside the block-forward path built here")
 
     @staticmethod
     def from_path(path: str) -> "Config":
@@ -113,6 +142,8 @@ class Config:
         )
         if self.head_dim:
             d["head_dim"] = self.head_dim
+        if self.sliding_window:
+            d["sliding_window"] = self.sliding_window
         if self.rope_scaling:
             d["rope_scaling"] = asdict(self.rope_scaling)
         return d
@@ -140,6 +171,10 @@ class CConfig(ctypes.Structure):
     def from_config(c: Config, dtype: str = "bf16", max_seq: Optional[int] = None) -> "CConfig":
         rs = c.rope_scaling
         llama3 = bool(rs and rs.rope_type == "llama3" and rs.original_max_position_embeddings > 0)
+        if c.sliding_window and c.sliding_window < (max_seq or c.max_seq_len):
+            # cache.rs:173-205 trims K/V to the window; the cache here is append-only
+            raise ValueError(f"sliding_window={c.sliding_window} < max_seq={max_seq or c.max_seq_len}: the windowed "
+                             "KV trim (cache.rs:173-205) is not built; cap max_seq at the window")
         return CConfig(
             c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.hd,
             c.num_hidden_layers, c.vocab_size, max_seq or c.max_seq_len,

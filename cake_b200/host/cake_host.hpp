@@ -139,7 +139,7 @@ inline std::string slurp(const std::string &path) {
 }
 
 // ---------------------------------------------------------------------------------------------- config
-// models/common/config.rs:87-150 via LlamaConfig / Qwen3Config::into_config (llama3/config.rs:62-98, qwen3/config.rs:55-93)
+// models/common/config.rs:87-150 via the into_config of the dense architectures whose block is this path
 struct Config {
   cake_b200_config c{};
   std::string model_prefix = "model";
@@ -149,10 +149,28 @@ struct Config {
     std::string txt = slurp(path);
     Json j = JsonParser(txt.data(), txt.size()).value();
     Config k;
-    if (const Json *a = j.get("architectures"))
-      if (!a->arr.empty()) k.arch = a->arr[0].str;  // config.rs detect_text_model_arch
-    if (!(k.arch.empty() || k.arch == "LlamaForCausalLM" || k.arch == "Qwen3ForCausalLM"))
-      throw Error("architecture " + k.arch + " is outside the block-forward path built here");
+    if (const Json *a = j.get("architectures"))  // config.rs:175-190: the first *string* entry
+      for (auto &e : a->arr)
+        if (e.kind == Json::Str) { k.arch = e.str; break; }
+    // Per-architecture serde defaults and hard-wired flags of each into_config (llama3/config.rs:62-98,
+    // qwen2/config.rs:69-105, qwen3/config.rs:55-93, mistral/config.rs:56-93, falcon3/config.rs:53-90).
+    // Unknown strings fall back to Llama (cake/mod.rs:81-109); known architectures with another block are refused.
+    struct Arch { const char *name; double rope; int max_pos; bool bias, qk_norm, head_dim, window; };
+    static const Arch archs[] = {
+        {"LlamaForCausalLM", 500000.0, 4096, false, false, false, false},
+        {"Qwen2ForCausalLM", 1000000.0, 32768, true, false, false, false},
+        {"Qwen3ForCausalLM", 1000000.0, 40960, false, true, true, false},
+        {"MistralForCausalLM", 1000000.0, 131072, false, false, true, true},
+        {"FalconForCausalLM", 500000.0, 131072, false, false, true, false},
+    };
+    static const char *other_blocks[] = {"Qwen3_5ForConditionalGeneration", "Qwen3MoeForCausalLM",
+        "Qwen3_5MoeForConditionalGeneration", "Phi3ForCausalLM", "Phi4ForCausalLM", "Gemma3ForCausalLM",
+        "OLMo2ForCausalLM", "Olmo2ForCausalLM", "ExaoneForCausalLM", "LuxTTSForTextToSpeech"};
+    for (const char *o : other_blocks)
+      if (k.arch == o) throw Error("architecture " + k.arch + " is outside the block-forward path built here");
+    const Arch *ar = &archs[0];
+    for (auto &a : archs)
+      if (k.arch == a.name) ar = &a;
     auto &c = k.c;
     c.hidden = (int)j.number("hidden_size", 0);
     c.inter = (int)j.number("intermediate_size", 0);
@@ -160,14 +178,21 @@ struct Config {
     c.n_layers = (int)j.number("num_hidden_layers", 0);
     c.n_heads = (int)j.number("num_attention_heads", 0);
     c.n_kv_heads = (int)j.number("num_key_value_heads", c.n_heads);
-    c.head_dim = (int)j.number("head_dim", c.n_heads ? c.hidden / c.n_heads : 0);
+    const int hd_default = c.n_heads ? c.hidden / c.n_heads : 0;  // attention.rs:85
+    c.head_dim = ar->head_dim ? (int)j.number("head_dim", hd_default) : hd_default;
     c.rms_eps = (float)j.number("rms_norm_eps", 1e-5);
-    c.rope_theta = (float)j.number("rope_theta", 10000.0);
+    c.rope_theta = (float)j.number("rope_theta", ar->rope);
     c.partial_rotary = 1.0f;
-    c.max_seq = max_seq_override ? max_seq_override : (int)j.number("max_position_embeddings", 4096);
+    c.max_seq = max_seq_override ? max_seq_override : (int)j.number("max_position_embeddings", ar->max_pos);
     c.tie_embeddings = j.boolean("tie_word_embeddings", false);
-    c.qk_norm = (k.arch == "Qwen3ForCausalLM");
-    c.qkv_bias = 0;
+    c.qk_norm = ar->qk_norm;
+    c.qkv_bias = ar->bias;
+    if (ar->window) {
+      const int w = (int)j.number("sliding_window", 0);  // null / absent -> 0
+      if (w > 0 && w < c.max_seq)  // cache.rs:173-205 trims K/V to the window; the cache here is append-only
+        throw Error("sliding_window=" + std::to_string(w) + " < max_seq=" + std::to_string(c.max_seq) +
+                    ": the windowed KV trim is not built; cap --max-seq at the window");
+    }
     c.dtype = dtype;
     c.rope_factor = 1.f; c.rope_low = 1.f; c.rope_high = 4.f;
     if (const Json *rs = j.get("rope_scaling")) {

@@ -3,6 +3,7 @@
 // the path):   cake_run <model_dir> --prompt-ids 1,2,3 [-n 32] [--dtype bf16|f16] [--repeat-penalty 1.0]
 // <model_dir> holds config.json + model.safetensors (or model.safetensors.index.json + shards), HF layout.
 // Prints one line:  tokens: t0 t1 ...   and   tok/s as the reference defines it (master.rs:160-166).
+// --show-config: parse config.json only and print the resolved block configuration (needs no GPU).
 #include <cstdio>
 #include <cstdlib>
 
@@ -20,6 +21,7 @@ int main(int argc, char **argv) {
   size_t n = 32;
   int dtype = CAKE_B200_BF16, max_seq = 0;
   float rp = 1.0f;
+  bool show_config = false;
   for (int i = 2; i < argc; i++) {
     std::string a = argv[i];
     auto next = [&]() -> std::string { return i + 1 < argc ? std::string(argv[++i]) : std::string(); };
@@ -31,8 +33,18 @@ int main(int argc, char **argv) {
     else if (a == "--dtype") dtype = (next() == "f16") ? CAKE_B200_F16 : CAKE_B200_BF16;
     else if (a == "--repeat-penalty") rp = std::stof(next());
     else if (a == "--max-seq") max_seq = std::stoi(next());
+    else if (a == "--show-config") show_config = true;
   }
   try {
+    if (show_config) {
+      Config k = Config::from_path(dir + "/config.json", dtype, max_seq);
+      const auto &c = k.c;
+      printf("arch=%s hidden=%d inter=%d heads=%d kv_heads=%d head_dim=%d layers=%d vocab=%d max_seq=%d rms_eps=%g "
+             "rope_theta=%g qkv_bias=%d qk_norm=%d tie=%d rope_llama3=%d n_eos=%zu\n",
+             k.arch.c_str(), c.hidden, c.inter, c.n_heads, c.n_kv_heads, c.head_dim, c.n_layers, c.vocab, c.max_seq,
+             (double)c.rms_eps, (double)c.rope_theta, c.qkv_bias, c.qk_norm, c.tie_embeddings, c.rope_llama3, k.eos.size());
+      return 0;
+    }
     Context ctx(dir, 0, dtype, max_seq);
     auto model = TextModelBase::load(ctx);
     model->repeat_penalty = rp;

@@ -2,8 +2,9 @@
 
 Each fixture holds a seeded synthetic checkpoint's *seed* (weights are regenerated from
 cake_b200.synth, not stored), the input ids, and the fp32 logits of HuggingFace transformers
-(LlamaForCausalLM / Qwen3ForCausalLM — an independent implementation of the architectures the
-reference's llama3/ and qwen3/ wrappers load) for every position.  tests/test_oracle_golden.py
+(LlamaForCausalLM / Qwen3ForCausalLM / Qwen2ForCausalLM / MistralForCausalLM — an independent implementation
+of the architectures the reference's llama3/, qwen3/, qwen2/, mistral/ and falcon3/ wrappers load) for every
+position.  tests/test_oracle_golden.py
 checks the oracle (f32 mode) against them; the GPU parity tests then compare against the oracle.
 
     python tests/golden/make_golden.py
@@ -24,6 +25,11 @@ CASES = {
     "llama3_rope_scaled": ("LlamaForCausalLM", dict(rope_theta=500000.0,
                            rope_scaling=RopeScaling(8.0, 1.0, 4.0, 16, "llama3"))),
     "qwen3_tiny": ("Qwen3ForCausalLM", dict(head_dim=32, use_qk_norm=True, tie_word_embeddings=True)),
+    # sibling dense architectures whose block is the same path
+    "qwen2_tiny": ("Qwen2ForCausalLM", dict(use_qkv_bias=True, rope_theta=1000000.0, tie_word_embeddings=True)),
+    "mistral_tiny": ("MistralForCausalLM", dict(head_dim=32, rope_theta=1000000.0)),
+    # Falcon3 checkpoints are Llama blocks with an explicit head_dim (falcon3/config.rs:53-90); HF runs them as Llama
+    "falcon3_tiny": ("FalconForCausalLM", dict(head_dim=24, rope_theta=500000.0, num_key_value_heads=1)),
 }
 SEED, STD, N_IDS = 3, 0.1, 12
 
@@ -34,11 +40,16 @@ def case_config(name):
 
 
 def hf_logits(arch, cfg, sd, ids):
-    from transformers import LlamaConfig, LlamaForCausalLM, Qwen3Config, Qwen3ForCausalLM
+    from transformers import (LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM, Qwen2Config,
+                              Qwen2ForCausalLM, Qwen3Config, Qwen3ForCausalLM)
     d = cfg.to_hf(arch)
     d.pop("architectures")
-    if arch == "LlamaForCausalLM":
+    if arch in ("LlamaForCausalLM", "FalconForCausalLM"):
         m = LlamaForCausalLM(LlamaConfig(**d, attention_bias=False, mlp_bias=False))
+    elif arch == "Qwen2ForCausalLM":
+        m = Qwen2ForCausalLM(Qwen2Config(**d, use_sliding_window=False))
+    elif arch == "MistralForCausalLM":
+        m = MistralForCausalLM(MistralConfig(**d, sliding_window=None))
     else:
         m = Qwen3ForCausalLM(Qwen3Config(**d))
     sd = {k: v.float() for k, v in sd.items()}
@@ -51,7 +62,7 @@ def hf_logits(arch, cfg, sd, ids):
 
 def main():
     out = os.path.dirname(os.path.abspath(__file__))
-    for name in CASES:
+    for name in (sys.argv[1:] or CASES):
         arch, cfg = case_config(name)
         sd = make_checkpoint(cfg, "f32", seed=SEED, std=STD)
         ids = torch.randint(0, cfg.vocab_size, (1, N_IDS), generator=torch.Generator().manual_seed(11))

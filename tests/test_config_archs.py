@@ -1,0 +1,93 @@
+"""config.json -> block configuration for the dense architectures whose block is the path built here
+(SURVEY.md §8f-4): per-architecture serde defaults and hard-wired flags of the reference's into_config
+(llama3/config.rs:62-98, qwen2/config.rs:69-105, qwen3/config.rs:55-93, mistral/config.rs:56-93,
+falcon3/config.rs:53-90), arch detection (common/config.rs:175-190, cake/mod.rs:81-109) — the Python mirror and
+the compiled C++ host must agree."""
+import json
+import os
+import subprocess
+
+import pytest
+
+from cake_b200.build import build_host
+from cake_b200.config import CConfig, Config
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+RUN = os.path.join(ROOT, "cake_b200", "host", "cake_run")
+BASE = dict(hidden_size=64, intermediate_size=128, vocab_size=256, num_hidden_layers=2, num_attention_heads=4,
+            rms_norm_eps=1e-6)
+
+CASES = {
+    # name: (config.json extras, expected resolved fields)
+    "llama_defaults": (dict(architectures=["LlamaForCausalLM"]),
+                       dict(rope_theta=500000.0, max_seq=4096, qkv_bias=0, qk_norm=0, head_dim=16, kv_heads=4)),
+    "llama_ignores_head_dim": (dict(architectures=["LlamaForCausalLM"], head_dim=32), dict(head_dim=16)),
+    "no_architectures_is_llama": (dict(), dict(rope_theta=500000.0, max_seq=4096, qkv_bias=0)),
+    "unknown_string_is_llama": (dict(architectures=["SomethingElseLM"]), dict(rope_theta=500000.0, qk_norm=0)),
+    "first_string_entry_wins": (dict(architectures=[42, "Qwen2ForCausalLM", "LlamaForCausalLM"]), dict(qkv_bias=1)),
+    "qwen2": (dict(architectures=["Qwen2ForCausalLM"], num_key_value_heads=2, sliding_window=4096),
+              dict(rope_theta=1000000.0, max_seq=32768, qkv_bias=1, qk_norm=0, head_dim=16, kv_heads=2)),
+    "qwen3": (dict(architectures=["Qwen3ForCausalLM"], head_dim=32, tie_word_embeddings=True),
+              dict(rope_theta=1000000.0, max_seq=40960, qkv_bias=0, qk_norm=1, head_dim=32, tie=1)),
+    "mistral": (dict(architectures=["MistralForCausalLM"], head_dim=32, sliding_window=None, rope_theta=10000.0),
+                dict(rope_theta=10000.0, max_seq=131072, head_dim=32, qkv_bias=0)),
+    "falcon3": (dict(architectures=["FalconForCausalLM"], head_dim=32, num_key_value_heads=1, eos_token_id=[7, 9]),
+                dict(rope_theta=500000.0, max_seq=131072, head_dim=32, kv_heads=1, n_eos=2)),
+}
+
+
+def _python_view(d: dict) -> dict:
+    c = Config.from_hf(d)
+    cc = CConfig.from_config(c, "bf16")
+    return dict(rope_theta=float(cc.rope_theta), max_seq=cc.max_seq, qkv_bias=cc.qkv_bias, qk_norm=cc.qk_norm,
+                head_dim=cc.head_dim, kv_heads=cc.n_kv_heads, tie=cc.tie_embeddings, n_eos=len(c.eos_token_id))
+
+
+def _cpp_view(tmp_path, d: dict) -> dict:
+    build_host()
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump(d, f)
+    r = subprocess.run([RUN, str(tmp_path), "--show-config"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    kv = dict(p.split("=", 1) for p in r.stdout.split())
+    return {k: (float(v) if k in ("rope_theta", "rms_eps") else v if k == "arch" else int(v)) for k, v in kv.items()}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_python_and_cpp_resolve_the_same_block_config(tmp_path, name):
+    extra, want = CASES[name]
+    d = {**BASE, **extra}
+    py, cpp = _python_view(d), _cpp_view(tmp_path, d)
+    for k, v in want.items():
+        assert py[k] == v, (name, "python", k, py[k], v)
+        assert cpp[k] == v, (name, "c++", k, cpp[k], v)
+    for k in py:
+        assert py[k] == cpp[k], (name, k, py[k], cpp[k])
+
+
+@pytest.mark.parametrize("arch", ["Phi3ForCausalLM", "Gemma3ForCausalLM", "Qwen3MoeForCausalLM", "OLMo2ForCausalLM"])
+def test_other_block_types_are_refused_by_name(tmp_path, arch):
+    d = {**BASE, "architectures": [arch]}
+    with pytest.raises(ValueError, match="outside the block-forward path"):
+        Config.from_hf(d)
+    build_host()
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump(d, f)
+    r = subprocess.run([RUN, str(tmp_path), "--show-config"], capture_output=True, text=True)
+    assert r.returncode == 1 and "outside the block-forward path" in r.stderr
+
+
+def test_active_sliding_window_is_refused_until_the_trim_exists(tmp_path):
+    d = {**BASE, "architectures": ["MistralForCausalLM"], "sliding_window": 4096, "max_position_embeddings": 32768}
+    c = Config.from_hf(d)
+    assert c.sliding_window == 4096
+    with pytest.raises(ValueError, match="sliding_window=4096"):
+        CConfig.from_config(c, "bf16")
+    assert CConfig.from_config(c, "bf16", max_seq=4096).max_seq == 4096  # inside the window nothing is ever trimmed
+    build_host()
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump(d, f)
+    r = subprocess.run([RUN, str(tmp_path), "--show-config"], capture_output=True, text=True)
+    assert r.returncode == 1 and "sliding_window=4096" in r.stderr
+    r = subprocess.run([RUN, str(tmp_path), "--show-config", "--max-seq", "4096"], capture_output=True, text=True)
+    assert r.returncode == 0 and "max_seq=4096" in r.stdout
