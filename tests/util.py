@@ -52,3 +52,14 @@ def medium_config(**kw) -> Config:
 
 def checkpoint(cfg: Config, dtype: str, seed: int = 1234, std: float = 0.05, peaked: bool = False):
     return make_checkpoint(cfg, dtype, seed=seed, std=std, peaked=peaked)
+
+
+def f32_to_bits(a, dtype: str) -> np.ndarray:
+    """f32 values that are exactly representable in D -> their 16-bit patterns (what travels on the wire)."""
+    t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(TORCH_DTYPES[dtype])
+    return t.view(torch.uint16).numpy()
+
+
+def bits_to_f32(bits, dtype: str) -> np.ndarray:
+    t = torch.from_numpy(np.ascontiguousarray(bits, dtype=np.uint16).copy())
+    return t.view(TORCH_DTYPES[dtype]).float().numpy()
