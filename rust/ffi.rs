@@ -55,6 +55,24 @@ extern "C" {
     pub fn cake_b200_decode_run(ctx: *mut cake_b200_ctx, n_steps: c_int) -> c_int;
     pub fn cake_b200_decode_tokens(ctx: *mut cake_b200_ctx, out_host: *mut u32, n: c_int) -> c_int;
     pub fn cake_b200_decode_step_host(ctx: *mut cake_b200_ctx, token_in: u32, token_out: *mut u32) -> c_int;
+    pub fn cake_b200_decode_logits(ctx: *mut cake_b200_ctx, logits_host: *mut c_void, bytes: usize) -> c_int;
+    pub fn cake_b200_repeat_penalty_argmax(ctx: *mut cake_b200_ctx, logits_dev: *mut c_void, penalty: f32,
+        ctx_tokens_host: *const u32, n_tokens: c_int, argmax_host: *mut u32) -> c_int;
+    // fused NVLink hand-off between the shards of one box (exchange the 64-byte handles out of band)
+    pub fn cake_b200_ring_export(ctx: *mut cake_b200_ctx, handle64: *mut c_void) -> c_int;
+    pub fn cake_b200_ring_import(ctx: *mut cake_b200_ctx, next_rank_handle64: *const c_void) -> c_int;
+    // introspection / utilities
+    pub fn cake_b200_version() -> *const c_char;
+    pub fn cake_b200_stream(ctx: *mut cake_b200_ctx) -> *mut c_void;
+    pub fn cake_b200_launch_count(ctx: *mut cake_b200_ctx, kernels: *mut u64) -> c_int;
+    pub fn cake_b200_dev_alloc(ctx: *mut cake_b200_ctx, bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn cake_b200_dev_free(ctx: *mut cake_b200_ctx, p: *mut c_void) -> c_int;
+    pub fn cake_b200_block_layer(b: *const cake_b200_block) -> c_int;
+    pub fn cake_b200_cache_len(c: *const cake_b200_cache, block_idx: c_int) -> c_int;
+    pub fn cake_b200_cache_read(c: *mut cake_b200_cache, block_idx: c_int, which: c_int, out_host: *mut c_void, bytes: usize) -> c_int;
+    pub fn cake_b200_cache_fill_synthetic(c: *mut cake_b200_cache, block_idx: *const c_int, n_blocks: c_int, len: c_int, seed: u32) -> c_int;
+    pub fn cake_b200_bench_kernel(ctx: *mut cake_b200_ctx, blocks: *const *mut cake_b200_block, block_idx: *const c_int,
+        n_blocks: c_int, cache: *mut cake_b200_cache, which: c_int, reps: c_int, ms_per_launch: *mut f32) -> c_int;
 }
 
 /// `anyhow!(cake_b200_last_error())` — the library stringifies failures with context the same way

@@ -30,6 +30,33 @@ def test_every_declared_symbol_is_exported_and_bound():
         assert hasattr(L, name)
 
 
+def _prototypes(src: str, pattern: str) -> dict:
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    out = {}
+    for m in re.finditer(pattern, src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_rust_binding_declares_every_entry_point_with_the_same_arity():
+    """rust/ffi.rs cannot be compiled here (no rustc): at least its extern block must list exactly the header's
+    functions with the header's argument counts, and its config struct the header's 20 fields in order."""
+    hdr = open(os.path.join(ROOT, "include", "cake_b200.h")).read()
+    rs = open(os.path.join(ROOT, "rust", "ffi.rs")).read()
+    c = _prototypes(hdr, r"\b(cake_b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;")
+    r = _prototypes(rs, r"pub fn (cake_b200_[a-z0-9_]+)\s*\(([^;]*?)\)\s*(?:->\s*[^;]+)?;")
+    assert set(c) == set(r), set(c) ^ set(r)
+    assert {k: (c[k], r[k]) for k in c if c[k] != r[k]} == {}
+    body = re.search(r"pub struct cake_b200_config \{(.*?)\n\}", rs, flags=re.S).group(1)
+    rust_fields = re.findall(r"pub (\w+):", body)
+    assert rust_fields == [n for n, _ in CConfig._fields_]
+    rust_types = dict(re.findall(r"pub (\w+): (\w+)", body))
+    for name, ct in CConfig._fields_:
+        assert rust_types[name] == ("f32" if ct is ctypes.c_float else "c_int"), name
+
+
 def test_cconfig_matches_header_layout():
     # 20 4-byte fields, no padding
     assert ctypes.sizeof(CConfig) == 20 * 4
