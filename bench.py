@@ -429,7 +429,7 @@ def run_cuda(args):
         "metric": METRIC, "value": tok_s, "unit": "tok/s", "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"Llama-3-8B bf16, bs=1 decode, 2k context, layers sharded over {world} B200 (contiguous ranges, NCCL p2p hand-off)" if world > 1
+        "config": {"workload": f"Llama-3-8B bf16, bs=1 decode, 2k context, layers sharded over {world} B200 (contiguous ranges, one hidden-state hand-off per boundary)" if world > 1
                    else "Llama-3-8B bf16, 1xB200, bs=1 decode, 2k context (BASELINE.json configs[1])",
                    "kv_len_start": CTX_LEN + W, "kv_cache": "synthetic fill to 2048 positions (prefill is outside the metric, master.rs:131-134)",
                    "weights": "random-init N(0,0.02) bf16, HF layout, seed 1234", "greedy": True,
