@@ -57,15 +57,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_host(force: bool = False) -> str:
-    """The C++ host side (cake_b200/host/cake_host.hpp) + its `cake_run` driver, linked against the C ABI."""
-    out = os.path.join(HERE, "host", "cake_run")
-    src = os.path.join(HERE, "host", "cake_run.cc")
-    deps = [src, os.path.join(HERE, "host", "cake_host.hpp"), os.path.join(ROOT, "include", "cake_b200.h")]
-    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
-        return out
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-o", out, src, "-I", os.path.join(ROOT, "include"),
-                           "-L", HERE, "-lcake_b200", "-Wl,-rpath,$ORIGIN/.."])
-    return out
+    """The C++ host side (cake_b200/host/cake_host.hpp, cake_wire.hpp) + its drivers `cake_run` and `cake_worker`,
+    linked against the C ABI."""
+    hdrs = [os.path.join(HERE, "host", "cake_host.hpp"), os.path.join(HERE, "host", "cake_wire.hpp"),
+            os.path.join(ROOT, "include", "cake_b200.h")]
+    for name in ("cake_run", "cake_worker"):
+        out = os.path.join(HERE, "host", name)
+        src = out + ".cc"
+        if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in [src] + hdrs):
+            continue
+        subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-o", out, src, "-I", os.path.join(ROOT, "include"),
+                               "-L", HERE, "-lcake_b200", "-Wl,-rpath,$ORIGIN/.."])
+    return os.path.join(HERE, "host", "cake_run")
 
 
 if __name__ == "__main__":

@@ -261,18 +261,44 @@ class VarBuilder {
     }
   }
  public:
-  explicit VarBuilder(const std::string &dir) {
+  // `only_under`: layer prefixes a worker serves — keep a shard iff it holds a tensor under one of them
+  // (utils/mod.rs:334-384 load_var_builder_for_specific_layers); empty = every shard (utils/mod.rs:250-267).
+  explicit VarBuilder(const std::string &dir, const std::vector<std::string> &only_under = {}) {
     const std::string idx = dir + "/model.safetensors.index.json";
     if (access(idx.c_str(), R_OK) == 0) {
       std::string txt = slurp(idx);
       Json j = JsonParser(txt.data(), txt.size()).value();
+      const Json *wm = j.get("weight_map");
+      if (!wm || wm->kind != Json::Obj) throw Error("no weight map in " + idx);
       std::map<std::string, bool> files;
-      if (const Json *wm = j.get("weight_map"))
-        for (auto &kv : wm->obj) files[kv.second.str] = true;
+      for (auto &kv : wm->obj) {
+        if (kv.second.kind != Json::Str) continue;
+        bool need = only_under.empty();
+        for (auto &p : only_under)
+          if (kv.first.compare(0, p.size() + 1, p + ".") == 0) need = true;
+        if (need) files[kv.second.str] = true;
+      }
       for (auto &f : files) add_file(dir + "/" + f.first);
     } else {
       add_file(dir + "/model.safetensors");
     }
+  }
+  size_t n_files() const { return maps_.size(); }
+  // cake/mod.rs:335-357: the text before the first ".layers.0." key of the index wins over the configured prefix
+  static std::string detect_model_prefix(const std::string &dir, const std::string &configured) {
+    const std::string idx = dir + "/model.safetensors.index.json";
+    if (access(idx.c_str(), R_OK) != 0) return configured;
+    try {
+      std::string txt = slurp(idx);
+      Json j = JsonParser(txt.data(), txt.size()).value();
+      if (const Json *wm = j.get("weight_map"))
+        for (auto &kv : wm->obj) {
+          size_t pos = kv.first.find(".layers.0.");
+          if (pos != std::string::npos) return kv.first.substr(0, pos);
+        }
+    } catch (const std::exception &) {
+    }
+    return configured;
   }
   ~VarBuilder() {
     for (auto &m : maps_) munmap(m.p, m.n);
@@ -312,8 +338,10 @@ struct Context {  // cake/mod.rs:41-65
   cake_b200_ctx *h = nullptr;
   std::unique_ptr<Cache> cache;
   std::string dtype_name;
-  Context(const std::string &model_dir, int device, int dtype, int max_seq = 0)
-      : config(Config::from_path(model_dir + "/config.json", dtype, max_seq)), var_builder(new VarBuilder(model_dir)) {
+  // `worker_layers`: non-empty on a worker — only the shards that hold those layers are mapped
+  Context(const std::string &model_dir, int device, int dtype, int max_seq = 0, const std::vector<std::string> &worker_layers = {})
+      : config(Config::from_path(model_dir + "/config.json", dtype, max_seq)), var_builder(new VarBuilder(model_dir, worker_layers)) {
+    config.model_prefix = VarBuilder::detect_model_prefix(model_dir, config.model_prefix);
     dtype_name = dtype == CAKE_B200_BF16 ? "BF16" : "F16";
     check(cake_b200_ctx_create(device, &config.c, &h), "ctx_create");
     cache.reset(new Cache(h, 1, config.c.max_seq));

@@ -1,0 +1,141 @@
+// cake_worker — a cake worker endpoint on a B200 (cake's `cake run --worker`, worker.rs:79-597, for the block-forward
+// path): listens for an unmodified cake master on cake's TCP protocol (cake_wire.hpp) and runs the requested layer
+// range through libcake_b200.so (cake_host.hpp).
+//   cake_worker <model_dir> --layers model.layers.16-31 [--address 0.0.0.0:10128] [--cluster-key K]
+//               [--dtype bf16|f16] [--max-seq S] [--device 0] [--connections N]
+//   cake_worker --echo [--reflect] [--address 127.0.0.1:0] [--cluster-key K] [--connections N]    (no GPU: protocol only)
+// --layers takes the topology file's syntax (topology.rs:13,143-168): names or inclusive ranges, comma separated.
+// Prints "listening on <host>:<port>" once the socket is bound.
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <memory>
+
+#include "cake_host.hpp"
+#include "cake_wire.hpp"
+
+using namespace cake_host;
+namespace cw = cake_wire;
+
+// topology.rs:143-168: "model.layers.0-5" -> model.layers.0 .. model.layers.5 (inclusive); regex ^(.+[^\d])(\d+)-(\d+)$
+static std::vector<std::string> expand_layers(const std::string &spec) {
+  std::vector<std::string> out;
+  std::stringstream ss(spec);
+  std::string item;
+  while (std::getline(ss, item, ',')) {
+    if (item.empty()) continue;
+    size_t dash = item.rfind('-');
+    bool range = dash != std::string::npos && dash + 1 < item.size();
+    size_t b = dash;
+    if (range) {
+      for (size_t i = dash + 1; i < item.size(); i++) range = range && isdigit((unsigned char)item[i]);
+      while (b > 0 && isdigit((unsigned char)item[b - 1])) b--;
+      range = range && b < dash && b > 0;  // digits before the dash, and a non-digit base in front of them
+    }
+    if (!range) { out.push_back(item); continue; }
+    const std::string base = item.substr(0, b);
+    const long start = std::stol(item.substr(b, dash - b)), stop = std::stol(item.substr(dash + 1));
+    if (stop < start) throw Error("invalid range expression " + item + ", end must be >= start");
+    for (long n = start; n <= stop; n++) out.push_back(base + std::to_string(n));
+  }
+  return out;
+}
+
+// The worker's blocks behind the wire: host buffers in, cake_b200_forward_batch_host, host buffers out.
+struct B200Backend : cw::Backend {
+  Context &ctx;
+  std::map<std::string, std::unique_ptr<Transformer>> blocks;
+  int device_;
+  B200Backend(Context &c, const std::vector<std::string> &names, int device) : ctx(c), device_(device) {
+    for (auto &n : names) blocks[n] = Transformer::load(n, ctx);
+  }
+  std::string dtype() const override { return ctx.dtype_name; }
+  std::string device() const override { return "cuda"; }
+  uint64_t device_idx() const override { return (uint64_t)device_; }
+  void clear_cache() override { ctx.cache->clear(); }
+  cw::RawTensor forward_ops(const cw::RawTensor &x, const std::vector<cw::Op> &ops) override {
+    for (auto &o : ops)
+      if (!blocks.count(std::get<0>(o))) throw Error("could not find layer " + std::get<0>(o));  // worker.rs:513
+    const uint8_t want = ctx.dtype_name == "BF16" ? cw::BF16 : cw::F16;
+    auto where = [&](size_t i) { return "forward pass failed for layer " + std::get<0>(ops[i]) + " (block_idx=" + std::to_string(std::get<2>(ops[i])) + "): "; };
+    if (x.dtype != want) throw Error(where(0) + "activation dtype tag " + std::to_string((int)x.dtype) + " is not the model dtype " + ctx.dtype_name);
+    if (x.shape.size() != 3 || x.shape[2] != (uint64_t)ctx.config.c.hidden) throw Error(where(0) + "unexpected activation shape");
+    cw::RawTensor cur = x, next = x;
+    size_t i = 0;
+    while (i < ops.size()) {  // consecutive ops that share index_pos go down in one call (text_model.rs:298-321)
+      size_t j = i;
+      std::vector<cake_b200_block *> hs;
+      std::vector<int> idx;
+      while (j < ops.size() && std::get<1>(ops[j]) == std::get<1>(ops[i])) {
+        hs.push_back(blocks[std::get<0>(ops[j])]->handle());
+        idx.push_back((int)std::get<2>(ops[j]));
+        j++;
+      }
+      int rc = cake_b200_forward_batch_host(ctx.h, hs.data(), idx.data(), (int)hs.size(), ctx.cache->h, cur.data.data(), next.data.data(),
+                                            (int)x.shape[0], (int)x.shape[1], (int)std::get<1>(ops[i]));
+      if (rc != 0) throw Error(where(i) + cake_b200_last_error());
+      std::swap(cur, next);
+      i = j;
+    }
+    return cur;
+  }
+};
+
+int main(int argc, char **argv) {
+  std::string dir, layers, address = "127.0.0.1:10128", key;
+  bool echo = false, reflect = false, has_key = false;
+  int dtype = CAKE_B200_BF16, max_seq = 0, device = 0, connections = -1;
+  for (int i = 1; i < argc; i++) {
+    std::string a = argv[i];
+    auto next = [&]() -> std::string { return i + 1 < argc ? std::string(argv[++i]) : std::string(); };
+    if (a == "--layers") layers = next();
+    else if (a == "--address") address = next();
+    else if (a == "--cluster-key") { key = next(); has_key = true; }
+    else if (a == "--dtype") dtype = (next() == "f16") ? CAKE_B200_F16 : CAKE_B200_BF16;
+    else if (a == "--max-seq") max_seq = std::stoi(next());
+    else if (a == "--device") device = std::stoi(next());
+    else if (a == "--connections") connections = std::stoi(next());
+    else if (a == "--echo") echo = true;
+    else if (a == "--reflect") reflect = true;
+    else if (a == "--expand") {  // print the expansion of a --layers expression and exit (no GPU)
+      try {
+        for (auto &n : expand_layers(next())) printf("%s\n", n.c_str());
+      } catch (const std::exception &e) {
+        fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+      }
+      return 0;
+    } else if (dir.empty() && a[0] != '-') dir = a;
+  }
+  if (!echo && (dir.empty() || layers.empty())) {
+    fprintf(stderr, "usage: %s <model_dir> --layers model.layers.A-B [--address host:port] [--cluster-key K] [--dtype bf16|f16] "
+                    "[--max-seq S] [--device N] [--connections N]\n       %s --echo [--reflect] [--address host:port] [--cluster-key K]\n", argv[0], argv[0]);
+    return 2;
+  }
+  try {
+    const size_t colon = address.rfind(':');
+    if (colon == std::string::npos) throw Error("--address needs host:port");
+    const std::string host = address.substr(0, colon);
+    const int port = std::stoi(address.substr(colon + 1));
+    std::unique_ptr<Context> ctx;
+    std::unique_ptr<cw::Backend> be;
+    if (echo) {
+      be.reset(new cw::EchoBackend());
+    } else {
+      const std::vector<std::string> names = expand_layers(layers);
+      ctx.reset(new Context(dir, device, dtype, max_seq, names));
+      be.reset(new B200Backend(*ctx, names, device));
+    }
+    cw::WireWorker w(*be, host, port, has_key ? &key : nullptr);
+    w.reflect = reflect;
+    printf("listening on %s\n", w.address.c_str());
+    fflush(stdout);
+    w.serve(connections);
+    be.reset();
+    ctx.reset();
+  } catch (const std::exception &e) {
+    fprintf(stderr, "error: %s\n", e.what());
+    return 1;
+  }
+  return 0;
+}
