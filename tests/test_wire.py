@@ -342,3 +342,35 @@ def test_gpu_worker_behind_the_wire_equals_local_blocks():
         if w is not None:
             w.stop()
         ctx.close()
+
+
+def test_wire_remote_adapter_round_trips_model_dtype_tensors():
+    """WireRemote (the `make_remote` hook of TextModelBase.load for TCP workers): device tensor -> RawTensor -> wire ->
+    device tensor.  A stand-in ctx keeps everything on the CPU; the worker echoes."""
+    import torch
+    from cake_b200.wire import WireRemote
+
+    class Ctx:
+        dtype, torch_dtype, synced = "bf16", torch.bfloat16, 0
+
+        def sync(self):
+            self.synced += 1
+
+        def to_device(self, t):
+            return t.clone()
+
+    be = EchoBackend()
+    be.dtype = "BF16"
+    w = WireWorker(be).start()
+    try:
+        ctx = Ctx()
+        r = WireRemote(WireClient(w.address, "model.layers.2"), "model.layers.2", ctx)
+        x = (torch.arange(2 * 3 * 8, dtype=torch.float32).reshape(2, 3, 8) * 0.37).to(torch.bfloat16)
+        y = r.forward_batch(x, [("model.layers.2", 4, 2), ("model.layers.3", 4, 3)], ctx)
+        assert y.dtype == torch.bfloat16 and y.shape == x.shape and torch.equal(y, x) and ctx.synced == 1
+        assert torch.equal(r.forward(x[:1], 0, 2, ctx), x[:1])
+        assert r.ident() == w.address and r.layer_name() == "model.layers.2"
+        r.goodbye()
+        r.client.close()
+    finally:
+        w.stop()
