@@ -67,7 +67,7 @@ def build_host(force: bool = False) -> str:
         if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in [src] + hdrs):
             continue
         subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-Wall", "-o", out, src, "-I", os.path.join(ROOT, "include"),
-                               "-L", HERE, "-lcake_b200", "-Wl,-rpath,$ORIGIN/.."])
+                               "-L", HERE, "-lcake_b200", "-pthread", "-Wl,-rpath,$ORIGIN/.."])
     return os.path.join(HERE, "host", "cake_run")
 
 

@@ -20,10 +20,13 @@
 #include <sys/utsname.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <memory>
+#include <thread>
 #include <random>
 #include <stdexcept>
 #include <string>
@@ -351,23 +354,29 @@ inline void authenticate_as_master(int fd, const std::string &key) {  // auth.rs
 }
 
 // ------------------------------------------------------------------------------------------ worker side
+// One Session per master connection = one KV cache (the reference clones a fresh cache per connection, worker.rs:60-75;
+// a cake master opens one connection per remote LAYER, text_model.rs:211-227, so many are open at once).
+struct Session {
+  virtual ~Session() = default;
+  virtual void clear_cache() = 0;
+  virtual RawTensor forward_ops(const RawTensor &x, const std::vector<Op> &ops) = 0;  // throws std::exception with the reason
+};
 struct Backend {  // the compute behind a worker endpoint
   virtual ~Backend() = default;
   virtual std::string dtype() const = 0;                 // "BF16" | "F16" (Debug form of candle's DType, worker.rs:55)
   virtual std::string device() const = 0;                // "cuda" | "cpu"
   virtual uint64_t device_idx() const { return 0; }
-  virtual void clear_cache() = 0;
-  virtual RawTensor forward_ops(const RawTensor &x, const std::vector<Op> &ops) = 0;  // throws std::exception with the reason
+  virtual std::unique_ptr<Session> new_session() = 0;    // called from the connection's thread
 };
 
-class WireWorker {  // worker.rs:79-597; one master connection at a time (one KV cache behind the backend)
+class WireWorker {  // worker.rs:79-597; one thread per master connection (the reference: one tokio task)
   Backend &be_;
   std::string key_;
   bool has_key_;
   int lfd_ = -1;
  public:
   std::string address;
-  size_t served = 0;
+  std::atomic<size_t> served{0};
   bool reflect = false;  // test aid: after the handshake, answer every message with the same message re-encoded
 
   WireWorker(Backend &be, const std::string &host, int port, const std::string *cluster_key) : be_(be), key_(cluster_key ? *cluster_key : ""), has_key_(cluster_key != nullptr) {
@@ -380,7 +389,7 @@ class WireWorker {  // worker.rs:79-597; one master connection at a time (one KV
     a.sin_port = htons((uint16_t)port);
     if (inet_pton(AF_INET, host.c_str(), &a.sin_addr) != 1) throw std::runtime_error("bad listen address " + host);
     if (::bind(lfd_, (sockaddr *)&a, sizeof a) != 0) throw std::runtime_error("can't bind " + host + ":" + std::to_string(port));
-    if (::listen(lfd_, 4) != 0) throw std::runtime_error("listen() failed");
+    if (::listen(lfd_, 64) != 0) throw std::runtime_error("listen() failed");
     socklen_t len = sizeof a;
     getsockname(lfd_, (sockaddr *)&a, &len);
     address = host + ":" + std::to_string(ntohs(a.sin_port));
@@ -418,7 +427,7 @@ class WireWorker {  // worker.rs:79-597; one master connection at a time (one KV
       return;
     }
     if (first.kind != Message::Hello) throw ProtocolError("unexpected first message (expected Hello)");
-    be_.clear_cache();  // a new master connection starts from an empty cache (worker.rs:60-75 clones a fresh one)
+    std::unique_ptr<Session> sess = be_.new_session();  // a fresh, empty cache for this connection
     write_message(fd, Message::worker_info(to_info(ms(t0))));
     for (;;) {
       auto t1 = std::chrono::steady_clock::now();
@@ -430,7 +439,7 @@ class WireWorker {  // worker.rs:79-597; one master connection at a time (one KV
       }
       if (reflect) { write_message(fd, m); continue; }
       if (m.kind == Message::Goodbye) {  // :363-383
-        be_.clear_cache();
+        sess->clear_cache();
         write_message(fd, Message::worker_info(to_info(ms(t1))));
         continue;
       }
@@ -441,7 +450,7 @@ class WireWorker {  // worker.rs:79-597; one master connection at a time (one KV
       try {
         if (ops.empty()) throw std::runtime_error("empty batch");
         m.x.validate();
-        RawTensor y = be_.forward_ops(m.x, ops);
+        RawTensor y = sess->forward_ops(m.x, ops);
         write_message(fd, Message::tensor(std::move(y)));
         served++;
       } catch (const ConnectionClosed &) {
@@ -452,32 +461,44 @@ class WireWorker {  // worker.rs:79-597; one master connection at a time (one KV
     }
   }
 
-  // Accept loop (worker.rs:577-597).  max_connections < 0: forever.
+  // Accept loop (worker.rs:577-597): one thread per connection.  max_connections < 0: forever; otherwise return once
+  // that many connections have been accepted and have ended.
   void serve(int max_connections = -1) {
+    std::vector<std::thread> threads;
     for (int n = 0; max_connections < 0 || n < max_connections; n++) {
       int fd = ::accept(lfd_, nullptr, nullptr);
-      if (fd < 0) return;
-      try {
-        handle_master_client(fd);
-      } catch (const std::exception &e) {
-        fprintf(stderr, "[worker] connection ended: %s\n", e.what());
+      if (fd < 0) break;
+      threads.emplace_back([this, fd]() {
+        try {
+          handle_master_client(fd);
+        } catch (const std::exception &e) {
+          fprintf(stderr, "[worker] connection ended: %s\n", e.what());
+        }
+        ::close(fd);
+      });
+      if (max_connections < 0 && threads.size() > 256) {  // reap finished threads now and then
+        for (auto &t : threads) t.join();
+        threads.clear();
       }
-      ::close(fd);
     }
+    for (auto &t : threads) t.join();
   }
 };
 
 // A backend that echoes the activation (tests/protocol.rs MockWorker); "model.layers.99" is reported missing.
 struct EchoBackend : Backend {
-  size_t cleared = 0;
+  std::atomic<size_t> sessions{0};
+  struct S : Session {
+    void clear_cache() override {}
+    RawTensor forward_ops(const RawTensor &x, const std::vector<Op> &ops) override {
+      for (auto &o : ops)
+        if (std::get<0>(o) == "model.layers.99") throw std::runtime_error("could not find layer " + std::get<0>(o));
+      return x;
+    }
+  };
   std::string dtype() const override { return "F16"; }
   std::string device() const override { return "cpu"; }
-  void clear_cache() override { cleared++; }
-  RawTensor forward_ops(const RawTensor &x, const std::vector<Op> &ops) override {
-    for (auto &o : ops)
-      if (std::get<0>(o) == "model.layers.99") throw std::runtime_error("could not find layer " + std::get<0>(o));
-    return x;
-  }
+  std::unique_ptr<Session> new_session() override { sessions++; return std::unique_ptr<Session>(new S()); }
 };
 
 }  // namespace cake_wire

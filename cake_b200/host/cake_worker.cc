@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <map>
 #include <memory>
+#include <mutex>
 
 #include "cake_host.hpp"
 #include "cake_wire.hpp"
@@ -41,44 +42,67 @@ static std::vector<std::string> expand_layers(const std::string &spec) {
   return out;
 }
 
-// The worker's blocks behind the wire: host buffers in, cake_b200_forward_batch_host, host buffers out.
+// The worker's blocks behind the wire: host buffers in, cake_b200_forward_batch_host, host buffers out.  Every
+// connection has its own KV cache (K/V pages are allocated per layer on first use, so idle sessions cost nothing);
+// forwards share the ctx's stream and scratch and are serialised by a mutex.
 struct B200Backend : cw::Backend {
   Context &ctx;
   std::map<std::string, std::unique_ptr<Transformer>> blocks;
   int device_;
+  std::mutex mu;
   B200Backend(Context &c, const std::vector<std::string> &names, int device) : ctx(c), device_(device) {
     for (auto &n : names) blocks[n] = Transformer::load(n, ctx);
   }
   std::string dtype() const override { return ctx.dtype_name; }
   std::string device() const override { return "cuda"; }
   uint64_t device_idx() const override { return (uint64_t)device_; }
-  void clear_cache() override { ctx.cache->clear(); }
-  cw::RawTensor forward_ops(const cw::RawTensor &x, const std::vector<cw::Op> &ops) override {
-    for (auto &o : ops)
-      if (!blocks.count(std::get<0>(o))) throw Error("could not find layer " + std::get<0>(o));  // worker.rs:513
-    const uint8_t want = ctx.dtype_name == "BF16" ? cw::BF16 : cw::F16;
-    auto where = [&](size_t i) { return "forward pass failed for layer " + std::get<0>(ops[i]) + " (block_idx=" + std::to_string(std::get<2>(ops[i])) + "): "; };
-    if (x.dtype != want) throw Error(where(0) + "activation dtype tag " + std::to_string((int)x.dtype) + " is not the model dtype " + ctx.dtype_name);
-    if (x.shape.size() != 3 || x.shape[2] != (uint64_t)ctx.config.c.hidden) throw Error(where(0) + "unexpected activation shape");
-    cw::RawTensor cur = x, next = x;
-    size_t i = 0;
-    while (i < ops.size()) {  // consecutive ops that share index_pos go down in one call (text_model.rs:298-321)
-      size_t j = i;
-      std::vector<cake_b200_block *> hs;
-      std::vector<int> idx;
-      while (j < ops.size() && std::get<1>(ops[j]) == std::get<1>(ops[i])) {
-        hs.push_back(blocks[std::get<0>(ops[j])]->handle());
-        idx.push_back((int)std::get<2>(ops[j]));
-        j++;
-      }
-      int rc = cake_b200_forward_batch_host(ctx.h, hs.data(), idx.data(), (int)hs.size(), ctx.cache->h, cur.data.data(), next.data.data(),
-                                            (int)x.shape[0], (int)x.shape[1], (int)std::get<1>(ops[i]));
-      if (rc != 0) throw Error(where(i) + cake_b200_last_error());
-      std::swap(cur, next);
-      i = j;
+
+  struct S : cw::Session {
+    B200Backend &be;
+    std::unique_ptr<Cache> cache;
+    explicit S(B200Backend &b) : be(b) {
+      std::lock_guard<std::mutex> g(be.mu);
+      cache = be.ctx.cache->as_new();  // worker.rs:60-75
     }
-    return cur;
-  }
+    ~S() override {
+      std::lock_guard<std::mutex> g(be.mu);
+      cake_b200_sync(be.ctx.h);
+      cache.reset();
+    }
+    void clear_cache() override {
+      std::lock_guard<std::mutex> g(be.mu);
+      cache->clear();
+    }
+    cw::RawTensor forward_ops(const cw::RawTensor &x, const std::vector<cw::Op> &ops) override {
+      Context &ctx = be.ctx;
+      for (auto &o : ops)
+        if (!be.blocks.count(std::get<0>(o))) throw Error("could not find layer " + std::get<0>(o));  // worker.rs:513
+      const uint8_t want = ctx.dtype_name == "BF16" ? cw::BF16 : cw::F16;
+      auto where = [&](size_t i) { return "forward pass failed for layer " + std::get<0>(ops[i]) + " (block_idx=" + std::to_string(std::get<2>(ops[i])) + "): "; };
+      if (x.dtype != want) throw Error(where(0) + "activation dtype tag " + std::to_string((int)x.dtype) + " is not the model dtype " + ctx.dtype_name);
+      if (x.shape.size() != 3 || x.shape[2] != (uint64_t)ctx.config.c.hidden) throw Error(where(0) + "unexpected activation shape");
+      cw::RawTensor cur = x, next = x;
+      std::lock_guard<std::mutex> g(be.mu);
+      size_t i = 0;
+      while (i < ops.size()) {  // consecutive ops that share index_pos go down in one call (text_model.rs:298-321)
+        size_t j = i;
+        std::vector<cake_b200_block *> hs;
+        std::vector<int> idx;
+        while (j < ops.size() && std::get<1>(ops[j]) == std::get<1>(ops[i])) {
+          hs.push_back(be.blocks[std::get<0>(ops[j])]->handle());
+          idx.push_back((int)std::get<2>(ops[j]));
+          j++;
+        }
+        int rc = cake_b200_forward_batch_host(ctx.h, hs.data(), idx.data(), (int)hs.size(), cache->h, cur.data.data(), next.data.data(),
+                                              (int)x.shape[0], (int)x.shape[1], (int)std::get<1>(ops[i]));
+        if (rc != 0) throw Error(where(i) + cake_b200_last_error());
+        std::swap(cur, next);
+        i = j;
+      }
+      return cur;
+    }
+  };
+  std::unique_ptr<cw::Session> new_session() override { return std::unique_ptr<cw::Session>(new S(*this)); }
 };
 
 int main(int argc, char **argv) {

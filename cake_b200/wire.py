@@ -389,53 +389,79 @@ def authenticate_as_worker(sock: socket.socket, key: str) -> None:
 # ------------------------------------------------------------------------------------------ worker side
 class B200Backend:
     """The compute behind a WireWorker on a B200: the worker's blocks through ``cake_b200_forward_batch_host``
-    (host buffers in, host buffers out; the H2D/D2H copies happen inside the C ABI call)."""
+    (host buffers in, host buffers out; the H2D/D2H copies happen inside the C ABI call).
+
+    Every master connection gets its own session = its own KV cache (the reference clones a fresh cache per
+    connection, worker.rs:60-75 — and a cake master opens one connection per remote *layer*, text_model.rs:211-227,
+    so many sessions are open at once while only the first of a contiguous run carries traffic).  K/V pages of a cache
+    are allocated per layer on first use, so idle sessions cost nothing.  Forwards of different sessions share the
+    ctx's stream and scratch and are serialised by a lock."""
 
     def __init__(self, ctx, blocks: Dict[str, "object"]):
         self.ctx, self.blocks = ctx, dict(blocks)
         self.dtype = ctx.dtype
+        self.lock = threading.Lock()
 
     def info(self) -> Tuple[str, int]:
         return "cuda", int(self.ctx.device)
 
+    def new_session(self) -> "_B200Session":
+        return _B200Session(self)
+
+
+class _B200Session:
+    def __init__(self, be: B200Backend):
+        from .model import Cache
+        self.be = be
+        with be.lock:
+            self.cache = Cache(be.ctx)
+
     def clear_cache(self) -> None:
-        self.ctx.cache.clear()
+        with self.be.lock:
+            self.cache.clear()
+
+    def close(self) -> None:
+        with self.be.lock:
+            self.be.ctx.sync()
+            self.cache.close()
 
     def forward_ops(self, x: RawTensor, ops: Sequence[Op]) -> RawTensor:
         from .capi import check, int_array, lib, ptr_array
+        be, ctx = self.be, self.be.ctx
         for name, _, _ in ops:
-            if name not in self.blocks:
+            if name not in be.blocks:
                 raise LookupError(f"could not find layer {name}")  # worker.rs:513
-        if x.dtype_name != self.dtype:
+        if x.dtype_name != be.dtype:
             raise ValueError(f"forward pass failed for layer {ops[0][0]} (block_idx={ops[0][2]}): activation dtype "
-                             f"{x.dtype_name} != model dtype {self.dtype}")
+                             f"{x.dtype_name} != model dtype {be.dtype}")
         a = x.to_numpy_bits()
-        if a.ndim != 3 or a.shape[2] != self.ctx.config.hidden_size:
+        if a.ndim != 3 or a.shape[2] != ctx.config.hidden_size:
             raise ValueError(f"forward pass failed for layer {ops[0][0]} (block_idx={ops[0][2]}): unexpected shape {x.shape}")
         a = np.ascontiguousarray(a)
         # consecutive ops that share index_pos go down in one call (they always do: text_model.rs:298-321)
         i = 0
-        while i < len(ops):
-            j = i
-            while j < len(ops) and ops[j][1] == ops[i][1]:
-                j += 1
-            y = np.empty_like(a)
-            hs = [self.blocks[n].h for n, _, _ in ops[i:j]]
-            rc = lib().cake_b200_forward_batch_host(self.ctx.h, ptr_array(hs), int_array([b for _, _, b in ops[i:j]]),
-                                                    j - i, self.ctx.cache.h, a.ctypes.data, y.ctypes.data,
-                                                    a.shape[0], a.shape[1], ops[i][1])
-            try:
-                check(rc)
-            except Exception as e:
-                raise RuntimeError(f"forward pass failed for layer {ops[i][0]} (block_idx={ops[i][2]}): {e}") from e
-            a, i = y, j
-        return RawTensor.from_numpy_bits(a, self.dtype)
+        with be.lock:
+            while i < len(ops):
+                j = i
+                while j < len(ops) and ops[j][1] == ops[i][1]:
+                    j += 1
+                y = np.empty_like(a)
+                hs = [be.blocks[n].h for n, _, _ in ops[i:j]]
+                rc = lib().cake_b200_forward_batch_host(ctx.h, ptr_array(hs), int_array([b for _, _, b in ops[i:j]]),
+                                                        j - i, self.cache.h, a.ctypes.data, y.ctypes.data,
+                                                        a.shape[0], a.shape[1], ops[i][1])
+                try:
+                    check(rc)
+                except Exception as e:
+                    raise RuntimeError(f"forward pass failed for layer {ops[i][0]} (block_idx={ops[i][2]}): {e}") from e
+                a, i = y, j
+        return RawTensor.from_numpy_bits(a, be.dtype)
 
 
 class WireWorker:
-    """One cake worker endpoint (worker.rs:79-597) in front of a backend.  Connections are served one at a time —
-    the backend has one KV cache, and a new master connection starts from a cleared cache (the reference clones a
-    fresh cache per connection, worker.rs:60-75)."""
+    """One cake worker endpoint (worker.rs:79-597) in front of a backend.  One thread per master connection (the
+    reference spawns a task per connection); a backend that offers ``new_session()`` gives every connection its own
+    KV cache, a plain backend object (tests) is shared by all connections."""
 
     VERSION = "cake-b200"
 
@@ -444,11 +470,14 @@ class WireWorker:
         self.sock = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
         self.sock.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
         self.sock.bind((host, port))
-        self.sock.listen(4)
+        self.sock.listen(64)
         self.address = "%s:%d" % self.sock.getsockname()
         self.served = 0
+        self.connections = 0
         self._stop = threading.Event()
         self._thread: Optional[threading.Thread] = None
+        self._conn_threads: List[threading.Thread] = []
+        self._conns: List[socket.socket] = []
 
     def to_info(self, latency_ms: int) -> WorkerInfo:
         """worker.rs:47-57 (dtype is the Debug form of candle's DType: "BF16", "F16")."""
@@ -470,8 +499,17 @@ class WireWorker:
             return
         if first.kind != "Hello":
             raise ProtocolError(f"unexpected first message (expected Hello): {first.kind}")
-        self.backend.clear_cache()
-        Message("WorkerInfo", info=self.to_info(latency)).to_writer(conn)
+        sess = self.backend.new_session() if hasattr(self.backend, "new_session") else self.backend
+        try:
+            if sess is self.backend:
+                sess.clear_cache()
+            Message("WorkerInfo", info=self.to_info(latency)).to_writer(conn)
+            self._serve_session(conn, sess)
+        finally:
+            if sess is not self.backend:
+                sess.close()
+
+    def _serve_session(self, conn: socket.socket, sess) -> None:
         while True:
             t0 = time.perf_counter()
             try:
@@ -480,7 +518,7 @@ class WireWorker:
                 return  # the reference's `while let Ok(..)` ends the same way
             read_ms = (time.perf_counter() - t0) * 1e3
             if msg.kind == "Goodbye":  # :363-383
-                self.backend.clear_cache()
+                sess.clear_cache()
                 Message("WorkerInfo", info=self.to_info(read_ms)).to_writer(conn)
                 continue
             if msg.kind == "SingleOp":
@@ -492,12 +530,20 @@ class WireWorker:
             try:
                 if not ops:
                     raise ValueError("empty batch")
-                y = self.backend.forward_ops(x.validate(), ops)
+                y = sess.forward_ops(x.validate(), ops)
             except Exception as e:  # :490-520: report, keep the connection
                 Message.worker_error(str(e)).to_writer(conn)
                 continue
             Message.from_tensor(y).to_writer(conn)
             self.served += 1
+
+    def _connection(self, conn: socket.socket) -> None:
+        with conn:
+            conn.settimeout(None)
+            try:
+                self.handle_master_client(conn)
+            except (ProtocolError, ConnectionError, OSError):
+                pass  # worker.rs:586-593: log and keep accepting
 
     def serve_forever(self) -> None:
         self.sock.settimeout(0.2)
@@ -508,12 +554,11 @@ class WireWorker:
                 continue
             except OSError:
                 return
-            with conn:
-                conn.settimeout(None)
-                try:
-                    self.handle_master_client(conn)
-                except (ProtocolError, ConnectionError, OSError):
-                    pass  # worker.rs:586-593: log and keep accepting
+            self.connections += 1
+            t = threading.Thread(target=self._connection, args=(conn,), daemon=True)
+            self._conns.append(conn)
+            self._conn_threads.append(t)
+            t.start()
 
     def start(self) -> "WireWorker":
         self._thread = threading.Thread(target=self.serve_forever, daemon=True)
@@ -525,6 +570,13 @@ class WireWorker:
         if self._thread:
             self._thread.join(timeout=5)
         self.sock.close()
+        for c in self._conns:  # unblock connection threads still waiting for a message
+            try:
+                c.shutdown(socket.SHUT_RDWR)
+            except OSError:
+                pass
+        for t in self._conn_threads:
+            t.join(timeout=5)
 
 
 # ------------------------------------------------------------------------------------------ master side

@@ -256,23 +256,36 @@ def test_layer_assignment_first_message_is_acked():
 
 # ---- a model split over the wire reproduces the unsplit model -------------------------------------------------------------
 class OracleBackend:
-    """Stand-in for B200Backend in CPU tests: the worker's layers run through the oracle."""
+    """Stand-in for B200Backend in CPU tests: the worker's layers run through the oracle; like B200Backend every
+    connection gets its own session (= its own KV cache)."""
 
-    def __init__(self, model, cache, dtype):
-        self.model, self.cache, self.dtype = model, cache, dtype
+    def __init__(self, model, dtype):
+        self.model, self.dtype, self.sessions = model, dtype, 0
 
     def info(self):
         return "cpu", 0
 
+    def new_session(self):
+        self.sessions += 1
+        return _OracleSession(self)
+
+
+class _OracleSession:
+    def __init__(self, be):
+        self.be, self.cache = be, be.model.new_cache()
+
     def clear_cache(self):
         self.cache.clear()
 
+    def close(self):
+        self.cache = None
+
     def forward_ops(self, x, ops):
         from tests.util import bits_to_f32, f32_to_bits
-        h = bits_to_f32(x.to_numpy_bits(), self.dtype)
+        h = bits_to_f32(x.to_numpy_bits(), self.be.dtype)
         for name, pos, idx in ops:
-            h = self.model.block_forward(idx, h, pos, self.cache)
-        return RawTensor.from_numpy_bits(f32_to_bits(h, self.dtype), self.dtype)
+            h = self.be.model.block_forward(idx, h, pos, self.cache)
+        return RawTensor.from_numpy_bits(f32_to_bits(h, self.be.dtype), self.be.dtype)
 
 
 def test_split_model_over_the_wire_equals_unsplit_oracle():
@@ -285,9 +298,11 @@ def test_split_model_over_the_wire_equals_unsplit_oracle():
     want, _ = full.generate(prompt, 6)
 
     remote = O.OracleModel(cfg, sd, "bf16", max_seq=64)
-    w = WireWorker(OracleBackend(remote, remote.new_cache(), "bf16")).start()
+    w = WireWorker(OracleBackend(remote, "bf16")).start()
     try:
+        # a cake master opens one connection per remote layer (text_model.rs:211-227) and drives the run through the first
         c = WireClient(w.address, cfg.layer_name(2))
+        idle = WireClient(w.address, cfg.layer_name(3))
         local = O.OracleModel(cfg, sd, "bf16", max_seq=64)
         cache = local.new_cache()
         ids, pos, got = list(prompt), 0, []
@@ -301,11 +316,17 @@ def test_split_model_over_the_wire_equals_unsplit_oracle():
             got.append(tok)
             pos += len(ids)
             ids = [tok]
-        c.goodbye()
-        c.close()
+        # a second session on the same worker starts from its own empty cache: position 0 is accepted again
+        h0 = local.embed(prompt)
+        again = idle.forward_batch(RawTensor.from_numpy_bits(f32_to_bits(local.forward_layers(h0, 0, 2, 0, local.new_cache()), "bf16"), "bf16"),
+                                   [(cfg.layer_name(i), 0, i) for i in (2, 3)])
+        assert again.shape == [len(prompt), cfg.hidden_size]
+        for cl in (c, idle):  # text_model.rs:517-528: goodbye goes to every block
+            cl.goodbye()
+            cl.close()
     finally:
         w.stop()
-    assert got == list(want)
+    assert got == list(want) and w.backend.sessions == 2 and w.connections == 2
 
 
 @pytest.mark.gpu
@@ -336,8 +357,11 @@ def test_gpu_worker_behind_the_wire_equals_local_blocks():
         assert y.shape == [1, 5, cfg.hidden_size] and np.array_equal(y.to_numpy_bits(), y_local)
         with pytest.raises(RuntimeError, match="could not find layer"):
             c.forward_batch(raw, [(cfg.layer_name(0), 0, 0)])
-        c.goodbye()
-        c.close()
+        other = WireClient(w.address, cfg.layer_name(3), timeout=60)   # second open connection = its own, empty KV cache
+        assert np.array_equal(other.forward_batch(raw, batch).to_numpy_bits(), y_local)
+        for cl in (c, other):
+            cl.goodbye()
+            cl.close()
     finally:
         if w is not None:
             w.stop()
@@ -374,3 +398,22 @@ def test_wire_remote_adapter_round_trips_model_dtype_tensors():
         r.client.close()
     finally:
         w.stop()
+
+
+def test_many_connections_at_once_like_a_cake_master():
+    """One Client per remote layer, all opened before any traffic (text_model.rs:211-227): every Hello must be answered
+    while the earlier connections stay open."""
+    w = WireWorker(EchoBackend()).start()
+    try:
+        clients = [WireClient(w.address, f"model.layers.{i}", timeout=5) for i in range(16, 32)]
+        t = raw_f16([1, 1, 64])
+        batch = [(f"model.layers.{i}", 7, i) for i in range(16, 32)]
+        for _ in range(3):
+            assert clients[0].forward_batch(t, batch).data == t.data
+        assert clients[5].forward_mut(t, 0, 21).data == t.data
+        for c in clients:
+            c.goodbye()
+            c.close()
+    finally:
+        w.stop()
+    assert w.connections == 16 and w.served == 4

@@ -192,8 +192,9 @@ def test_gpu_cpp_worker_equals_local_blocks(tmp_path):
         y1_local = y1_local.cpu().view(torch.uint16).numpy()
     finally:
         ctx.close()
-    with Proc(str(tmp_path), "--layers", "model.layers.2-3", "--max-seq", "64", "--address", "127.0.0.1:0", "--connections", "1") as w:
+    with Proc(str(tmp_path), "--layers", "model.layers.2-3", "--max-seq", "64", "--address", "127.0.0.1:0", "--connections", "2") as w:
         c = WireClient(w.address, cfg.layer_name(2), timeout=120)
+        other = WireClient(w.address, cfg.layer_name(3), timeout=120)   # a second open connection = its own KV cache
         assert c.info.device == "cuda" and c.info.dtype == "BF16"
         y = c.forward_batch(RawTensor.from_numpy_bits(x.view(torch.uint16).numpy(), "bf16"), batch)
         assert y.shape == [1, 5, cfg.hidden_size] and np.array_equal(y.to_numpy_bits(), y_local)
@@ -203,6 +204,26 @@ def test_gpu_cpp_worker_equals_local_blocks(tmp_path):
             c.forward_batch(RawTensor.from_numpy_bits(x1.view(torch.uint16).numpy(), "bf16"), [(cfg.layer_name(0), 6, 0)])
         with pytest.raises(RuntimeError, match="forward pass failed for layer"):   # position out of order: reported, not fatal
             c.forward_batch(RawTensor.from_numpy_bits(x1.view(torch.uint16).numpy(), "bf16"), [(cfg.layer_name(2), 9, 2)])
-        c.goodbye()
-        c.close()
+        # the other session's cache is still empty: the same prefill at position 0 is accepted there and gives the same bits
+        y2 = other.forward_batch(RawTensor.from_numpy_bits(x.view(torch.uint16).numpy(), "bf16"), batch)
+        assert np.array_equal(y2.to_numpy_bits(), y_local)
+        for cl in (c, other):
+            cl.goodbye()
+            cl.close()
         assert w.close(30) == 0
+
+
+def test_cpp_worker_serves_many_open_connections_like_a_cake_master():
+    """text_model.rs:211-227 opens one Client per remote layer before any traffic: all Hellos must be answered while
+    the earlier connections stay open; only the first connection of the run carries the batch."""
+    with Proc("--echo", "--address", "127.0.0.1:0", "--connections", "16") as w:
+        clients = [WireClient(w.address, f"model.layers.{i}", timeout=10) for i in range(16, 32)]
+        t = raw_f16([1, 1, 64])
+        batch = [(f"model.layers.{i}", 7, i) for i in range(16, 32)]
+        for _ in range(3):
+            assert clients[0].forward_batch(t, batch).data == t.data
+        assert clients[5].forward_mut(t, 0, 21).data == t.data
+        for c in clients:
+            c.goodbye()
+            c.close()
+        assert w.close() == 0
