@@ -3,6 +3,8 @@
 // range through libcake_b200.so (cake_host.hpp).
 //   cake_worker <model_dir> --layers model.layers.16-31 [--address 0.0.0.0:10128] [--cluster-key K]
 //               [--dtype bf16|f16] [--max-seq S] [--device 0] [--connections N]
+//   cake_worker <model_dir> --topology topology.yml --name worker1 ...   (layers from the master's topology file)
+//   cake_worker --topology topology.yml --name worker1                    (dry run: print the expanded layer list)
 //   cake_worker --echo [--reflect] [--address 127.0.0.1:0] [--cluster-key K] [--connections N]    (no GPU: protocol only)
 // --layers takes the topology file's syntax (topology.rs:13,143-168): names or inclusive ranges, comma separated.
 // Prints "listening on <host>:<port>" once the socket is bound.
@@ -40,6 +42,70 @@ static std::vector<std::string> expand_layers(const std::string &spec) {
     for (long n = start; n <= stop; n++) out.push_back(base + std::to_string(n));
   }
   return out;
+}
+
+// The subset of YAML a cake topology file uses (topology.rs:15-40,126-168): a map  worker-name -> { host: str,
+// description: str, layers: [str, ...] (block list "- item" or inline "[a, b]"), other scalars ignored }.
+struct TopologyNode {
+  std::string host;
+  std::vector<std::string> layers;  // as written (ranges not expanded)
+};
+static std::string yaml_scalar(std::string s) {
+  size_t hash = std::string::npos;
+  bool in_s = false, in_d = false;
+  for (size_t i = 0; i < s.size(); i++) {
+    if (s[i] == '\'' && !in_d) in_s = !in_s;
+    else if (s[i] == '"' && !in_s) in_d = !in_d;
+    else if (s[i] == '#' && !in_s && !in_d && (i == 0 || isspace((unsigned char)s[i - 1]))) { hash = i; break; }
+  }
+  if (hash != std::string::npos) s = s.substr(0, hash);
+  size_t a = s.find_first_not_of(" \t\r"), b = s.find_last_not_of(" \t\r");
+  if (a == std::string::npos) return "";
+  s = s.substr(a, b - a + 1);
+  if (s.size() >= 2 && ((s.front() == '"' && s.back() == '"') || (s.front() == '\'' && s.back() == '\''))) s = s.substr(1, s.size() - 2);
+  return s;
+}
+static std::map<std::string, TopologyNode> parse_topology(const std::string &text) {
+  std::map<std::string, TopologyNode> topo;
+  std::stringstream ss(text);
+  std::string line, cur, key;
+  while (std::getline(ss, line)) {
+    const size_t ind = line.find_first_not_of(" \t");
+    if (ind == std::string::npos || line[ind] == '#' || line.compare(ind, 3, "---") == 0) continue;
+    std::string body = line.substr(ind);
+    if (ind == 0) {  // "name:"
+      const size_t c = body.find(':');
+      if (c == std::string::npos) throw Error("topology: expected 'name:' at '" + body + "'");
+      cur = yaml_scalar(body.substr(0, c));
+      topo[cur];
+      key.clear();
+      continue;
+    }
+    if (cur.empty()) throw Error("topology: indented line before any worker name");
+    if (body[0] == '-') {  // list item of the last key
+      if (key == "layers") topo[cur].layers.push_back(yaml_scalar(body.substr(1)));
+      continue;
+    }
+    const size_t c = body.find(':');
+    if (c == std::string::npos) continue;
+    key = yaml_scalar(body.substr(0, c));
+    std::string val = yaml_scalar(body.substr(c + 1));
+    if (key == "host") topo[cur].host = val;
+    else if (key == "layers" && !val.empty() && val.front() == '[') {  // inline list
+      std::stringstream ls(val.substr(1, val.rfind(']') == std::string::npos ? std::string::npos : val.rfind(']') - 1));
+      std::string item;
+      while (std::getline(ls, item, ',')) {
+        item = yaml_scalar(item);
+        if (!item.empty()) topo[cur].layers.push_back(item);
+      }
+    }
+  }
+  return topo;
+}
+static std::string join(const std::vector<std::string> &v) {
+  std::string s;
+  for (auto &x : v) s += (s.empty() ? "" : ",") + x;
+  return s;
 }
 
 // The worker's blocks behind the wire: host buffers in, cake_b200_forward_batch_host, host buffers out.  Every
@@ -106,7 +172,7 @@ struct B200Backend : cw::Backend {
 };
 
 int main(int argc, char **argv) {
-  std::string dir, layers, address = "127.0.0.1:10128", key;
+  std::string dir, layers, address = "127.0.0.1:10128", key, topology, name;
   bool echo = false, reflect = false, has_key = false;
   int dtype = CAKE_B200_BF16, max_seq = 0, device = 0, connections = -1;
   for (int i = 1; i < argc; i++) {
@@ -119,6 +185,8 @@ int main(int argc, char **argv) {
     else if (a == "--max-seq") max_seq = std::stoi(next());
     else if (a == "--device") device = std::stoi(next());
     else if (a == "--connections") connections = std::stoi(next());
+    else if (a == "--topology") topology = next();
+    else if (a == "--name") name = next();
     else if (a == "--echo") echo = true;
     else if (a == "--reflect") reflect = true;
     else if (a == "--expand") {  // print the expansion of a --layers expression and exit (no GPU)
@@ -130,6 +198,20 @@ int main(int argc, char **argv) {
       }
       return 0;
     } else if (dir.empty() && a[0] != '-') dir = a;
+  }
+  if (!topology.empty()) {  // `cake run --mode worker --name N --topology T` picks the node's layers (worker.rs:150-154)
+    try {
+      auto topo = parse_topology(slurp(topology));
+      if (!topo.count(name)) throw Error("could not find topology node for worker '" + name + "'");
+      if (layers.empty()) layers = join(topo[name].layers);
+      if (dir.empty() && !echo) {  // --expand-topology style dry run: print what this worker would serve
+        for (auto &n : expand_layers(layers)) printf("%s\n", n.c_str());
+        return 0;
+      }
+    } catch (const std::exception &e) {
+      fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
   }
   if (!echo && (dir.empty() || layers.empty())) {
     fprintf(stderr, "usage: %s <model_dir> --layers model.layers.A-B [--address host:port] [--cluster-key K] [--dtype bf16|f16] "

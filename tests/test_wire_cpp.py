@@ -227,3 +227,55 @@ def test_cpp_worker_serves_many_open_connections_like_a_cake_master():
             c.goodbye()
             c.close()
         assert w.close() == 0
+
+
+TOPOLOGY = """# two workers, the syntax of cake's topology.yml
+gpu1:
+  host: "10.0.0.2:10128"   # first box
+  description: 'B200 #1'
+  layers:
+    - "model.layers.8-15"
+    - model.layers.20
+gpu2:
+  host: 10.0.0.3:10128
+  layers: ["model.layers.16-17", 'model.layers.31']
+  vram_bytes: 1000
+"""
+
+
+def test_topology_file_gives_cpp_and_python_workers_the_same_layers(tmp_path):
+    import sys
+    from cake_b200.parallel import load_topology
+    build_host()
+    p = tmp_path / "topology.yml"
+    p.write_text(TOPOLOGY)
+    topo = load_topology(str(p))
+    assert topo["gpu2"]["layers"] == ["model.layers.16", "model.layers.17", "model.layers.31"]
+    for name in ("gpu1", "gpu2"):
+        r = subprocess.run([WORKER, "--topology", str(p), "--name", name], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.split() == topo[name]["layers"], r.stderr
+        r = subprocess.run([sys.executable, "-m", "cake_b200.worker", "--topology", str(p), "--name", name],
+                           capture_output=True, text=True, cwd=ROOT)
+        assert r.returncode == 0 and r.stdout.split() == topo[name]["layers"], r.stderr
+    r = subprocess.run([WORKER, "--topology", str(p), "--name", "gpu9"], capture_output=True, text=True)
+    assert r.returncode == 1 and "could not find topology node" in r.stderr
+    r = subprocess.run([sys.executable, "-m", "cake_b200.worker", "--topology", str(p), "--name", "gpu9"],
+                       capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode != 0 and "could not find topology node" in r.stderr
+
+
+def test_python_worker_cli_speaks_to_the_python_client():
+    import sys
+    p = subprocess.Popen([sys.executable, "-m", "cake_b200.worker", "--echo", "--address", "127.0.0.1:0"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT)
+    try:
+        line = p.stdout.readline().strip()
+        assert line.startswith("listening on "), p.stderr.read()
+        c = WireClient(line[len("listening on "):], "model.layers.0", timeout=10)
+        t = raw_f16([1, 1, 32])
+        assert c.forward_mut(t, 0, 0).data == t.data and c.info.device == "cpu"
+        c.goodbye()
+        c.close()
+    finally:
+        p.kill()
+        p.wait(5)
