@@ -4,7 +4,7 @@ built here).  tok/s as the reference defines it: (generated - 1) / time since th
 
     python bench_tools/config0_cpu.py [n_tokens=32] [prompt_len=16]
 
-The GPU counterpart of this configuration is tests/test_gpu_fullsize.py::test_qwen3_0_6b_f16_decode_matches_oracle.
+The GPU counterpart of this configuration is tests/test_gpu_fullsize.py::test_qwen3_0_6b_config0_f16_greedy_against_oracle.
 """
 import json
 import os
