@@ -418,12 +418,14 @@ extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
   delete c;
 }
 extern "C" int cake_b200_sync(cake_b200_ctx *c) {
+  if (!c) return fail(CAKE_B200_EINVAL, "null argument");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
   return CAKE_B200_OK;
 }
-extern "C" void *cake_b200_stream(cake_b200_ctx *c) { return (void *)c->stream; }
+extern "C" void *cake_b200_stream(cake_b200_ctx *c) { return c ? (void *)c->stream : nullptr; }
 extern "C" int cake_b200_launch_count(cake_b200_ctx *c, uint64_t *k) {
+  if (!c || !k) return fail(CAKE_B200_EINVAL, "null argument");
   *k = c->launches;
   return CAKE_B200_OK;
 }
@@ -496,7 +498,7 @@ extern "C" void cake_b200_block_free(cake_b200_block *b) {
   (void)cudaGetLastError();
   delete b;
 }
-extern "C" int cake_b200_block_layer(const cake_b200_block *b) { return b->layer; }
+extern "C" int cake_b200_block_layer(const cake_b200_block *b) { return b ? b->layer : -1; }
 
 // ------------------------------------------------------------------------------------------ cache
 extern "C" int cake_b200_cache_create(cake_b200_ctx *c, int batch, int max_seq, cake_b200_cache **out) {
@@ -521,6 +523,7 @@ static int cache_ensure(cake_b200_cache *k, int layer) {
   return CAKE_B200_OK;
 }
 extern "C" int cake_b200_cache_clear(cake_b200_cache *k) {
+  if (!k) return fail(CAKE_B200_EINVAL, "null argument");
   for (auto &l : k->len) l = 0;
   return CAKE_B200_OK;
 }
@@ -536,10 +539,11 @@ extern "C" void cake_b200_cache_free(cake_b200_cache *k) {
   delete k;
 }
 extern "C" int cake_b200_cache_len(const cake_b200_cache *k, int block_idx) {
-  if (block_idx < 0 || block_idx >= (int)k->len.size()) return -1;
+  if (!k || block_idx < 0 || block_idx >= (int)k->len.size()) return -1;
   return k->len[block_idx];
 }
 extern "C" int cake_b200_cache_read(cake_b200_cache *k, int block_idx, int which, void *out_host, size_t bytes) {
+  if (!k || !out_host) return fail(CAKE_B200_EINVAL, "null argument");
   cake_b200_ctx *c = k->ctx;
   CU(cudaSetDevice(c->device));
   if (block_idx < 0 || block_idx >= (int)k->len.size() || !k->k[block_idx]) return fail(CAKE_B200_EINVAL, "layer %d has no cache", block_idx);
@@ -554,6 +558,7 @@ extern "C" int cake_b200_cache_read(cake_b200_cache *k, int block_idx, int which
 }
 extern "C" int cake_b200_cache_fill_synthetic(cake_b200_cache *k, const int *block_idx, int n_blocks, int len,
                                               uint32_t seed) {
+  if (!k || (!block_idx && n_blocks > 0) || n_blocks < 0 || len < 0) return fail(CAKE_B200_EINVAL, "bad cache_fill_synthetic arguments");
   cake_b200_ctx *c = k->ctx;
   CU(cudaSetDevice(c->device));
   if (len > k->cap) return fail(CAKE_B200_EINVAL, "len %d > cache capacity %d", len, k->cap);
@@ -1072,6 +1077,7 @@ extern "C" int cake_b200_repeat_penalty_argmax(cake_b200_ctx *c, void *logits_de
 
 // ------------------------------------------------------------------------------------------ comm
 extern "C" int cake_b200_comm_unique_id(void *out128) {
+  if (!out128) return fail(CAKE_B200_EINVAL, "null argument");
   RC(nccl_load());
   ncclUniqueId id;
   NC(g_nccl.GetUniqueId(&id));

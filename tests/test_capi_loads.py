@@ -85,3 +85,36 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
                 src = open(os.path.join(dp, f)).read()
                 assert not bad.search(src), f"{f} reaches into the oracle"
+
+
+def test_null_handles_are_errors_not_crashes():
+    """`errors never abort`: every entry point called with null handles / zero sizes returns a
+    status (or a null/negative value) and leaves a message — checked in a child process so that a regression shows up as
+    a failed assertion, not a dead test runner."""
+    import subprocess
+    import sys
+    code = r'''
+import ctypes, sys
+sys.path.insert(0, %r)
+from cake_b200 import capi
+L = capi.lib()
+bad = []
+for name, restype, argtypes in capi.SYMBOLS:
+    args = [0.0 if t is ctypes.c_float else 0 if t in (ctypes.c_int, ctypes.c_uint32, ctypes.c_size_t, ctypes.c_uint64) else None
+            for t in argtypes]
+    rc = getattr(L, name)(*args)
+    if name in ("cake_b200_version", "cake_b200_last_error", "cake_b200_ctx_destroy", "cake_b200_block_free", "cake_b200_cache_free"):
+        continue
+    if name == "cake_b200_stream":
+        ok = rc in (None, 0)
+    elif name in ("cake_b200_block_layer", "cake_b200_cache_len"):
+        ok = rc < 0
+    else:
+        ok = rc != 0 and bool(L.cake_b200_last_error())
+    if not ok:
+        bad.append((name, rc))
+print("BAD", bad)
+''' % ROOT
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, f"crashed with {r.returncode}: {r.stderr[-500:]}"
+    assert "BAD []" in r.stdout, r.stdout
