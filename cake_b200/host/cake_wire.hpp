@@ -99,7 +99,14 @@ struct RawTensor {  // message.rs:39-48; data = elements in native (little-endia
   std::vector<uint8_t> data;
   uint8_t dtype = F16;
   std::vector<uint64_t> shape;
-  uint64_t numel() const { uint64_t n = 1; for (auto d : shape) n *= d; return n; }
+  uint64_t numel() const {  // saturating: a hostile shape must not wrap around to a plausible byte count
+    uint64_t n = 1;
+    for (auto d : shape) {
+      if (d != 0 && n > (UINT64_MAX >> 8) / d) return UINT64_MAX >> 8;
+      n *= d;
+    }
+    return n;
+  }
   void validate() const {
     if (data.size() != numel() * dtype_size(dtype)) throw ProtocolError("tensor shape and dtype do not match " + std::to_string(data.size()) + " bytes");
   }

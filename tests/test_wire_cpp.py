@@ -279,3 +279,31 @@ def test_python_worker_cli_speaks_to_the_python_client():
     finally:
         p.kill()
         p.wait(5)
+
+
+def test_hostile_frames_are_answered_or_dropped_never_fatal():
+    """Shapes whose element count wraps around u64, absurd element counts and truncated payloads must not take the
+    worker down: the op is reported as an error (or the connection dropped) and the next connection is served."""
+    with Proc("--echo", "--address", "127.0.0.1:0", "--connections", "3") as w:
+        c = WireClient(w.address, "model.layers.0", timeout=10)
+        wrap = RawTensor(b"", DTYPE_TAGS["f16"], [1 << 63, 2, 64])           # product == 0 (mod 2**64)
+        c.sock.sendall(Message.single_op("model.layers.0", wrap, 0, 0).frame())
+        assert Message.from_reader(c.sock)[1].kind == "WorkerError"
+        assert c.forward_mut(raw_f16([1, 8]), 0, 0).shape == [1, 8]           # connection still usable
+        c.close()
+        host, port = w.address.rsplit(":", 1)
+        s = socket.create_connection((host, int(port)), timeout=10)
+        Message.hello().to_writer(s)
+        assert Message.from_reader(s)[1].kind == "WorkerInfo"
+        # Batch that announces 2**32-1 ops but carries none: decoding fails, the connection is dropped
+        payload = Message.from_batch(raw_f16([1, 8]), []).to_bytes()[:-4] + b"\xff\xff\xff\xff"
+        s.sendall(bytes([0x01, 0x04, 0xF4, 0xC7]) + len(payload).to_bytes(4, "big") + payload)
+        try:
+            assert s.recv(16) == b""
+        except ConnectionResetError:
+            pass
+        s.close()
+        c = WireClient(w.address, "model.layers.0", timeout=10)
+        assert c.forward_mut(raw_f16([1, 8]), 0, 0).shape == [1, 8]
+        c.close()
+        assert w.close() == 0
