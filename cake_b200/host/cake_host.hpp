@@ -172,11 +172,19 @@ struct Config {
     for (auto &a : archs)
       if (k.arch == a.name) ar = &a;
     auto &c = k.c;
-    c.hidden = (int)j.number("hidden_size", 0);
-    c.inter = (int)j.number("intermediate_size", 0);
-    c.vocab = (int)j.number("vocab_size", 0);
-    c.n_layers = (int)j.number("num_hidden_layers", 0);
-    c.n_heads = (int)j.number("num_attention_heads", 0);
+    // the fields every *Config struct of the reference declares without a serde default: absent -> parse error
+    auto required = [&](const char *name) -> int {
+      const Json *v = j.get(name);
+      if (!v || v->kind != Json::Num) throw Error("can't parse " + path + ": missing field `" + name + "`");
+      if (!(v->num >= 1.0 && v->num <= 2147483647.0)) throw Error("can't parse " + path + ": field `" + name + "` is out of range");
+      return (int)v->num;
+    };
+    c.hidden = required("hidden_size");
+    c.inter = required("intermediate_size");
+    c.vocab = required("vocab_size");
+    c.n_layers = required("num_hidden_layers");
+    c.n_heads = required("num_attention_heads");
+    if (!j.get("rms_norm_eps") || j.get("rms_norm_eps")->kind != Json::Num) throw Error("can't parse " + path + ": missing field `rms_norm_eps`");
     c.n_kv_heads = (int)j.number("num_key_value_heads", c.n_heads);
     const int hd_default = c.n_heads ? c.hidden / c.n_heads : 0;  // attention.rs:85
     c.head_dim = ar->head_dim ? (int)j.number("head_dim", hd_default) : hd_default;

@@ -91,3 +91,27 @@ def test_active_sliding_window_is_refused_until_the_trim_exists(tmp_path):
     assert r.returncode == 1 and "sliding_window=4096" in r.stderr
     r = subprocess.run([RUN, str(tmp_path), "--show-config", "--max-seq", "4096"], capture_output=True, text=True)
     assert r.returncode == 0 and "max_seq=4096" in r.stdout
+
+
+@pytest.mark.parametrize("drop", ["hidden_size", "intermediate_size", "vocab_size", "num_hidden_layers", "num_attention_heads",
+                                  "rms_norm_eps"])
+def test_fields_without_a_serde_default_are_required(tmp_path, drop):
+    """Every *Config struct of the reference declares these without `#[serde(default)]`: a config.json without one of
+    them does not load (serde: "missing field")."""
+    d = {**BASE, "architectures": ["LlamaForCausalLM"]}
+    d.pop(drop)
+    with pytest.raises(KeyError, match=drop):
+        Config.from_hf(d)
+    build_host()
+    with open(tmp_path / "config.json", "w") as f:
+        json.dump(d, f)
+    r = subprocess.run([RUN, str(tmp_path), "--show-config"], capture_output=True, text=True)
+    assert r.returncode == 1 and f"missing field `{drop}`" in r.stderr
+
+
+@pytest.mark.parametrize("text", ["{", '{"hidden_size": }', "[1,2", "", '{"hidden_size": 1e999}'])
+def test_malformed_config_is_an_error_not_a_crash(tmp_path, text):
+    build_host()
+    (tmp_path / "config.json").write_text(text)
+    r = subprocess.run([RUN, str(tmp_path), "--show-config"], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("error:")
