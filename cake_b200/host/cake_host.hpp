@@ -252,19 +252,37 @@ class VarBuilder {
     close(fd);
     if (p == MAP_FAILED) throw Error("mmap failed for " + path);
     maps_.push_back({p, (size_t)st.st_size});
+    const size_t size = (size_t)st.st_size;
+    if (size < 8) throw Error(path + ": shorter than a safetensors header");
     uint64_t hl;
     memcpy(&hl, p, 8);
+    if (hl > 100ull * 1024 * 1024 || 8 + hl > size) throw Error(path + ": header length " + std::to_string(hl) + " does not fit the file");
     const char *hdr = (const char *)p + 8;
     Json j = JsonParser(hdr, (size_t)hl).value();
+    if (j.kind != Json::Obj) throw Error(path + ": header is not a JSON object");
     const char *base = hdr + hl;
+    const size_t data_len = size - 8 - (size_t)hl;
     for (auto &kv : j.obj) {
       if (kv.first == "__metadata__") continue;
+      const Json *dt = kv.second.get("dtype"), *sh = kv.second.get("shape"), *off = kv.second.get("data_offsets");
+      if (!dt || dt->kind != Json::Str || !sh || sh->kind != Json::Arr || !off || off->kind != Json::Arr || off->arr.size() != 2 ||
+          off->arr[0].kind != Json::Num || off->arr[1].kind != Json::Num)
+        throw Error(path + ": bad entry for tensor " + kv.first);
       TensorView v;
-      v.dtype = kv.second.get("dtype")->str;
-      for (auto &d : kv.second.get("shape")->arr) v.shape.push_back((int64_t)d.num);
-      const auto &off = kv.second.get("data_offsets")->arr;
-      v.data = base + (size_t)off[0].num;
-      v.bytes = (size_t)(off[1].num - off[0].num);
+      v.dtype = dt->str;
+      double numel = 1;
+      for (auto &d : sh->arr) {
+        if (d.kind != Json::Num || d.num < 0) throw Error(path + ": bad shape for tensor " + kv.first);
+        v.shape.push_back((int64_t)d.num);
+        numel *= d.num;
+      }
+      const double b = off->arr[0].num, e = off->arr[1].num;
+      const size_t item = (v.dtype == "F64" || v.dtype == "I64") ? 8 : (v.dtype == "F32" || v.dtype == "I32") ? 4
+                          : (v.dtype == "BF16" || v.dtype == "F16" || v.dtype == "I16") ? 2 : 1;
+      if (!(b >= 0 && b <= e && e <= (double)data_len) || e - b != numel * (double)item)
+        throw Error(path + ": tensor " + kv.first + " has offsets that do not match its shape");
+      v.data = base + (size_t)b;
+      v.bytes = (size_t)(e - b);
       t_[kv.first] = v;
     }
   }
@@ -316,13 +334,20 @@ class VarBuilder {
     auto it = t_.find(name);
     return it == t_.end() ? nullptr : &it->second;
   }
-  const void *get(const std::string &name, const std::string &want_dtype) const {
+  // `shape`: what the loader is about to read through the pointer (candle's vb.get(shape, name) check)
+  const void *get(const std::string &name, const std::string &want_dtype, const std::vector<int64_t> &shape) const {
     const TensorView *v = find(name);
     if (!v) throw Error("cannot find tensor " + name);  // candle VarBuilder error text
     if (v->dtype != want_dtype) throw Error("tensor " + name + " is " + v->dtype + ", expected " + want_dtype);
+    if (v->shape != shape) {
+      auto str = [](const std::vector<int64_t> &s) { std::string o = "["; for (size_t i = 0; i < s.size(); i++) o += (i ? ", " : "") + std::to_string(s[i]); return o + "]"; };
+      throw Error("shape mismatch for " + name + ", expected: " + str(shape) + ", got: " + str(v->shape));
+    }
     return v->data;
   }
-  const void *get_opt(const std::string &name, const std::string &want_dtype) const { return find(name) ? get(name, want_dtype) : nullptr; }
+  const void *get_opt(const std::string &name, const std::string &want_dtype, const std::vector<int64_t> &shape) const {
+    return find(name) ? get(name, want_dtype, shape) : nullptr;
+  }
 };
 
 // ---------------------------------------------------------------------------------------------- Cache / Context
@@ -383,18 +408,21 @@ class Transformer : public Forwarder {  // transformer.rs:14-150, backed by the 
   static std::unique_ptr<Transformer> load(const std::string &name, Context &ctx) {  // transformer.rs:79-101
     const VarBuilder &vb = *ctx.var_builder;
     const std::string &dt = ctx.dtype_name;
-    auto g = [&](const char *s) { return vb.get(name + "." + s, dt); };
-    auto o = [&](const char *s) { return vb.get_opt(name + "." + s, dt); };
+    const auto &c = ctx.config.c;
+    const int64_t H = c.hidden, I = c.inter, sq = (int64_t)c.n_heads * c.head_dim, skv = (int64_t)c.n_kv_heads * c.head_dim, hd = c.head_dim;
+    typedef std::vector<int64_t> Sh;
+    auto g = [&](const char *s, const Sh &shape) { return vb.get(name + "." + s, dt, shape); };
     int layer = std::stoi(name.substr(name.rfind('.') + 1));
     auto t = std::unique_ptr<Transformer>(new Transformer());
     t->name_ = name;
-    check(cake_b200_block_load(ctx.h, layer, g("self_attn.q_proj.weight"), g("self_attn.k_proj.weight"), g("self_attn.v_proj.weight"),
-                               g("self_attn.o_proj.weight"), g("mlp.gate_proj.weight"), g("mlp.up_proj.weight"), g("mlp.down_proj.weight"),
-                               g("input_layernorm.weight"), g("post_attention_layernorm.weight"),
-                               ctx.config.c.qkv_bias ? g("self_attn.q_proj.bias") : nullptr, ctx.config.c.qkv_bias ? g("self_attn.k_proj.bias") : nullptr,
-                               ctx.config.c.qkv_bias ? g("self_attn.v_proj.bias") : nullptr,
-                               ctx.config.c.qk_norm ? g("self_attn.q_norm.weight") : o("self_attn.q_norm.weight"),
-                               ctx.config.c.qk_norm ? g("self_attn.k_norm.weight") : o("self_attn.k_norm.weight"), &t->h_),
+    check(cake_b200_block_load(ctx.h, layer, g("self_attn.q_proj.weight", Sh{sq, H}), g("self_attn.k_proj.weight", Sh{skv, H}),
+                               g("self_attn.v_proj.weight", Sh{skv, H}), g("self_attn.o_proj.weight", Sh{H, sq}),
+                               g("mlp.gate_proj.weight", Sh{I, H}), g("mlp.up_proj.weight", Sh{I, H}), g("mlp.down_proj.weight", Sh{H, I}),
+                               g("input_layernorm.weight", Sh{H}), g("post_attention_layernorm.weight", Sh{H}),
+                               c.qkv_bias ? g("self_attn.q_proj.bias", Sh{sq}) : nullptr, c.qkv_bias ? g("self_attn.k_proj.bias", Sh{skv}) : nullptr,
+                               c.qkv_bias ? g("self_attn.v_proj.bias", Sh{skv}) : nullptr,
+                               c.qk_norm ? g("self_attn.q_norm.weight", Sh{hd}) : nullptr,   // attention.rs:120-129: only when use_qk_norm
+                               c.qk_norm ? g("self_attn.k_norm.weight", Sh{hd}) : nullptr, &t->h_),
           name);
     return t;
   }
@@ -430,8 +458,9 @@ class TextModelBase {  // text_model.rs:133-530 for token-id prompts
     auto m = std::make_unique<TextModelBase>(ctx);
     const VarBuilder &vb = *ctx.var_builder;
     const std::string p = ctx.config.model_prefix, &dt = ctx.dtype_name;
-    check(cake_b200_head_load(ctx.h, vb.get(p + ".embed_tokens.weight", dt), vb.get(p + ".norm.weight", dt),
-                              ctx.config.c.tie_embeddings ? nullptr : vb.get("lm_head.weight", dt)),
+    const int64_t V = ctx.config.c.vocab, H = ctx.config.c.hidden;
+    check(cake_b200_head_load(ctx.h, vb.get(p + ".embed_tokens.weight", dt, {V, H}), vb.get(p + ".norm.weight", dt, {H}),
+                              ctx.config.c.tie_embeddings ? nullptr : vb.get("lm_head.weight", dt, {V, H})),
           "head_load");
     for (int i = 0; i < ctx.config.c.n_layers; i++) m->blocks.push_back(Transformer::load(ctx.config.layer_name(i), ctx));
     return m;

@@ -28,7 +28,7 @@ import torch
 from . import capi
 from .capi import byref, c_uint32, c_void_p, check, int_array, lib, ptr, ptr_array
 from .config import CConfig, Config
-from .synth import TORCH_DTYPES
+from .synth import TORCH_DTYPES, layer_tensor_shapes
 
 
 class Cache:
@@ -181,12 +181,17 @@ class B200Transformer(Forwarder):
     def load(cls, name: str, ctx: Context) -> "B200Transformer":
         vb, cfg = ctx.var_builder, ctx.config
 
+        shapes = layer_tensor_shapes(cfg)
+
         def get(short: str, required: bool = True):
             t = vb.get(f"{name}.{short}")
             if t is None:
                 if required:
                     raise KeyError(f"tensor {name}.{short} not found")  # candle VarBuilder error
                 return None
+            want = shapes.get(short)
+            if want is not None and tuple(t.shape) != tuple(want):  # candle's vb.get(shape, name) check
+                raise ValueError(f"shape mismatch for {name}.{short}, expected: {list(want)}, got: {list(t.shape)}")
             if t.dtype != ctx.torch_dtype:
                 t = t.to(ctx.torch_dtype)
             return t.contiguous()
@@ -270,9 +275,15 @@ class TextModelBase:
         """text_model.rs:150-264: embed, lm_head (tied -> embed), ln_f, then one block per layer —
         local ones via Forwarder::load, layers the topology assigns elsewhere via `make_remote`."""
         cfg, vb, p = ctx.config, ctx.var_builder, ctx.config.model_prefix
-        emb = vb[f"{p}.embed_tokens.weight"].to(ctx.torch_dtype).contiguous()
-        lnf = vb[f"{p}.norm.weight"].to(ctx.torch_dtype).contiguous()
-        head = None if cfg.tie_word_embeddings else vb["lm_head.weight"].to(ctx.torch_dtype).contiguous()
+        def get(tname: str, shape):
+            t = vb[tname]
+            if tuple(t.shape) != tuple(shape):
+                raise ValueError(f"shape mismatch for {tname}, expected: {list(shape)}, got: {list(t.shape)}")
+            return t.to(ctx.torch_dtype).contiguous()
+
+        emb = get(f"{p}.embed_tokens.weight", (cfg.vocab_size, cfg.hidden_size))
+        lnf = get(f"{p}.norm.weight", (cfg.hidden_size,))
+        head = None if cfg.tie_word_embeddings else get("lm_head.weight", (cfg.vocab_size, cfg.hidden_size))
         check(lib().cake_b200_head_load(ctx.h, ptr(emb), ptr(lnf), ptr(head)))
         blocks: List[Forwarder] = []
         for i in range(cfg.num_hidden_layers):

@@ -65,3 +65,29 @@ def test_cake_run_tokens_equal_python_master(tmp_path, sharded):
     ref = Master(TextModelBase.load(ctx)).generate_text(prompt, 12)["tokens"]
     ctx.close()
     assert toks == ref
+
+
+@pytest.mark.parametrize("damage", ["truncate", "offsets", "header_len", "not_json"])
+def test_damaged_safetensors_is_an_error_not_a_crash(tmp_path, damage):
+    """The mmapped reader validates header length, JSON, and every tensor's offsets against its shape and the file size."""
+    import struct
+    build()
+    cfg = medium_config(num_hidden_layers=1)
+    _write_model(tmp_path, cfg, checkpoint(cfg, "bf16", seed=1))
+    p = tmp_path / "model.safetensors"
+    raw = p.read_bytes()
+    (n,) = struct.unpack("<Q", raw[:8])
+    if damage == "truncate":
+        p.write_bytes(raw[: len(raw) // 2])
+    elif damage == "offsets":
+        hdr = json.loads(raw[8:8 + n])
+        k = next(k for k in hdr if k != "__metadata__")
+        hdr[k]["data_offsets"][1] += 2
+        blob = json.dumps(hdr).encode()
+        p.write_bytes(struct.pack("<Q", len(blob)) + blob + raw[8 + n:])
+    elif damage == "header_len":
+        p.write_bytes(struct.pack("<Q", 1 << 40) + raw[8:])
+    else:
+        p.write_bytes(struct.pack("<Q", 16) + b"this is not json" + raw[8 + n:])
+    r = subprocess.run([RUN, str(tmp_path), "--prompt-ids", "1,2", "-n", "1"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1 and r.stderr.startswith("error:") and "ctx_create" not in r.stderr, r.stderr

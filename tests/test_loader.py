@@ -195,3 +195,28 @@ def test_gpu_master_loads_from_disk(tmp_path):
     got, vb = open_model(str(tmp_path))
     from_disk, from_memory = run(got, vb), run(cfg, sd)
     assert len(from_disk) == 12 and from_disk == from_memory
+
+
+def test_wrong_shapes_are_refused_before_anything_is_copied():
+    """candle's `vb.get(shape, name)` refuses a tensor whose shape is not the one the layer declares; the loader must do
+    the same before it hands a pointer to the library (which would read rows x cols elements through it)."""
+    from cake_b200.model import B200Transformer, TextModelBase
+
+    cfg = medium_config(num_hidden_layers=1)
+    sd = checkpoint(cfg, "bf16", seed=3)
+
+    class Ctx:  # only what load() touches before the first library call
+        config, var_builder, torch_dtype, topology = cfg, sd, torch.bfloat16, {}
+
+    name = cfg.layer_name(0)
+    good = sd[f"{name}.mlp.down_proj.weight"]
+    sd[f"{name}.mlp.down_proj.weight"] = good[:, :-8].contiguous()
+    with pytest.raises(ValueError, match=r"shape mismatch for model.layers.0.mlp.down_proj.weight, expected: \[512, 1024\], got: \[512, 1016\]"):
+        B200Transformer.load(name, Ctx)
+    sd[f"{name}.mlp.down_proj.weight"] = good
+    del sd[f"{name}.self_attn.o_proj.weight"]
+    with pytest.raises(KeyError, match="self_attn.o_proj.weight not found"):
+        B200Transformer.load(name, Ctx)
+    sd["lm_head.weight"] = sd["lm_head.weight"][:-1].contiguous()
+    with pytest.raises(ValueError, match="shape mismatch for lm_head.weight"):
+        TextModelBase.load(Ctx)
