@@ -9,9 +9,12 @@
  * returns; cake-mobile's cake_mobile_c.h explicit free functions):
  *   - every function returns CAKE_B200_OK (0) or a negative CAKE_B200_E*; the message of the last
  *     failure on the calling thread is available from cake_b200_last_error();
- *   - all handles are thread-compatible; a cake_b200_block is immutable after load and may be
- *     shared by several caches/sessions (worker.rs:60-75 shares blocks across connections, each
- *     with its own Cache); a cake_b200_cache belongs to one session;
+ *   - all handles are thread-compatible: any thread may call (the device is bound inside every call, as
+ *     worker.rs:412-418 has to), but calls on ONE ctx share its stream and scratch buffers, so concurrent callers
+ *     must serialise them (cake_worker / wire.py hold one lock per ctx); a cake_b200_block is immutable after load and
+ *     may be shared by several caches/sessions (worker.rs:60-75 shares blocks across connections, each with its own
+ *     Cache); a cake_b200_cache belongs to one session; null handles are reported as CAKE_B200_EINVAL, never
+ *     dereferenced;
  *   - "_dev" pointers are device memory on the ctx's GPU, everything is enqueued on the ctx's
  *     stream and is asynchronous unless the name ends in _host or the doc says it synchronises.
  *
