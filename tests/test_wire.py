@@ -417,3 +417,54 @@ def test_many_connections_at_once_like_a_cake_master():
     finally:
         w.stop()
     assert w.connections == 16 and w.served == 4
+
+
+@pytest.mark.gpu
+def test_gpu_master_with_tcp_worker_generates_the_same_tokens(tmp_path):
+    """The reference's deployment shape over its own protocol: a master keeps layers 0-1, a worker endpoint serves
+    layers 2-3 (weights from the shards of a checkpoint on disk), one connection per remote layer
+    (text_model.rs:211-227).  Greedy tokens must equal the all-local run."""
+    from cake_b200.loader import open_model, save_checkpoint
+    from cake_b200.model import B200Transformer, Context, Master, TextModelBase
+    from cake_b200.parallel import parse_topology
+    from cake_b200.wire import B200Backend, WireRemote
+    from tests.util import checkpoint, medium_config
+    cfg = medium_config(num_hidden_layers=4)
+    sd = checkpoint(cfg, "bf16", seed=23, peaked=True)
+    save_checkpoint(str(tmp_path), cfg, sd, shard_bytes=2_000_000)
+    prompt = np.random.default_rng(9).integers(0, cfg.vocab_size - 1, 7).tolist()
+
+    ctx = Context(cfg, sd, "bf16", max_seq=64)
+    try:
+        want = Master(TextModelBase.load(ctx)).generate_text(prompt, 10)["tokens"]
+    finally:
+        ctx.close()
+
+    topo = parse_topology({"w1": {"host": "set below", "layers": [f"{cfg.model_prefix}.layers.2-3"]}})
+    wcfg, wvb = open_model(str(tmp_path), topo, worker="w1")          # only the shards holding layers 2-3
+    wctx = Context(wcfg, wvb, "bf16", max_seq=64)
+    w = mctx = None
+    clients = []
+    try:
+        w = WireWorker(B200Backend(wctx, {n: B200Transformer.load(n, wctx) for n in topo["w1"]["layers"]})).start()
+        topo["w1"]["host"] = w.address
+        mcfg, mvb = open_model(str(tmp_path), topo)                    # master: shards with only worker layers are skipped
+        mctx = Context(mcfg, mvb, "bf16", max_seq=64, topology=topo)
+
+        def make_remote(owner, name, c):
+            clients.append(WireClient(topo[owner]["host"], name, timeout=60))
+            return WireRemote(clients[-1], name, c)
+
+        model = TextModelBase.load(mctx, make_remote=make_remote)
+        assert [b.ident() for b in model.blocks] == ["local", "local", w.address, w.address]
+        got = Master(model).generate_text(prompt, 10)["tokens"]
+        model.goodbye()
+        assert got == want and len(clients) == 2 and w.connections == 2
+    finally:
+        for c in clients:
+            c.close()
+        if w is not None:
+            w.stop()
+        if mctx is not None:
+            mctx.close()
+        wctx.close()
