@@ -310,6 +310,7 @@ class VarBuilder {
     }
   }
   size_t n_files() const { return maps_.size(); }
+  const std::map<std::string, TensorView> &tensors() const { return t_; }
   // cake/mod.rs:335-357: the text before the first ".layers.0." key of the index wins over the configured prefix
   static std::string detect_model_prefix(const std::string &dir, const std::string &configured) {
     const std::string idx = dir + "/model.safetensors.index.json";

@@ -5,6 +5,7 @@
 //               [--dtype bf16|f16] [--max-seq S] [--device 0] [--connections N]
 //   cake_worker <model_dir> --topology topology.yml --name worker1 ...   (layers from the master's topology file)
 //   cake_worker --topology topology.yml --name worker1                    (dry run: print the expanded layer list)
+//   cake_worker <model_dir> [--layers ...] --list-tensors                 (dry run: tensors the node's VarBuilder maps)
 //   cake_worker --echo [--reflect] [--address 127.0.0.1:0] [--cluster-key K] [--connections N]    (no GPU: protocol only)
 // --layers takes the topology file's syntax (topology.rs:13,143-168): names or inclusive ranges, comma separated.
 // Prints "listening on <host>:<port>" once the socket is bound.
@@ -173,7 +174,7 @@ struct B200Backend : cw::Backend {
 
 int main(int argc, char **argv) {
   std::string dir, layers, address = "127.0.0.1:10128", key, topology, name;
-  bool echo = false, reflect = false, has_key = false;
+  bool echo = false, reflect = false, has_key = false, list_tensors = false;
   int dtype = CAKE_B200_BF16, max_seq = 0, device = 0, connections = -1;
   for (int i = 1; i < argc; i++) {
     std::string a = argv[i];
@@ -189,6 +190,7 @@ int main(int argc, char **argv) {
     else if (a == "--name") name = next();
     else if (a == "--echo") echo = true;
     else if (a == "--reflect") reflect = true;
+    else if (a == "--list-tensors") list_tensors = true;
     else if (a == "--expand") {  // print the expansion of a --layers expression and exit (no GPU)
       try {
         for (auto &n : expand_layers(next())) printf("%s\n", n.c_str());
@@ -212,6 +214,25 @@ int main(int argc, char **argv) {
       fprintf(stderr, "error: %s\n", e.what());
       return 1;
     }
+  }
+  if (list_tensors && !dir.empty()) {  // dry run (no GPU): what the mmapped VarBuilder of this node holds
+    try {
+      const std::vector<std::string> names = layers.empty() ? std::vector<std::string>{} : expand_layers(layers);
+      VarBuilder vb(dir, names);
+      printf("files %zu prefix %s\n", vb.n_files(), VarBuilder::detect_model_prefix(dir, "model").c_str());
+      for (auto &kv : vb.tensors()) {
+        uint64_t hsh = 1469598103934665603ull;  // FNV-1a over the tensor bytes
+        const unsigned char *p = (const unsigned char *)kv.second.data;
+        for (size_t i = 0; i < kv.second.bytes; i++) { hsh ^= p[i]; hsh *= 1099511628211ull; }
+        std::string shape;
+        for (auto d : kv.second.shape) shape += (shape.empty() ? "" : "x") + std::to_string(d);
+        printf("%s %s [%s] %zu %016llx\n", kv.first.c_str(), kv.second.dtype.c_str(), shape.c_str(), kv.second.bytes, (unsigned long long)hsh);
+      }
+    } catch (const std::exception &e) {
+      fprintf(stderr, "error: %s\n", e.what());
+      return 1;
+    }
+    return 0;
   }
   if (!echo && (dir.empty() || layers.empty())) {
     fprintf(stderr, "usage: %s <model_dir> --layers model.layers.A-B [--address host:port] [--cluster-key K] [--dtype bf16|f16] "

@@ -220,3 +220,40 @@ def test_wrong_shapes_are_refused_before_anything_is_copied():
     sd["lm_head.weight"] = sd["lm_head.weight"][:-1].contiguous()
     with pytest.raises(ValueError, match="shape mismatch for lm_head.weight"):
         TextModelBase.load(Ctx)
+
+
+def _fnv1a(b: bytes) -> int:
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return h
+
+
+@pytest.mark.parametrize("layers", [None, "model.layers.2-3"])
+def test_cpp_varbuilder_maps_the_same_tensors_as_the_python_loader(tmp_path, layers):
+    """The compiled mmapped reader (cake_host.hpp VarBuilder) and cake_b200/loader.py must see the same shards, names,
+    dtypes, shapes and bytes — for the whole checkpoint and for a worker's layer subset (utils/mod.rs:334-384)."""
+    import subprocess
+    from cake_b200.build import build_host
+    build_host()
+    worker = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "cake_b200", "host", "cake_worker")
+    cfg = medium_config(num_hidden_layers=4, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+                        num_key_value_heads=2, head_dim=32)
+    sd = checkpoint(cfg, "bf16", seed=12)
+    _sharded_by_layer(tmp_path, cfg, sd)
+    args = [worker, str(tmp_path), "--list-tensors"] + (["--layers", layers] if layers else [])
+    r = subprocess.run(args, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().split("\n")
+    index = str(tmp_path / INDEX_NAME)
+    vb = VarBuilder.for_specific_layers(index, [cfg.layer_name(2), cfg.layer_name(3)]) if layers else VarBuilder.from_index(index)
+    assert lines[0] == f"files {len(vb.shard_paths())} prefix model"
+    got = {}
+    for ln in lines[1:]:
+        name, dtype, shape, nbytes, h = ln.split()
+        got[name] = (dtype, shape, int(nbytes), int(h, 16))
+    assert set(got) == set(vb)
+    for name in vb:
+        t = vb[name]
+        raw = t.contiguous().view(torch.uint8).numpy().tobytes()
+        assert got[name] == ("BF16", "[" + "x".join(str(d) for d in t.shape) + "]", len(raw), _fnv1a(raw)), name
