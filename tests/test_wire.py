@@ -210,8 +210,10 @@ def test_handshake_ops_goodbye_and_continue(key):
         t = raw_f16([1, 64])
         batch = [("model.layers.0", 0, 0), ("model.layers.1", 0, 1), ("model.layers.2", 0, 2)]
         assert c.forward_batch(t, batch).data == t.data                # test_batch_echo
-        for i in range(10):                                            # test_multiple_sequential_ops
-            assert c.forward_mut(t, i, 0).data == t.data
+        for i in range(10):                                            # test_multiple_sequential_ops: [1, 32+i]
+            ti = raw_f16([1, 32 + i])
+            yi = c.forward_mut(ti, i, 0)
+            assert yi.data == ti.data and yi.shape == [1, 32 + i]
         cleared = be.cleared
         c.goodbye()                                                    # test_goodbye_and_continue
         assert be.cleared == cleared + 1

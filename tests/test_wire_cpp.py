@@ -75,8 +75,10 @@ def test_python_master_against_cpp_worker(key):
         assert y.dtype == DTYPE_TAGS["f16"] and y.shape == [1, 128] and y.data == t.data
         t = raw_f16([1, 64])
         assert c.forward_batch(t, [("model.layers.0", 0, 0), ("model.layers.1", 0, 1), ("model.layers.2", 0, 2)]).data == t.data
-        for i in range(10):
-            assert c.forward_mut(t, i, 0).data == t.data
+        for i in range(10):   # tests/protocol.rs:262-290: a different shape every time
+            ti = raw_f16([1, 32 + i])
+            yi = c.forward_mut(ti, i, 0)
+            assert yi.data == ti.data and yi.shape == [1, 32 + i]
         c.goodbye()
         assert c.forward_mut(t, 0, 0).data == t.data
         big = raw_f16([1, 5120])
