@@ -27,7 +27,8 @@ fi
 if [[ "$what" == probes || "$what" == all ]]; then
   step "phase-boundary probes"
   $NVCC $ARCH -o /tmp/barrier_probe bench_tools/barrier_probe.cu && timeout 120 /tmp/barrier_probe 2000 > "$out/barrier_probe.txt" 2>&1
-  $NVCC $ARCH -o /tmp/l2_prefetch_probe bench_tools/l2_prefetch_probe.cu && { timeout 120 /tmp/l2_prefetch_probe 32 8; timeout 120 /tmp/l2_prefetch_probe 24 4; } > "$out/l2_prefetch_probe.txt" 2>&1
+  $NVCC $ARCH -o /tmp/l2_prefetch_probe bench_tools/l2_prefetch_probe.cu && { timeout 120 /tmp/l2_prefetch_probe 32 8; timeout 120 /tmp/l2_prefetch_probe 24 4;
+    for idle in 0 100 1000 3000; do echo "--- HBM idle ${idle} us"; timeout 120 /tmp/l2_prefetch_probe 32 $idle | grep "mode 0"; done; } > "$out/l2_prefetch_probe.txt" 2>&1
   cat "$out/barrier_probe.txt" "$out/l2_prefetch_probe.txt" | tee -a "$out/round.log"
 fi
 if [[ "$what" == ncu || "$what" == all ]]; then

@@ -4,6 +4,9 @@
 // issued by the producer lane itself and showed no gain; this isolates the mechanism.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I cake_b200/csrc -o bench_tools/l2_prefetch_probe bench_tools/l2_prefetch_probe.cu
 //   ./bench_tools/l2_prefetch_probe [region_MB=32] [idle_us=8]
+// Second use: HBM wake-up.  Run mode 0 with idle_us = 0 / 100 / 1000 / 3000: if the time to the first stage (or the whole
+// phase B) grows with the idle time, an idle HBM drops into a state with a visible exit latency — the suspected part of
+// the 45-70 us per shard boundary in the multi-GPU ring, where a shard's HBM is idle for milliseconds between its turns.
 // One CTA per SM.  Each round uses a fresh 1/Nth of a large buffer (no reuse across rounds), then:
 //   phase A ("attention"): every CTA spins for idle_us — HBM idle; in mode 1/2 a helper lane prefetches this CTA's slice
 //                          of region B into L2 during the spin (mode 1: 32 KB requests, mode 2: 4 KB requests)
@@ -39,6 +42,7 @@ struct Args {
   size_t slice;        // bytes of region B per CTA (multiple of STAGE)
   int mode, idle_ns;
   unsigned long long *t_b;  // per CTA: duration of phase B in ns
+  unsigned long long *t_first;  // per CTA: phase-B start -> first stage landed, ns
   float *sink;
 };
 
@@ -82,6 +86,7 @@ __global__ void __launch_bounds__((CW + 2) * 32, 1) k_probe(const Args a, const 
     int s = 0; uint32_t ph = 0;
     for (int i = 0; i < nst; i++) {
       mbar_wait(&full[s], ph);
+      if (i == 0 && threadIdx.x == 0) a.t_first[blockIdx.x] = gtime() - tb;
       const uint4 *st = reinterpret_cast<const uint4 *>(smem + (size_t)s * STAGE);
       for (int v = warp * 32 + lane; v < STAGE / 16; v += CW * 32) {
         const uint4 q = st[v];
@@ -108,31 +113,34 @@ int main(int argc, char **argv) {
   unsigned char *buf;
   CK(cudaMalloc(&buf, total));
   CK(cudaMemset(buf, 1, total));
-  unsigned long long *t_b;
+  unsigned long long *t_b, *t_first;
   CK(cudaMalloc(&t_b, grid * 8));
+  CK(cudaMalloc(&t_first, grid * 8));
   const size_t smem = (size_t)NSTAGE * STAGE + 256;
   CK(cudaFuncSetAttribute(k_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   printf("%s: region B = %.1f MB (%zu KB per CTA), idle %d us, %d rounds over a %.1f GB buffer\n", p.name, region / 1e6,
          slice / 1024, idle_us, rounds, total / 1e9);
-  std::vector<unsigned long long> h(grid);
+  std::vector<unsigned long long> h(grid), hf(grid);
   unsigned char *flush;  // > L2: written before every mode so that no slice of `buf` starts out L2-resident
   CK(cudaMalloc(&flush, (size_t)256 << 20));
   for (int mode = 0; mode < 3; mode++) {
     CK(cudaMemset(flush, mode, (size_t)256 << 20));
-    double sum_max = 0, sum_avg = 0;
+    double sum_max = 0, sum_avg = 0, sum_first = 0;
     for (int r = 0; r < rounds; r++) {
-      Args a{buf, slice, mode, idle_us * 1000, t_b, nullptr};
+      Args a{buf, slice, mode, idle_us * 1000, t_b, t_first, nullptr};
       k_probe<<<grid, (CW + 2) * 32, smem>>>(a, (size_t)r * region);
       CK(cudaDeviceSynchronize());
       CK(cudaMemcpy(h.data(), t_b, grid * 8, cudaMemcpyDeviceToHost));
-      unsigned long long mx = 0, sm = 0;
+      CK(cudaMemcpy(hf.data(), t_first, grid * 8, cudaMemcpyDeviceToHost));
+      unsigned long long mx = 0, sm = 0, sf = 0;
       for (auto v : h) { mx = v > mx ? v : mx; sm += v; }
-      if (r >= 4) { sum_max += (double)mx; sum_avg += (double)sm / grid; }
+      for (auto v : hf) sf += v;
+      if (r >= 4) { sum_max += (double)mx; sum_avg += (double)sm / grid; sum_first += (double)sf / grid; }
     }
     const double n = rounds - 4;
-    printf("mode %d (%s): phase B  max-CTA %.2f us  avg-CTA %.2f us  -> %.0f GB/s on the slowest CTA's clock\n", mode,
+    printf("mode %d (%s): phase B  first stage after %.2f us  max-CTA %.2f us  avg-CTA %.2f us  -> %.0f GB/s on the slowest CTA's clock\n", mode,
            mode == 0 ? "no prefetch" : mode == 1 ? "L2 prefetch, 32 KB requests" : "L2 prefetch, 4 KB requests",
-           sum_max / n / 1e3, sum_avg / n / 1e3, region / (sum_max / n));
+           sum_first / n / 1e3, sum_max / n / 1e3, sum_avg / n / 1e3, region / (sum_max / n));
   }
   return 0;
 }
