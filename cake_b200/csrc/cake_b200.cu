@@ -451,6 +451,7 @@ static int upload(void **dst, const void *src, size_t bytes) {
   return CAKE_B200_OK;
 }
 
+extern "C" void cake_b200_block_free(cake_b200_block *b);
 extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void *q, const void *k, const void *v,
                                     const void *o, const void *gate, const void *up, const void *down, const void *ln1,
                                     const void *ln2, const void *q_bias, const void *k_bias, const void *v_bias,
@@ -462,6 +463,7 @@ extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void 
   const size_t es = c->es, H = c->cfg.hidden, I = c->cfg.inter, hd = c->cfg.head_dim;
   const size_t sq = (size_t)c->cfg.n_heads * hd, skv = (size_t)c->cfg.n_kv_heads * hd;
   auto *b = new cake_b200_block{c, layer_idx, c->device};
+  const int rc = [&]() -> int {  // on any failure (e.g. out of memory half way through a shard) nothing is leaked
   // attention.rs:109-113: Wqkv = cat([q,k,v], 0)
   CU(cudaMalloc(&b->wqkv, (sq + 2 * skv) * H * es + 16));
   CU(cudaMemcpy(b->wqkv, q, sq * H * es, cudaMemcpyDefault));
@@ -486,6 +488,12 @@ extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void 
     RC(upload(&b->qn, q_norm, hd * es));
     RC(upload(&b->kn, k_norm, hd * es));
   }
+  return CAKE_B200_OK;
+  }();
+  if (rc != CAKE_B200_OK) {
+    cake_b200_block_free(b);
+    return rc;
+  }
   *out = b;
   return CAKE_B200_OK;
 }
@@ -509,8 +517,14 @@ extern "C" int cake_b200_cache_create(cake_b200_ctx *c, int batch, int max_seq, 
   k->k.assign(c->cfg.n_layers, nullptr);
   k->v.assign(c->cfg.n_layers, nullptr);
   k->len.assign(c->cfg.n_layers, 0);
-  CU(cudaMalloc(&k->d_pos, 4));
-  CU(cudaMemset(k->d_pos, 0, 4));
+  cudaError_t e = cudaMalloc(&k->d_pos, 4);
+  if (e == cudaSuccess) e = cudaMemset(k->d_pos, 0, 4);
+  if (e != cudaSuccess) {
+    if (k->d_pos) cudaFree(k->d_pos);
+    delete k;
+    (void)cudaGetLastError();
+    return fail(CAKE_B200_ECUDA, "cache_create: %s", cudaGetErrorString(e));
+  }
   *out = k;
   return CAKE_B200_OK;
 }
