@@ -1,0 +1,52 @@
+"""Batch > 1 through the Forwarder (BASELINE.json configs[4] is a bs=32 prefill; `cake run` itself never builds
+b > 1, text_model.rs:418-420, so the reference's contract here is the Forwarder's `x: (b, s, H)`): every sequence of
+the batch must equal the oracle run on that sequence alone with its own cache.  Kept in its own file, last in
+collection order: round-1 GPU time ran out before this case could be run on hardware."""
+import pytest
+import torch
+
+from oracle import oracle as O
+from tests.util import checkpoint, max_ulp_err, mean_ulp_err, medium_config, rand_x, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+def test_batched_prefill_then_batched_decode_matches_oracle_per_sequence(dtype):
+    from cake_b200.model import B200Transformer, Cache, Context
+    cfg = medium_config()
+    sd = checkpoint(cfg, dtype, seed=31)
+    B, S = 3, 9
+    ctx = Context(cfg, sd, dtype, device=0, max_seq=64)
+    try:
+        ctx.cache = Cache(ctx, batch=B, max_seq=64)
+        blk = B200Transformer.load(cfg.layer_name(1), ctx)
+        x = rand_x((B, S + 2, cfg.hidden_size), dtype, seed=8)
+        om = O.OracleModel(cfg, sd, dtype, max_seq=64)
+        caches = [om.new_cache() for _ in range(B)]
+        y = blk.forward(ctx.to_device(x[:, :S].contiguous()), 0, 1, ctx)          # prefill (B, S, H) at position 0
+        ctx.sync()
+        assert y.shape == (B, S, cfg.hidden_size)
+        for b in range(B):
+            ref = om.block_forward(1, x[b, :S].float().numpy(), 0, caches[b])
+            e = max_ulp_err(to_np(y[b]), ref, dtype)
+            assert e <= 4.0 and mean_ulp_err(to_np(y[b]), ref, dtype) <= 0.25, f"prefill seq {b}: {e} ulp"
+        for t in (S, S + 1):                                                        # then (B, 1, H) steps
+            y = blk.forward(ctx.to_device(x[:, t:t + 1].contiguous()), t, 1, ctx)
+            ctx.sync()
+            for b in range(B):
+                ref = om.block_forward(1, x[b, t:t + 1].float().numpy(), t, caches[b])
+                e = max_ulp_err(to_np(y[b]), ref, dtype)
+                assert e <= 4.0, f"decode @{t} seq {b}: {e} ulp"
+        assert ctx.cache.len(1) == S + 2
+        k, v = ctx.cache.kv(1)                                                      # (B, n_kv, len, hd)
+        for b in range(B):
+            ko, vo = caches[b].kv(1)
+            assert max_ulp_err(to_np(k[b]), ko[:, :S + 2], dtype) <= 2.0
+            assert max_ulp_err(to_np(v[b]), vo[:, :S + 2], dtype) <= 2.0
+        # a batch that does not match the cache's batch is an error, not a crash
+        from cake_b200.capi import CakeB200Error
+        with pytest.raises(CakeB200Error, match="batch"):
+            blk.forward(ctx.to_device(x[:1, :1].contiguous()), S + 2, 1, ctx)
+    finally:
+        ctx.close()
