@@ -29,7 +29,8 @@ if [[ "$what" == probes || "$what" == all ]]; then
   $NVCC $ARCH -o /tmp/barrier_probe bench_tools/barrier_probe.cu && timeout 120 /tmp/barrier_probe 2000 > "$out/barrier_probe.txt" 2>&1
   $NVCC $ARCH -o /tmp/l2_prefetch_probe bench_tools/l2_prefetch_probe.cu && { timeout 120 /tmp/l2_prefetch_probe 32 8; timeout 120 /tmp/l2_prefetch_probe 24 4;
     for idle in 0 100 1000 3000; do echo "--- HBM idle ${idle} us"; timeout 120 /tmp/l2_prefetch_probe 32 $idle | grep "mode 0"; done; } > "$out/l2_prefetch_probe.txt" 2>&1
-  cat "$out/barrier_probe.txt" "$out/l2_prefetch_probe.txt" | tee -a "$out/round.log"
+  $NVCC $ARCH -o /tmp/attn_tile_probe bench_tools/attn_tile_probe.cu && timeout 60 /tmp/attn_tile_probe 200 > "$out/attn_tile_probe.txt" 2>&1
+  cat "$out/barrier_probe.txt" "$out/l2_prefetch_probe.txt" "$out/attn_tile_probe.txt" | tee -a "$out/round.log"
 fi
 if [[ "$what" == ncu || "$what" == all ]]; then
   step "ncu launch list + full capture of the decode kernel (numbers under ncu are never bench values)"
