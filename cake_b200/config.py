@@ -4,8 +4,9 @@ Mirrors the reference's generalized ``Config`` (cake-core/src/models/common/conf
 fields the dense Llama-family block path reads, and the HF ``config.json`` mappings of the architectures
 whose blocks are exactly that path: ``LlamaConfig::into_config`` (models/llama3/config.rs:62-98),
 ``Qwen3Config`` (qwen3/config.rs:55-93), ``Qwen2Config`` (qwen2/config.rs:69-105, q/k/v bias),
-``MistralConfig`` (mistral/config.rs:56-93, without an active sliding window) and ``Falcon3Config``
-(falcon3/config.rs:53-90).  Field names follow the reference.
+``MistralConfig`` (mistral/config.rs:56-93, without an active sliding window), ``Falcon3Config``
+(falcon3/config.rs:53-90) and ``Phi4Config`` (phi4/config.rs:63-100: pre-fused qkv / gate_up tensors, partial
+rotary).  Field names follow the reference.
 """
 from __future__ import annotations
 
@@ -47,6 +48,8 @@ class Config:
     use_qk_norm: bool = False
     eos_token_id: list = field(default_factory=list)
     sliding_window: Optional[int] = None
+    fused_qkv_proj: bool = False      # Phi-3/4: one 'qkv_proj' tensor = cat(q, k, v) (attention.rs:90-94)
+    fused_gate_up_proj: bool = False  # Phi-3/4: one 'gate_up_proj' tensor = cat(gate, up) (mlp.rs:38-40)
 
     @property
     def hd(self) -> int:
@@ -75,9 +78,11 @@ class Config:
         "Qwen3ForCausalLM": (1000000.0, 40960, dict(use_qk_norm=True, _head_dim=True)),
         "MistralForCausalLM": (1000000.0, 131072, dict(_head_dim=True, _sliding_window=True)),
         "FalconForCausalLM": (500000.0, 131072, dict(_head_dim=True)),
+        "Phi3ForCausalLM": (1000000.0, 131072, dict(_head_dim=True, _partial=True, _fused=True)),
+        "Phi4ForCausalLM": (1000000.0, 131072, dict(_head_dim=True, _partial=True, _fused=True)),
     }
     _OTHER_BLOCKS = ("Qwen3_5ForConditionalGeneration", "Qwen3MoeForCausalLM", "Qwen3_5MoeForConditionalGeneration",
-                     "Phi3ForCausalLM", "Phi4ForCausalLM", "Gemma3ForCausalLM", "OLMo2ForCausalLM",
+                     "Gemma3ForCausalLM", "OLMo2ForCausalLM",
                      "Olmo2ForCausalLM", "ExaoneForCausalLM", "LuxTTSForTextToSpeech")
 
     @staticmethod
@@ -125,6 +130,8 @@ class Config:
             use_qk_norm=bool(flags.get("use_qk_norm", False)),
             head_dim=d.get("head_dim") if flags.get("_head_dim") else None,
             sliding_window=d.get("sliding_window") if flags.get("_sliding_window") else None,
+            partial_rotary_factor=float(d.get("partial_rotary_factor") or 1.0) if flags.get("_partial") else 1.0,
+            fused_qkv_proj=bool(flags.get("_fused")), fused_gate_up_proj=bool(flags.get("_fused")),
         )
 
     @staticmethod
@@ -144,6 +151,8 @@ class Config:
             d["head_dim"] = self.head_dim
         if self.sliding_window:
             d["sliding_window"] = self.sliding_window
+        if self.partial_rotary_factor != 1.0:
+            d["partial_rotary_factor"] = self.partial_rotary_factor
         if self.rope_scaling:
             d["rope_scaling"] = asdict(self.rope_scaling)
         return d

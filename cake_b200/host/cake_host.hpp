@@ -145,6 +145,7 @@ struct Config {
   std::string model_prefix = "model";
   std::vector<uint32_t> eos;
   std::string arch;
+  bool fused_qkv_proj = false, fused_gate_up_proj = false;  // attention.rs:90-94, mlp.rs:38-40
   static Config from_path(const std::string &path, int dtype, int max_seq_override = 0) {
     std::string txt = slurp(path);
     Json j = JsonParser(txt.data(), txt.size()).value();
@@ -155,16 +156,19 @@ struct Config {
     // Per-architecture serde defaults and hard-wired flags of each into_config (llama3/config.rs:62-98,
     // qwen2/config.rs:69-105, qwen3/config.rs:55-93, mistral/config.rs:56-93, falcon3/config.rs:53-90).
     // Unknown strings fall back to Llama (cake/mod.rs:81-109); known architectures with another block are refused.
-    struct Arch { const char *name; double rope; int max_pos; bool bias, qk_norm, head_dim, window; };
+    struct Arch { const char *name; double rope; int max_pos; bool bias, qk_norm, head_dim, window, phi; };
     static const Arch archs[] = {
-        {"LlamaForCausalLM", 500000.0, 4096, false, false, false, false},
-        {"Qwen2ForCausalLM", 1000000.0, 32768, true, false, false, false},
-        {"Qwen3ForCausalLM", 1000000.0, 40960, false, true, true, false},
-        {"MistralForCausalLM", 1000000.0, 131072, false, false, true, true},
-        {"FalconForCausalLM", 500000.0, 131072, false, false, true, false},
+        {"LlamaForCausalLM", 500000.0, 4096, false, false, false, false, false},
+        {"Qwen2ForCausalLM", 1000000.0, 32768, true, false, false, false, false},
+        {"Qwen3ForCausalLM", 1000000.0, 40960, false, true, true, false, false},
+        {"MistralForCausalLM", 1000000.0, 131072, false, false, true, true, false},
+        {"FalconForCausalLM", 500000.0, 131072, false, false, true, false, false},
+        // phi4/config.rs:63-100: pre-fused qkv_proj / gate_up_proj tensors, partial rotary
+        {"Phi3ForCausalLM", 1000000.0, 131072, false, false, true, false, true},
+        {"Phi4ForCausalLM", 1000000.0, 131072, false, false, true, false, true},
     };
     static const char *other_blocks[] = {"Qwen3_5ForConditionalGeneration", "Qwen3MoeForCausalLM",
-        "Qwen3_5MoeForConditionalGeneration", "Phi3ForCausalLM", "Phi4ForCausalLM", "Gemma3ForCausalLM",
+        "Qwen3_5MoeForConditionalGeneration", "Gemma3ForCausalLM",
         "OLMo2ForCausalLM", "Olmo2ForCausalLM", "ExaoneForCausalLM", "LuxTTSForTextToSpeech"};
     for (const char *o : other_blocks)
       if (k.arch == o) throw Error("architecture " + k.arch + " is outside the block-forward path built here");
@@ -190,7 +194,8 @@ struct Config {
     c.head_dim = ar->head_dim ? (int)j.number("head_dim", hd_default) : hd_default;
     c.rms_eps = (float)j.number("rms_norm_eps", 1e-5);
     c.rope_theta = (float)j.number("rope_theta", ar->rope);
-    c.partial_rotary = 1.0f;
+    c.partial_rotary = ar->phi ? (float)j.number("partial_rotary_factor", 1.0) : 1.0f;
+    k.fused_qkv_proj = k.fused_gate_up_proj = ar->phi;
     c.max_seq = max_seq_override ? max_seq_override : (int)j.number("max_position_embeddings", ar->max_pos);
     c.tie_embeddings = j.boolean("tie_word_embeddings", false);
     c.qk_norm = ar->qk_norm;
@@ -416,9 +421,22 @@ class Transformer : public Forwarder {  // transformer.rs:14-150, backed by the 
     int layer = std::stoi(name.substr(name.rfind('.') + 1));
     auto t = std::unique_ptr<Transformer>(new Transformer());
     t->name_ = name;
-    check(cake_b200_block_load(ctx.h, layer, g("self_attn.q_proj.weight", Sh{sq, H}), g("self_attn.k_proj.weight", Sh{skv, H}),
-                               g("self_attn.v_proj.weight", Sh{skv, H}), g("self_attn.o_proj.weight", Sh{H, sq}),
-                               g("mlp.gate_proj.weight", Sh{I, H}), g("mlp.up_proj.weight", Sh{I, H}), g("mlp.down_proj.weight", Sh{H, I}),
+    const size_t es = 2;  // bf16 / f16
+    const void *q, *k, *v, *gate, *up;
+    if (ctx.config.fused_qkv_proj) {  // one tensor = cat(q, k, v): the three are contiguous row ranges of it
+      const char *w = (const char *)g("self_attn.qkv_proj.weight", Sh{sq + 2 * skv, H});
+      q = w; k = w + (size_t)sq * H * es; v = w + (size_t)(sq + skv) * H * es;
+    } else {
+      q = g("self_attn.q_proj.weight", Sh{sq, H}); k = g("self_attn.k_proj.weight", Sh{skv, H}); v = g("self_attn.v_proj.weight", Sh{skv, H});
+    }
+    if (ctx.config.fused_gate_up_proj) {
+      const char *w = (const char *)g("mlp.gate_up_proj.weight", Sh{2 * I, H});
+      gate = w; up = w + (size_t)I * H * es;
+    } else {
+      gate = g("mlp.gate_proj.weight", Sh{I, H}); up = g("mlp.up_proj.weight", Sh{I, H});
+    }
+    check(cake_b200_block_load(ctx.h, layer, q, k, v, g("self_attn.o_proj.weight", Sh{H, sq}),
+                               gate, up, g("mlp.down_proj.weight", Sh{H, I}),
                                g("input_layernorm.weight", Sh{H}), g("post_attention_layernorm.weight", Sh{H}),
                                c.qkv_bias ? g("self_attn.q_proj.bias", Sh{sq}) : nullptr, c.qkv_bias ? g("self_attn.k_proj.bias", Sh{skv}) : nullptr,
                                c.qkv_bias ? g("self_attn.v_proj.bias", Sh{skv}) : nullptr,

@@ -195,6 +195,57 @@ class VarBuilder(Mapping):
         return sum(f.nbytes(n) for n, f in self._where.items())
 
 
+BLOCK_TENSORS = ("self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight", "self_attn.o_proj.weight",
+                 "mlp.gate_proj.weight", "mlp.up_proj.weight", "mlp.down_proj.weight", "input_layernorm.weight",
+                 "post_attention_layernorm.weight", "self_attn.q_proj.bias", "self_attn.k_proj.bias", "self_attn.v_proj.bias",
+                 "self_attn.q_norm.weight", "self_attn.k_norm.weight")
+
+
+def block_tensors(vb, cfg: Config, name: str) -> Dict[str, Optional[torch.Tensor]]:
+    """The tensors `Transformer::load` reads for layer ``name`` (transformer.rs:79-101, attention.rs:76-149,
+    mlp.rs:34-59), by the short names of BLOCK_TENSORS, each checked against the shape the layer declares (candle's
+    ``vb.get(shape, name)``).  Pre-fused checkpoints (Phi-3/4: ``cfg.fused_qkv_proj`` / ``cfg.fused_gate_up_proj``,
+    attention.rs:90-94, mlp.rs:38-40) are split into row views of the fused tensor — q, k, v and gate, up are
+    contiguous row ranges of it, so no copy is made.  Biases / QK-norm weights are None unless the config uses them."""
+    H, I, sq, skv, hd = cfg.hidden_size, cfg.intermediate_size, cfg.size_q, cfg.size_kv, cfg.hd
+
+    def get(short: str, shape) -> torch.Tensor:
+        t = vb.get(f"{name}.{short}")
+        if t is None:
+            raise KeyError(f"tensor {name}.{short} not found")  # candle VarBuilder error
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"shape mismatch for {name}.{short}, expected: {list(shape)}, got: {list(t.shape)}")
+        return t
+
+    out: Dict[str, Optional[torch.Tensor]] = {k: None for k in BLOCK_TENSORS}
+    if cfg.fused_qkv_proj:
+        w = get("self_attn.qkv_proj.weight", (sq + 2 * skv, H))
+        out["self_attn.q_proj.weight"], out["self_attn.k_proj.weight"], out["self_attn.v_proj.weight"] = \
+            w[:sq], w[sq:sq + skv], w[sq + skv:]
+    else:
+        out["self_attn.q_proj.weight"] = get("self_attn.q_proj.weight", (sq, H))
+        out["self_attn.k_proj.weight"] = get("self_attn.k_proj.weight", (skv, H))
+        out["self_attn.v_proj.weight"] = get("self_attn.v_proj.weight", (skv, H))
+    out["self_attn.o_proj.weight"] = get("self_attn.o_proj.weight", (H, sq))
+    if cfg.fused_gate_up_proj:
+        w = get("mlp.gate_up_proj.weight", (2 * I, H))
+        out["mlp.gate_proj.weight"], out["mlp.up_proj.weight"] = w[:I], w[I:]
+    else:
+        out["mlp.gate_proj.weight"] = get("mlp.gate_proj.weight", (I, H))
+        out["mlp.up_proj.weight"] = get("mlp.up_proj.weight", (I, H))
+    out["mlp.down_proj.weight"] = get("mlp.down_proj.weight", (H, I))
+    out["input_layernorm.weight"] = get("input_layernorm.weight", (H,))
+    out["post_attention_layernorm.weight"] = get("post_attention_layernorm.weight", (H,))
+    if cfg.use_qkv_bias:  # attention.rs:96-107 (never together with a fused qkv_proj)
+        out["self_attn.q_proj.bias"] = get("self_attn.q_proj.bias", (sq,))
+        out["self_attn.k_proj.bias"] = get("self_attn.k_proj.bias", (skv,))
+        out["self_attn.v_proj.bias"] = get("self_attn.v_proj.bias", (skv,))
+    if cfg.use_qk_norm:   # attention.rs:120-129
+        out["self_attn.q_norm.weight"] = get("self_attn.q_norm.weight", (hd,))
+        out["self_attn.k_norm.weight"] = get("self_attn.k_norm.weight", (hd,))
+    return out
+
+
 def detect_model_prefix(index_path: str, configured: str) -> str:
     """cake/mod.rs:335-357: the text before the first ``.layers.0.`` key of the index wins over the configured prefix."""
     if not os.path.exists(index_path):

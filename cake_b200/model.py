@@ -28,7 +28,7 @@ import torch
 from . import capi
 from .capi import byref, c_uint32, c_void_p, check, int_array, lib, ptr, ptr_array
 from .config import CConfig, Config
-from .synth import TORCH_DTYPES, layer_tensor_shapes
+from .synth import TORCH_DTYPES
 
 
 class Cache:
@@ -179,33 +179,16 @@ class B200Transformer(Forwarder):
 
     @classmethod
     def load(cls, name: str, ctx: Context) -> "B200Transformer":
-        vb, cfg = ctx.var_builder, ctx.config
-
-        shapes = layer_tensor_shapes(cfg)
-
-        def get(short: str, required: bool = True):
-            t = vb.get(f"{name}.{short}")
-            if t is None:
-                if required:
-                    raise KeyError(f"tensor {name}.{short} not found")  # candle VarBuilder error
-                return None
-            want = shapes.get(short)
-            if want is not None and tuple(t.shape) != tuple(want):  # candle's vb.get(shape, name) check
-                raise ValueError(f"shape mismatch for {name}.{short}, expected: {list(want)}, got: {list(t.shape)}")
-            if t.dtype != ctx.torch_dtype:
-                t = t.to(ctx.torch_dtype)
-            return t.contiguous()
-
-        keep = [get("self_attn.q_proj.weight"), get("self_attn.k_proj.weight"), get("self_attn.v_proj.weight"),
-                get("self_attn.o_proj.weight"), get("mlp.gate_proj.weight"), get("mlp.up_proj.weight"),
-                get("mlp.down_proj.weight"), get("input_layernorm.weight"), get("post_attention_layernorm.weight"),
-                get("self_attn.q_proj.bias", cfg.use_qkv_bias), get("self_attn.k_proj.bias", cfg.use_qkv_bias),
-                get("self_attn.v_proj.bias", cfg.use_qkv_bias),
-                get("self_attn.q_norm.weight", cfg.use_qk_norm), get("self_attn.k_norm.weight", cfg.use_qk_norm)]
-        if not cfg.use_qkv_bias:
-            keep[9] = keep[10] = keep[11] = None
-        if not cfg.use_qk_norm:
-            keep[12] = keep[13] = None
+        from .loader import BLOCK_TENSORS, block_tensors
+        views = block_tensors(ctx.var_builder, ctx.config, name)
+        keep = []
+        for short in BLOCK_TENSORS:  # the argument order of cake_b200_block_load
+            t = views[short]
+            if t is not None:
+                if t.dtype != ctx.torch_dtype:
+                    t = t.to(ctx.torch_dtype)
+                t = t.contiguous()   # row views of a fused tensor are contiguous already
+            keep.append(t)
         h = c_void_p()
         check(lib().cake_b200_block_load(ctx.h, _layer_index(name), *[ptr(t) for t in keep], byref(h)))
         return cls(name, h, ctx)

@@ -46,13 +46,19 @@ def _fill(shape, name: str, gen: torch.Generator, device, dtype, std: float):
 
 
 def make_layer(cfg: Config, i: int, dtype: str = "bf16", seed: int = 1234, device="cpu", std: float = 0.02) -> dict:
-    """Weights of one block, keyed by full HF name.  Deterministic per (seed, layer, device type)."""
+    """Weights of one block, keyed by full HF name.  Deterministic per (seed, layer, device type).  With
+    ``cfg.fused_qkv_proj`` / ``cfg.fused_gate_up_proj`` (Phi-3/4 checkpoints) the same values are stored as
+    ``self_attn.qkv_proj.weight = cat(q, k, v)`` / ``mlp.gate_up_proj.weight = cat(gate, up)``."""
     gen = torch.Generator(device=device)
     gen.manual_seed(seed * 1000003 + i)
     out = {}
     for short, shape in layer_tensor_shapes(cfg).items():
-        out[f"{cfg.layer_name(i)}.{short}"] = _fill(shape, short, gen, device, TORCH_DTYPES[dtype], std)
-    return out
+        out[short] = _fill(shape, short, gen, device, TORCH_DTYPES[dtype], std)
+    if cfg.fused_qkv_proj:
+        out["self_attn.qkv_proj.weight"] = torch.cat([out.pop(f"self_attn.{p}_proj.weight") for p in "qkv"], 0)
+    if cfg.fused_gate_up_proj:
+        out["mlp.gate_up_proj.weight"] = torch.cat([out.pop("mlp.gate_proj.weight"), out.pop("mlp.up_proj.weight")], 0)
+    return {f"{cfg.layer_name(i)}.{short}": t for short, t in out.items()}
 
 
 def make_head(cfg: Config, dtype: str = "bf16", seed: int = 1234, device="cpu", std: float = 0.02,

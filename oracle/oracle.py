@@ -209,14 +209,17 @@ class OracleModel:
             self._keep.append(t)
             return t
 
+        from cake_b200.loader import BLOCK_TENSORS, block_tensors  # same tensor naming / fused-checkpoint rules as the loader
         for i in (layers if layers is not None else range(cfg.num_hidden_layers)):
-            n = cfg.layer_name(i)
-            g = lambda s: _ptr(W(f"{n}.{s}"))
-            ol = OraLayer(g("self_attn.q_proj.weight"), g("self_attn.k_proj.weight"), g("self_attn.v_proj.weight"),
-                          g("self_attn.o_proj.weight"), g("mlp.gate_proj.weight"), g("mlp.up_proj.weight"),
-                          g("mlp.down_proj.weight"), g("input_layernorm.weight"), g("post_attention_layernorm.weight"),
-                          g("self_attn.q_proj.bias"), g("self_attn.k_proj.bias"), g("self_attn.v_proj.bias"),
-                          g("self_attn.q_norm.weight"), g("self_attn.k_norm.weight"))
+            views = block_tensors(weights, cfg, cfg.layer_name(i))
+            ptrs = []
+            for short in BLOCK_TENSORS:
+                t = views[short]
+                if t is not None:
+                    t = t.detach().cpu().contiguous()
+                    self._keep.append(t)
+                ptrs.append(_ptr(t))
+            ol = OraLayer(*ptrs)
             lib().ora_model_set_layer(self.h, i, ctypes.byref(ol))
         emb, lnf, head = W(f"{p}.embed_tokens.weight"), W(f"{p}.norm.weight"), W("lm_head.weight")
         lib().ora_model_set_head(self.h, _ptr(emb), _ptr(lnf), _ptr(head))

@@ -30,6 +30,9 @@ CASES = {
     "mistral_tiny": ("MistralForCausalLM", dict(head_dim=32, rope_theta=1000000.0)),
     # Falcon3 checkpoints are Llama blocks with an explicit head_dim (falcon3/config.rs:53-90); HF runs them as Llama
     "falcon3_tiny": ("FalconForCausalLM", dict(head_dim=24, rope_theta=500000.0, num_key_value_heads=1)),
+    # Phi-3/4: pre-fused qkv_proj / gate_up_proj tensors, rotary on the first half of each head only (phi4/config.rs:63-100)
+    "phi3_tiny": ("Phi3ForCausalLM", dict(partial_rotary_factor=0.5, rope_theta=1000000.0, fused_qkv_proj=True,
+                                          fused_gate_up_proj=True)),
 }
 SEED, STD, N_IDS = 3, 0.1, 12
 
@@ -40,8 +43,8 @@ def case_config(name):
 
 
 def hf_logits(arch, cfg, sd, ids):
-    from transformers import (LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM, Qwen2Config,
-                              Qwen2ForCausalLM, Qwen3Config, Qwen3ForCausalLM)
+    from transformers import (LlamaConfig, LlamaForCausalLM, MistralConfig, MistralForCausalLM, Phi3Config, Phi3ForCausalLM,
+                              Qwen2Config, Qwen2ForCausalLM, Qwen3Config, Qwen3ForCausalLM)
     d = cfg.to_hf(arch)
     d.pop("architectures")
     if arch in ("LlamaForCausalLM", "FalconForCausalLM"):
@@ -50,6 +53,8 @@ def hf_logits(arch, cfg, sd, ids):
         m = Qwen2ForCausalLM(Qwen2Config(**d, use_sliding_window=False))
     elif arch == "MistralForCausalLM":
         m = MistralForCausalLM(MistralConfig(**d, sliding_window=None))
+    elif arch == "Phi3ForCausalLM":
+        m = Phi3ForCausalLM(Phi3Config(**d, pad_token_id=0, original_max_position_embeddings=d["max_position_embeddings"]))
     else:
         m = Qwen3ForCausalLM(Qwen3Config(**d))
     sd = {k: v.float() for k, v in sd.items()}

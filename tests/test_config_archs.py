@@ -33,6 +33,11 @@ CASES = {
                 dict(rope_theta=10000.0, max_seq=131072, head_dim=32, qkv_bias=0)),
     "falcon3": (dict(architectures=["FalconForCausalLM"], head_dim=32, num_key_value_heads=1, eos_token_id=[7, 9]),
                 dict(rope_theta=500000.0, max_seq=131072, head_dim=32, kv_heads=1, n_eos=2)),
+    "phi4_mini": (dict(architectures=["Phi3ForCausalLM"], partial_rotary_factor=0.75, head_dim=32, num_key_value_heads=2),
+                  dict(rope_theta=1000000.0, max_seq=131072, head_dim=32, kv_heads=2, partial_rotary=0.75, fused=1, qkv_bias=0)),
+    "phi4": (dict(architectures=["Phi4ForCausalLM"]), dict(partial_rotary=1.0, fused=1, head_dim=16)),
+    "llama_ignores_partial_rotary": (dict(architectures=["LlamaForCausalLM"], partial_rotary_factor=0.5),
+                                     dict(partial_rotary=1.0, fused=0)),
 }
 
 
@@ -40,7 +45,8 @@ def _python_view(d: dict) -> dict:
     c = Config.from_hf(d)
     cc = CConfig.from_config(c, "bf16")
     return dict(rope_theta=float(cc.rope_theta), max_seq=cc.max_seq, qkv_bias=cc.qkv_bias, qk_norm=cc.qk_norm,
-                head_dim=cc.head_dim, kv_heads=cc.n_kv_heads, tie=cc.tie_embeddings, n_eos=len(c.eos_token_id))
+                head_dim=cc.head_dim, kv_heads=cc.n_kv_heads, tie=cc.tie_embeddings, n_eos=len(c.eos_token_id),
+                partial_rotary=float(cc.partial_rotary), fused=int(c.fused_qkv_proj and c.fused_gate_up_proj))
 
 
 def _cpp_view(tmp_path, d: dict) -> dict:
@@ -50,7 +56,7 @@ def _cpp_view(tmp_path, d: dict) -> dict:
     r = subprocess.run([RUN, str(tmp_path), "--show-config"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     kv = dict(p.split("=", 1) for p in r.stdout.split())
-    return {k: (float(v) if k in ("rope_theta", "rms_eps") else v if k == "arch" else int(v)) for k, v in kv.items()}
+    return {k: (float(v) if k in ("rope_theta", "rms_eps", "partial_rotary") else v if k == "arch" else int(v)) for k, v in kv.items()}
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -65,7 +71,7 @@ def test_python_and_cpp_resolve_the_same_block_config(tmp_path, name):
         assert py[k] == cpp[k], (name, k, py[k], cpp[k])
 
 
-@pytest.mark.parametrize("arch", ["Phi3ForCausalLM", "Gemma3ForCausalLM", "Qwen3MoeForCausalLM", "OLMo2ForCausalLM"])
+@pytest.mark.parametrize("arch", ["Gemma3ForCausalLM", "Qwen3MoeForCausalLM", "OLMo2ForCausalLM", "ExaoneForCausalLM"])
 def test_other_block_types_are_refused_by_name(tmp_path, arch):
     d = {**BASE, "architectures": [arch]}
     with pytest.raises(ValueError, match="outside the block-forward path"):

@@ -257,3 +257,39 @@ def test_cpp_varbuilder_maps_the_same_tensors_as_the_python_loader(tmp_path, lay
         t = vb[name]
         raw = t.contiguous().view(torch.uint8).numpy().tobytes()
         assert got[name] == ("BF16", "[" + "x".join(str(d) for d in t.shape) + "]", len(raw), _fnv1a(raw)), name
+
+
+def test_prefused_checkpoints_split_into_views_and_give_the_same_model(tmp_path):
+    """Phi-3/4 checkpoints store qkv_proj / gate_up_proj pre-fused (attention.rs:90-94, mlp.rs:38-40).  The loader hands
+    the library row views of the fused tensor (no copy), and the model is the same as the unfused one."""
+    from cake_b200.loader import block_tensors
+    from oracle.oracle import OracleModel
+    kw = dict(num_hidden_layers=2, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+              num_key_value_heads=2, head_dim=32, partial_rotary_factor=0.75)
+    plain = medium_config(**kw)
+    fused = medium_config(**kw, fused_qkv_proj=True, fused_gate_up_proj=True)
+    sd_p, sd_f = checkpoint(plain, "bf16", seed=4, peaked=True), checkpoint(fused, "bf16", seed=4, peaked=True)
+    n = fused.layer_name(1)
+    assert f"{n}.self_attn.qkv_proj.weight" in sd_f and f"{n}.self_attn.q_proj.weight" not in sd_f
+    assert f"{n}.mlp.gate_up_proj.weight" in sd_f and f"{n}.mlp.up_proj.weight" not in sd_f
+    save_checkpoint(str(tmp_path), fused, sd_f, arch="Phi3ForCausalLM", shard_bytes=300_000)
+    cfg, vb = open_model(str(tmp_path))
+    assert cfg.fused_qkv_proj and cfg.fused_gate_up_proj and cfg.partial_rotary_factor == 0.75 and cfg.hd == 32
+    views, ref = block_tensors(vb, cfg, n), block_tensors(sd_p, plain, n)
+    for k, t in ref.items():
+        assert (t is None) == (views[k] is None), k
+        if t is not None:
+            assert torch.equal(views[k], t), k
+    w = vb[f"{n}.self_attn.qkv_proj.weight"]
+    assert views["self_attn.q_proj.weight"].data_ptr() == w.data_ptr()                       # views, not copies
+    assert views["self_attn.k_proj.weight"].data_ptr() == w.data_ptr() + cfg.size_q * cfg.hidden_size * 2
+    assert views["self_attn.v_proj.weight"].is_contiguous() and views["mlp.up_proj.weight"].is_contiguous()
+    prompt = np.random.default_rng(1).integers(0, cfg.vocab_size - 1, 6).tolist()
+    a = OracleModel(plain, sd_p, "bf16", max_seq=32).generate(prompt, 6)[0]
+    b = OracleModel(cfg, vb, "bf16", max_seq=32).generate(prompt, 6)[0]
+    assert list(a) == list(b)
+    # a fused tensor of the wrong height is refused
+    bad = dict(sd_f)
+    bad[f"{n}.mlp.gate_up_proj.weight"] = bad[f"{n}.mlp.gate_up_proj.weight"][:-2].contiguous()
+    with pytest.raises(ValueError, match="shape mismatch for model.layers.1.mlp.gate_up_proj.weight"):
+        block_tensors(bad, fused, n)

@@ -50,3 +50,35 @@ def test_batched_prefill_then_batched_decode_matches_oracle_per_sequence(dtype):
             blk.forward(ctx.to_device(x[:1, :1].contiguous()), S + 2, 1, ctx)
     finally:
         ctx.close()
+
+
+def test_phi_style_block_partial_rotary_and_prefused_weights():
+    """Phi-3/4 shape of the same block: rotary on the first 3/4 of every head only, qkv_proj / gate_up_proj stored
+    pre-fused.  The oracle side of this configuration is pinned by the HuggingFace Phi3 fixture; on the GPU it is the
+    first run of `rot < head_dim` (also not yet run on hardware)."""
+    from cake_b200.model import B200Transformer, Context
+    dtype = "bf16"
+    cfg = medium_config(partial_rotary_factor=0.75, fused_qkv_proj=True, fused_gate_up_proj=True)
+    sd = checkpoint(cfg, dtype, seed=41)
+    om = O.OracleModel(cfg, sd, dtype, max_seq=64)
+    oc = om.new_cache()
+    ctx = Context(cfg, sd, dtype, device=0, max_seq=64)
+    try:
+        blk = B200Transformer.load(cfg.layer_name(1), ctx)
+        x = rand_x((1, 12, cfg.hidden_size), dtype, seed=6)
+        ref = om.block_forward(1, x[0, :9].float().numpy(), 0, oc)
+        y = blk.forward(ctx.to_device(x[:, :9].contiguous()), 0, 1, ctx)         # prefill kernels
+        ctx.sync()
+        e = max_ulp_err(to_np(y[0]), ref, dtype)
+        assert e <= 4.0 and mean_ulp_err(to_np(y[0]), ref, dtype) <= 0.25, f"prefill: {e} ulp"
+        for t in range(9, 12):                                                     # decode megakernel
+            ref = om.block_forward(1, x[0, t:t + 1].float().numpy(), t, oc)
+            y = blk.forward(ctx.to_device(x[:, t:t + 1].contiguous()), t, 1, ctx)
+            ctx.sync()
+            e = max_ulp_err(to_np(y[0]), ref, dtype)
+            assert e <= 4.0, f"decode @{t}: {e} ulp"
+        k, _ = ctx.cache.kv(1)
+        ko, _ = oc.kv(1)
+        assert max_ulp_err(to_np(k[0]), ko[:, :12], dtype) <= 2.0                 # rotated part and pass-through part of K
+    finally:
+        ctx.close()
