@@ -91,3 +91,169 @@ def test_damaged_safetensors_is_an_error_not_a_crash(tmp_path, damage):
         p.write_bytes(struct.pack("<Q", 16) + b"this is not json" + raw[8 + n:])
     r = subprocess.run([RUN, str(tmp_path), "--prompt-ids", "1,2", "-n", "1"], capture_output=True, text=True, timeout=60)
     assert r.returncode == 1 and r.stderr.startswith("error:") and "ctx_create" not in r.stderr, r.stderr
+
+
+def _fnv(b: bytes) -> str:
+    h = 1469598103934665603
+    for x in b:
+        h = ((h ^ x) * 1099511628211) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+@pytest.mark.parametrize("flavour", ["llama", "qwen2_bias", "qwen3_qknorm_tied", "phi_fused", "sharded_worker"])
+def test_compiled_host_hands_the_library_the_right_bytes(tmp_path, flavour):
+    """cake_run / cake_worker against a recording stand-in for libcake_b200.so (tests/fake_b200): the compiled path
+    config.json -> mmapped VarBuilder -> TextModelBase::load / Transformer::load must give ctx_create the resolved
+    config and head_load / block_load pointers to exactly the checkpoint's bytes, in header order, null where unused —
+    for plain, biased, QK-norm + tied, pre-fused (Phi) checkpoints and for a worker's shard subset.  No GPU."""
+    import torch
+    from cake_b200.loader import save_checkpoint
+    from tests.fake_b200.make_fake import build as build_fake
+    build()
+    fake_dir = tmp_path / "fake"
+    fake_dir.mkdir()
+    build_fake(str(fake_dir))
+    kw = dict(num_hidden_layers=3, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+              num_key_value_heads=2, head_dim=32)
+    arch, extra = {"llama": ("LlamaForCausalLM", {}),
+                   "qwen2_bias": ("Qwen2ForCausalLM", dict(use_qkv_bias=True)),
+                   "qwen3_qknorm_tied": ("Qwen3ForCausalLM", dict(use_qk_norm=True, tie_word_embeddings=True)),
+                   "phi_fused": ("Phi3ForCausalLM", dict(fused_qkv_proj=True, fused_gate_up_proj=True, partial_rotary_factor=0.75)),
+                   "sharded_worker": ("LlamaForCausalLM", {})}[flavour]
+    cfg = medium_config(**kw, **extra)
+    plain = medium_config(**kw, **{k: v for k, v in extra.items() if not k.startswith("fused")})
+    sd, sd_plain = checkpoint(cfg, "bf16", seed=9), checkpoint(plain, "bf16", seed=9)
+    model = tmp_path / "model"
+    save_checkpoint(str(model), cfg, sd, arch=arch, shard_bytes=200_000)
+    log = tmp_path / "log.txt"
+    env = {**os.environ, "LD_LIBRARY_PATH": str(fake_dir), "FAKE_B200_LOG": str(log)}
+    if flavour == "sharded_worker":
+        worker = os.path.join(ROOT, "cake_b200", "host", "cake_worker")
+        p = subprocess.Popen([worker, str(model), "--layers", "model.layers.1-2", "--address", "127.0.0.1:0", "--max-seq", "64"],
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+        assert p.stdout.readline().startswith("listening on "), p.stderr.read()
+        p.kill()
+        p.wait(5)
+        layers = [1, 2]
+    else:
+        r = subprocess.run([RUN, str(model), "--prompt-ids", "1,2", "-n", "1", "--max-seq", "64"], capture_output=True, text=True, env=env, timeout=60)
+        assert r.returncode == 1 and "fake libcake_b200" in r.stderr, r.stderr   # loads everything, then the stand-in refuses to compute
+        layers = [0, 1, 2]
+    lines = log.read_text().split("\n")
+    ctx = [ln.split() for ln in lines if ln.startswith("ctx ")][0]
+    want_ctx = [0, cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.num_key_value_heads, cfg.hd, cfg.num_hidden_layers,
+                cfg.vocab_size, 64]
+    assert [int(x) for x in ctx[1:10]] == want_ctx
+    assert float(ctx[12]) == cfg.partial_rotary_factor and [int(x) for x in ctx[13:17]] == [int(cfg.use_qkv_bias), int(cfg.use_qk_norm), int(cfg.tie_word_embeddings), 0]
+
+    def h(name):
+        t = sd_plain.get(name)
+        return "0" * 16 if t is None else _fnv(t.contiguous().view(torch.uint8).numpy().tobytes())
+
+    if flavour != "sharded_worker":
+        head = [ln.split() for ln in lines if ln.startswith("head ")][0]
+        assert head[1:] == [h("model.embed_tokens.weight"), h("model.norm.weight"), "0" * 16 if cfg.tie_word_embeddings else h("lm_head.weight")]
+    order = ["self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight", "self_attn.o_proj.weight",
+             "mlp.gate_proj.weight", "mlp.up_proj.weight", "mlp.down_proj.weight", "input_layernorm.weight",
+             "post_attention_layernorm.weight", "self_attn.q_proj.bias", "self_attn.k_proj.bias", "self_attn.v_proj.bias",
+             "self_attn.q_norm.weight", "self_attn.k_norm.weight"]
+    blocks = {int(ln.split()[1]): ln.split()[2:] for ln in lines if ln.startswith("block ")}
+    assert sorted(blocks) == layers
+    for i in layers:
+        assert blocks[i] == [h(f"model.layers.{i}.{s}") for s in order], f"layer {i}"
+
+
+def _emulation(tmp_path):
+    from tests.fake_b200.make_fake import build as build_fake
+    build()
+    d = tmp_path / "emu"
+    d.mkdir(exist_ok=True)
+    build_fake(str(d), oracle=True)
+    return {**os.environ, "LD_LIBRARY_PATH": str(d)}
+
+
+@pytest.mark.parametrize("flavour,penalty", [("llama", 1.0), ("llama", 1.3), ("qwen3_tied", 1.0), ("phi_fused", 1.0)])
+def test_cake_run_host_loop_reproduces_the_oracle_on_the_cpu(tmp_path, flavour, penalty):
+    """The compiled TextModelBase / Master loop (prefill through the block walk, then the host-stepped decode loop, or
+    the logits + repeat-penalty path) over an oracle-backed emulation of the C ABI (tests/fake_b200): its token ids must
+    be the oracle's own — i.e. positions, cache handling, sampling rule and tok/s bookkeeping are driven correctly."""
+    from cake_b200.loader import save_checkpoint
+    from oracle import oracle as O
+    env = _emulation(tmp_path)
+    kw = dict(num_hidden_layers=3, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+              num_key_value_heads=2, head_dim=32)
+    arch, extra = {"llama": ("LlamaForCausalLM", {}),
+                   "qwen3_tied": ("Qwen3ForCausalLM", dict(use_qk_norm=True, tie_word_embeddings=True)),
+                   "phi_fused": ("Phi3ForCausalLM", dict(fused_qkv_proj=True, fused_gate_up_proj=True, partial_rotary_factor=0.5))}[flavour]
+    cfg = medium_config(**kw, **extra)
+    sd = checkpoint(cfg, "bf16", seed=13, peaked=not cfg.tie_word_embeddings)
+    model = tmp_path / "model"
+    save_checkpoint(str(model), cfg, sd, arch=arch, shard_bytes=300_000)
+    prompt = np.random.default_rng(3).integers(0, cfg.vocab_size - 1, 9).tolist()
+    n = 12
+    r = subprocess.run([RUN, str(model), "--prompt-ids", ",".join(map(str, prompt)), "-n", str(n), "--max-seq", "64",
+                        "--repeat-penalty", str(penalty)], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = [int(t) for t in r.stdout.splitlines()[0].split(":")[1].split()]
+    om = O.OracleModel(cfg, sd, "bf16", max_seq=64)
+    cache, ids, pos, want = om.new_cache(), list(prompt), 0, []
+    for _ in range(n):   # text_model.rs:397-495 with the repeat-penalty rule of :435-452 (generated tokens only)
+        lg = om.forward(ids, pos, cache)
+        pos += len(ids)
+        if penalty != 1.0:
+            lg = O.repeat_penalty(O.round_to(lg, "bf16"), penalty, want[-128:], "bf16")
+        want.append(O.argmax(lg))
+        ids = [want[-1]]
+    assert got == want
+    assert "tok/s:" in r.stdout
+
+
+def test_cake_worker_sessions_and_errors_on_the_cpu(tmp_path):
+    """cake_worker's B200Backend (one KV cache per connection, forwards under a lock, errors reported per request) over
+    the oracle-backed emulation: activations must equal the oracle's block outputs bit for bit, a second connection
+    starts from an empty cache, an out-of-order position is a WorkerError and the session stays usable."""
+    from cake_b200.loader import save_checkpoint
+    from cake_b200.wire import RawTensor, WireClient
+    from oracle import oracle as O
+    from tests.util import bits_to_f32, f32_to_bits, rand_x
+    env = _emulation(tmp_path)
+    cfg = medium_config(num_hidden_layers=4, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+                        num_key_value_heads=2, head_dim=32)
+    sd = checkpoint(cfg, "bf16", seed=19)
+    model = tmp_path / "model"
+    save_checkpoint(str(model), cfg, sd, shard_bytes=200_000)
+    worker = os.path.join(ROOT, "cake_b200", "host", "cake_worker")
+    p = subprocess.Popen([worker, str(model), "--layers", "model.layers.2-3", "--address", "127.0.0.1:0", "--max-seq", "32", "--connections", "2"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+    try:
+        line = p.stdout.readline().strip()
+        assert line.startswith("listening on "), p.stderr.read()
+        addr = line[len("listening on "):]
+        om = O.OracleModel(cfg, sd, "bf16", max_seq=32)
+        x = rand_x((1, 6, cfg.hidden_size), "bf16", seed=2)
+        raw = lambda t: RawTensor.from_numpy_bits(f32_to_bits(t.float().numpy(), "bf16"), "bf16")  # noqa: E731
+        for conn in range(2):   # second connection: own, empty cache -> the same prefill at position 0 is accepted again
+            c = WireClient(addr, cfg.layer_name(2), timeout=30)
+            assert c.info.dtype == "BF16" and c.info.device == "cuda"
+            oc = om.new_cache()
+            batch = [(cfg.layer_name(i), 0, i) for i in (2, 3)]
+            y = c.forward_batch(raw(x[:, :5]), batch)
+            ref = om.block_forward(3, om.block_forward(2, x[0, :5].float().numpy(), 0, oc), 0, oc)
+            assert y.shape == [1, 5, cfg.hidden_size] and np.array_equal(bits_to_f32(y.to_numpy_bits(), "bf16")[0], ref)
+            with pytest.raises(RuntimeError, match=r"forward pass failed for layer model.layers.2 \(block_idx=2\).*cache length"):
+                c.forward_batch(raw(x[:, 5:6]), [(cfg.layer_name(2), 9, 2)])
+            with pytest.raises(RuntimeError, match="could not find layer model.layers.0"):
+                c.forward_batch(raw(x[:, 5:6]), [(cfg.layer_name(0), 5, 0)])
+            y = c.forward_batch(raw(x[:, 5:6]), [(cfg.layer_name(i), 5, i) for i in (2, 3)])    # the session is intact
+            ref = om.block_forward(3, om.block_forward(2, x[0, 5:6].float().numpy(), 5, oc), 5, oc)
+            assert np.array_equal(bits_to_f32(y.to_numpy_bits(), "bf16")[0], ref)
+            c.goodbye()                                                                           # clears this session's cache
+            y0 = c.forward_mut(raw(x[:, :1]), 0, 2)
+            oc.clear()
+            assert np.array_equal(bits_to_f32(y0.to_numpy_bits(), "bf16")[0], om.block_forward(2, x[0, :1].float().numpy(), 0, oc))
+            c.close()
+        assert p.wait(20) == 0
+    finally:
+        if p.poll() is None:
+            p.kill()
+            p.wait(5)

@@ -293,3 +293,48 @@ def test_prefused_checkpoints_split_into_views_and_give_the_same_model(tmp_path)
     bad[f"{n}.mlp.gate_up_proj.weight"] = bad[f"{n}.mlp.gate_up_proj.weight"][:-2].contiguous()
     with pytest.raises(ValueError, match="shape mismatch for model.layers.1.mlp.gate_up_proj.weight"):
         block_tensors(bad, fused, n)
+
+
+@pytest.mark.parametrize("flavour", ["llama", "qwen2_bias", "qwen3_qknorm", "phi_fused"])
+def test_block_load_receives_the_fourteen_tensors_in_header_order(monkeypatch, flavour):
+    """B200Transformer.load hands cake_b200_block_load (include/cake_b200.h) q,k,v,o,gate,up,down,ln1,ln2, three biases
+    and two QK-norm weights — in that order, null where the config does not use them, and pointing at exactly the
+    checkpoint's bytes (row views for pre-fused checkpoints).  A recording stand-in for the library reads the memory
+    behind every pointer; no GPU involved."""
+    import ctypes
+    from cake_b200 import model as M
+    from cake_b200.synth import layer_tensor_shapes
+    kw = dict(num_hidden_layers=2, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+              num_key_value_heads=2, head_dim=32)
+    extra = {"llama": {}, "qwen2_bias": dict(use_qkv_bias=True), "qwen3_qknorm": dict(use_qk_norm=True),
+             "phi_fused": dict(fused_qkv_proj=True, fused_gate_up_proj=True, partial_rotary_factor=0.5)}[flavour]
+    cfg = medium_config(**kw, **extra)
+    plain = medium_config(**kw, **{k: v for k, v in extra.items() if not k.startswith("fused")})
+    sd, sd_plain = checkpoint(cfg, "bf16", seed=77), checkpoint(plain, "bf16", seed=77)
+    seen = {}
+
+    class FakeLib:
+        def cake_b200_block_load(self, ctx_h, layer, *rest):
+            seen["layer"], seen["ptrs"] = layer, list(rest[:14])
+            return 0
+
+    monkeypatch.setattr(M, "lib", lambda: FakeLib())
+
+    class Ctx:
+        config, var_builder, torch_dtype, h, _children = cfg, sd, torch.bfloat16, ctypes.c_void_p(1), []
+
+    name = cfg.layer_name(1)
+    blk = M.B200Transformer.load(name, Ctx)
+    assert blk.layer_name() == name and seen["layer"] == 1 and len(Ctx._children) == 1
+    order = ["self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_attn.v_proj.weight", "self_attn.o_proj.weight",
+             "mlp.gate_proj.weight", "mlp.up_proj.weight", "mlp.down_proj.weight", "input_layernorm.weight",
+             "post_attention_layernorm.weight", "self_attn.q_proj.bias", "self_attn.k_proj.bias", "self_attn.v_proj.bias",
+             "self_attn.q_norm.weight", "self_attn.k_norm.weight"]
+    shapes = layer_tensor_shapes(plain)
+    for short, p in zip(order, seen["ptrs"]):
+        if short not in shapes:
+            assert not p, f"{short} must be null for {flavour}"
+            continue
+        want = sd_plain[f"{name}.{short}"].contiguous().view(torch.uint8).numpy().tobytes()
+        assert p and ctypes.string_at(p, len(want)) == want, short
+    blk.h = None  # nothing to free in the stand-in

@@ -470,3 +470,72 @@ def test_gpu_master_with_tcp_worker_generates_the_same_tokens(tmp_path):
         if mctx is not None:
             mctx.close()
         wctx.close()
+
+
+def test_python_b200_backend_over_the_emulated_library(tmp_path, monkeypatch):
+    """`B200Backend` / `_B200Session` (what a B200 worker runs behind the wire: one Cache per connection, forwards under
+    a lock, `cake_b200_forward_batch_host` marshalling, error reporting) driven on the CPU: the C ABI is provided by the
+    oracle-backed emulation of tests/fake_b200, so the activations must equal the oracle's block outputs bit for bit."""
+    import ctypes
+    from cake_b200 import capi
+    from cake_b200.config import CConfig
+    from cake_b200.model import B200Transformer, Cache
+    from cake_b200.wire import B200Backend
+    from oracle import oracle as O
+    from tests.fake_b200.make_fake import build as build_fake
+    from tests.util import bits_to_f32, checkpoint, f32_to_bits, medium_config, rand_x
+    so = build_fake(str(tmp_path), oracle=True)
+    monkeypatch.setattr(capi, "SO_PATH", so)
+    monkeypatch.setattr(capi, "_lib", None)
+    try:
+        import torch
+        cfg = medium_config(num_hidden_layers=4, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+                            num_key_value_heads=2, head_dim=32)
+        sd = checkpoint(cfg, "bf16", seed=29)
+
+        class Ctx:  # the attributes of model.Context that the worker side touches; no CUDA
+            config, var_builder, dtype, torch_dtype, device, max_seq, _children = cfg, sd, "bf16", torch.bfloat16, 0, 32, []
+
+            def __init__(self):
+                self.ccfg = CConfig.from_config(cfg, "bf16", 32)
+                self.h = ctypes.c_void_p()
+                capi.check(capi.lib().cake_b200_ctx_create(0, ctypes.byref(self.ccfg), ctypes.byref(self.h)))
+
+            def sync(self):
+                capi.check(capi.lib().cake_b200_sync(self.h))
+
+        ctx = Ctx()
+        ctx.cache = Cache(ctx)
+        blocks = {cfg.layer_name(i): B200Transformer.load(cfg.layer_name(i), ctx) for i in (2, 3)}
+        w = WireWorker(B200Backend(ctx, blocks)).start()
+        try:
+            om = O.OracleModel(cfg, sd, "bf16", max_seq=32)
+            x = rand_x((1, 6, cfg.hidden_size), "bf16", seed=2)
+            raw = lambda t: RawTensor.from_numpy_bits(f32_to_bits(t.float().numpy(), "bf16"), "bf16")  # noqa: E731
+            clients = [WireClient(w.address, cfg.layer_name(2), timeout=30), WireClient(w.address, cfg.layer_name(3), timeout=30)]
+            for c in clients:   # each connection has its own cache: both accept the prefill at position 0
+                assert c.info.dtype == "BF16" and c.info.device == "cuda"
+                oc = om.new_cache()
+                y = c.forward_batch(raw(x[:, :5]), [(cfg.layer_name(i), 0, i) for i in (2, 3)])
+                ref = om.block_forward(3, om.block_forward(2, x[0, :5].float().numpy(), 0, oc), 0, oc)
+                assert y.shape == [1, 5, cfg.hidden_size] and np.array_equal(bits_to_f32(y.to_numpy_bits(), "bf16")[0], ref)
+                with pytest.raises(RuntimeError, match=r"forward pass failed for layer model.layers.2 \(block_idx=2\).*cache length"):
+                    c.forward_batch(raw(x[:, 5:6]), [(cfg.layer_name(2), 9, 2)])
+                with pytest.raises(RuntimeError, match="could not find layer model.layers.0"):
+                    c.forward_batch(raw(x[:, 5:6]), [(cfg.layer_name(0), 5, 0)])
+                with pytest.raises(RuntimeError, match="activation dtype f16 != model dtype bf16"):
+                    c.forward_batch(RawTensor(raw(x[:, 5:6]).data, DTYPE_TAGS["f16"], [1, 1, cfg.hidden_size]), [(cfg.layer_name(2), 5, 2)])
+                y = c.forward_batch(raw(x[:, 5:6]), [(cfg.layer_name(i), 5, i) for i in (2, 3)])
+                ref = om.block_forward(3, om.block_forward(2, x[0, 5:6].float().numpy(), 5, oc), 5, oc)
+                assert np.array_equal(bits_to_f32(y.to_numpy_bits(), "bf16")[0], ref)
+            for c in clients:
+                c.goodbye()
+                c.close()
+        finally:
+            w.stop()
+        for b in blocks.values():
+            b.close()
+        ctx.cache.close()
+        capi.lib().cake_b200_ctx_destroy(ctx.h)
+    finally:
+        capi._lib = None   # the next user of capi.lib() reloads the real library
