@@ -306,7 +306,9 @@ def build(out_dir: str, oracle: bool = False) -> str:
     with open(src, "w") as f:
         f.write(hand + "\n" + "\n".join(stubs) + "\n")
     so = os.path.join(out_dir, "libcake_b200.so")
-    cmd = ["/usr/bin/gcc", "-shared", "-fPIC", "-O1", "-w", "-I", os.path.join(ROOT, "include"), "-o", so, src]
+    # -Bsymbolic: calls between the stand-in's own entry points must not be interposed by a real libcake_b200.so that the
+    # same process loaded earlier with RTLD_GLOBAL (pytest runs everything in one interpreter)
+    cmd = ["/usr/bin/gcc", "-shared", "-fPIC", "-O1", "-w", "-Wl,-Bsymbolic", "-I", os.path.join(ROOT, "include"), "-o", so, src]
     if oracle:
         sys.path.insert(0, ROOT)
         from oracle import oracle as O
