@@ -111,7 +111,8 @@ uint32_t ora_argmax(const float *logits, int V);
 void ora_repeat_penalty(float *logits, int V, float penalty, const uint32_t *ctx, int n, int dt);
 float ora_round(float f, int dt);
 
-struct cake_b200_ctx { cake_b200_config cfg; ora_config oc; ora_model *m; int n_blocks_dec; int dec_idx[512]; cake_b200_cache *dec_cache; int pos; float *last_logits; };
+struct cake_b200_ctx { cake_b200_config cfg; ora_config oc; ora_model *m; int n_blocks_dec; int dec_idx[512]; cake_b200_cache *dec_cache; int pos; float *last_logits;
+  uint32_t cur_token; uint32_t ring[4096]; unsigned long long steps; };
 struct cake_b200_block { int layer; };
 struct cake_b200_cache { cake_b200_ctx *c; ora_cache *k; int batch; int cap; };
 static __thread char g_err[256] = "";
@@ -252,7 +253,7 @@ int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *blocks, con
   for (int i = 0; i < n; i++) { c->dec_idx[i] = idx[i]; g_dec_blocks[i] = *blocks[i]; }
   return 0;
 }
-int cake_b200_decode_begin(cake_b200_ctx *c, uint32_t first_token, int pos) { if (!c || !c->n_blocks_dec) return fail(CAKE_B200_ESTATE, "decode_build has not been called"); c->pos = pos; (void)first_token; return 0; }
+int cake_b200_decode_begin(cake_b200_ctx *c, uint32_t first_token, int pos) { if (!c || !c->n_blocks_dec) return fail(CAKE_B200_ESTATE, "decode_build has not been called"); c->pos = pos; c->cur_token = first_token; return 0; }
 int cake_b200_decode_step_host(cake_b200_ctx *c, uint32_t token_in, uint32_t *token_out) {
   if (!c || !c->n_blocks_dec || !token_out) return fail(CAKE_B200_ESTATE, "decode_build has not been called");
   if (token_in >= (uint32_t)c->cfg.vocab) token_in = 0;
@@ -266,9 +267,27 @@ int cake_b200_decode_step_host(cake_b200_ctx *c, uint32_t token_in, uint32_t *to
     ora_logits(c->m, x, 1, c->last_logits);
     *token_out = ora_argmax(c->last_logits, c->cfg.vocab);
     c->pos++;
+    c->cur_token = *token_out;
+    c->ring[c->steps++ % 4096] = *token_out;
   }
   free(x);
   return rc;
+}
+/* the device-resident loop: every step feeds the previous step's token back */
+int cake_b200_decode_run(cake_b200_ctx *c, int n_steps) {
+  if (!c || !c->n_blocks_dec) return fail(CAKE_B200_ESTATE, "decode_build has not been called");
+  for (int i = 0; i < n_steps; i++) { uint32_t t; int rc = cake_b200_decode_step_host(c, c->cur_token, &t); if (rc) return rc; }
+  return 0;
+}
+int cake_b200_decode_tokens(cake_b200_ctx *c, uint32_t *out, int n) {
+  if (!c || !out || n < 0 || (unsigned long long)n > c->steps || n > 4096) return fail(CAKE_B200_EINVAL, "bad decode_tokens arguments");
+  for (int i = 0; i < n; i++) out[i] = c->ring[(c->steps - n + i) % 4096];
+  return 0;
+}
+int cake_b200_decode_logits(cake_b200_ctx *c, void *logits_host, size_t bytes) {
+  if (!c || !logits_host || !c->last_logits || bytes < (size_t)c->cfg.vocab * 2) return fail(CAKE_B200_EINVAL, "bad decode_logits arguments");
+  from_f32(c, c->last_logits, logits_host, (size_t)c->cfg.vocab);
+  return 0;
 }
 '''
 
@@ -276,7 +295,7 @@ DONE_ORACLE = {"cake_b200_last_error", "cake_b200_version", "cake_b200_ctx_creat
                "cake_b200_dev_free", "cake_b200_head_load", "cake_b200_block_load", "cake_b200_block_free", "cake_b200_block_layer",
                "cake_b200_cache_create", "cake_b200_cache_clear", "cake_b200_cache_free", "cake_b200_cache_len", "cake_b200_forward_batch",
                "cake_b200_forward_batch_host", "cake_b200_embed", "cake_b200_logits", "cake_b200_repeat_penalty_argmax", "cake_b200_decode_build",
-               "cake_b200_decode_begin", "cake_b200_decode_step_host"}
+               "cake_b200_decode_begin", "cake_b200_decode_step_host", "cake_b200_decode_run", "cake_b200_decode_tokens", "cake_b200_decode_logits"}
 
 DONE = {"cake_b200_last_error", "cake_b200_version", "cake_b200_ctx_create", "cake_b200_ctx_destroy", "cake_b200_head_load",
         "cake_b200_block_load", "cake_b200_block_free", "cake_b200_cache_create", "cake_b200_cache_free"}

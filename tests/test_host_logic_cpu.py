@@ -60,6 +60,13 @@ def test_master_generate_text_equals_the_oracle(tmp_path, monkeypatch, flavour, 
                 check(lib().cake_b200_decode_step_host(ctx.h, toks[-1], byref(nxt)))
                 toks.append(int(nxt.value))
             assert toks == _oracle_tokens(cfg, sd, prompt, 6)
+            # and the device-resident loop API (decode_begin / decode_run / decode_tokens) behind TextModelBase.decode_greedy
+            model.prepare_prompt(prompt)
+            first = model.next_token(0).id
+            model.decode_build()
+            assert [first] + model.decode_greedy(first, 5) == _oracle_tokens(cfg, sd, prompt, 6)
+            # prepare_prompt does not reset `generated` (text_model.rs:371-395; only reset() does, :497-502): 1 + (1 + 5)
+            assert model.index_pos == len(prompt) + 5 and model.generated == 7
     finally:
         ctx.close()
 
