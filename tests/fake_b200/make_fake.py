@@ -114,7 +114,7 @@ float ora_round(float f, int dt);
 struct cake_b200_ctx { cake_b200_config cfg; ora_config oc; ora_model *m; int n_blocks_dec; int dec_idx[512]; cake_b200_cache *dec_cache; int pos; float *last_logits;
   uint32_t cur_token; uint32_t ring[4096]; unsigned long long steps; };
 struct cake_b200_block { int layer; };
-struct cake_b200_cache { cake_b200_ctx *c; ora_cache *k; int batch; int cap; };
+struct cake_b200_cache { cake_b200_ctx *c; ora_cache *k; ora_cache **rows; int batch; int cap; };  /* k == rows[0] */
 static __thread char g_err[256] = "";
 static int fail(int code, const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg); return code; }
 const char *cake_b200_last_error(void) { return g_err; }
@@ -170,23 +170,41 @@ int cake_b200_cache_create(cake_b200_ctx *c, int batch, int max_seq, cake_b200_c
   if (!c || !out || batch < 1 || max_seq < 1) return fail(CAKE_B200_EINVAL, "bad cache arguments");
   if (max_seq > c->cfg.max_seq) return fail(CAKE_B200_EINVAL, "cache max_seq exceeds config max_seq");
   cake_b200_cache *k = (cake_b200_cache *)calloc(1, sizeof *k);
-  k->c = c; k->batch = batch; k->cap = max_seq; k->k = ora_cache_create(&c->oc, max_seq);
+  k->c = c; k->batch = batch; k->cap = max_seq;
+  k->rows = (ora_cache **)calloc((size_t)batch, sizeof *k->rows);
+  for (int b = 0; b < batch; b++) k->rows[b] = ora_cache_create(&c->oc, max_seq);
+  k->k = k->rows[0];
   *out = k;
   return 0;
 }
-int cake_b200_cache_clear(cake_b200_cache *k) { if (!k) return fail(CAKE_B200_EINVAL, "null argument"); ora_cache_clear(k->k); return 0; }
-void cake_b200_cache_free(cake_b200_cache *k) { if (k) { ora_cache_free(k->k); free(k); } }
+int cake_b200_cache_clear(cake_b200_cache *k) { if (!k) return fail(CAKE_B200_EINVAL, "null argument"); for (int b = 0; b < k->batch; b++) ora_cache_clear(k->rows[b]); return 0; }
+void cake_b200_cache_free(cake_b200_cache *k) { if (k) { for (int b = 0; b < k->batch; b++) ora_cache_free(k->rows[b]); free(k->rows); free(k); } }
+float *ora_cache_k(ora_cache *, int);
+float *ora_cache_v(ora_cache *, int);
+int cake_b200_cache_read(cake_b200_cache *k, int idx, int which, void *out_host, size_t bytes) {
+  if (!k || !out_host) return fail(CAKE_B200_EINVAL, "null argument");
+  if (idx < 0 || idx >= k->c->cfg.n_layers) return fail(CAKE_B200_EINVAL, "layer has no cache");
+  const int len = ora_cache_len(k->k, idx), hd = k->c->cfg.head_dim, nkv = k->c->cfg.n_kv_heads;
+  if (bytes < (size_t)k->batch * nkv * len * hd * 2) return fail(CAKE_B200_EINVAL, "cache_read needs more bytes");
+  uint16_t *dst = (uint16_t *)out_host;
+  for (int b = 0; b < k->batch; b++) {
+    const float *src = which ? ora_cache_v(k->rows[b], idx) : ora_cache_k(k->rows[b], idx);   /* (n_kv, cap, hd) */
+    for (int h = 0; h < nkv; h++) { from_f32(k->c, src + (size_t)h * k->cap * hd, dst, (size_t)len * hd); dst += (size_t)len * hd; }
+  }
+  return 0;
+}
 int cake_b200_cache_len(const cake_b200_cache *k, int i) { return (!k || i < 0 || i >= k->c->cfg.n_layers) ? -1 : ora_cache_len(k->k, i); }
 
-static int forward_f32(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *idx, int n, cake_b200_cache *kc, float *x, int seq, int pos) {
+static int forward_f32(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *idx, int n, cake_b200_cache *kc, float *x, int seq, int pos, int row) {
+  ora_cache *oc = kc->rows[row];
   if (pos + seq > kc->cap) return fail(CAKE_B200_ESTATE, "index_pos + seq exceeds cache capacity");
   for (int i = 0; i < n; i++) {
     if (idx[i] < 0 || idx[i] >= c->cfg.n_layers) return fail(CAKE_B200_EINVAL, "block_idx out of range");
-    if (ora_cache_len(kc->k, idx[i]) != pos) { snprintf(g_err, sizeof g_err, "block %d: index_pos %d != cache length %d", idx[i], pos, ora_cache_len(kc->k, idx[i])); return CAKE_B200_ESTATE; }
+    if (ora_cache_len(oc, idx[i]) != pos) { snprintf(g_err, sizeof g_err, "block %d: index_pos %d != cache length %d", idx[i], pos, ora_cache_len(oc, idx[i])); return CAKE_B200_ESTATE; }
   }
   float *tmp = (float *)malloc((size_t)seq * c->cfg.hidden * 4);
   for (int i = 0; i < n; i++) {
-    if (ora_block_forward(c->m, blocks[i]->layer, kc->k, x, seq, pos, tmp)) { free(tmp); return fail(CAKE_B200_ESTATE, "oracle block_forward failed"); }
+    if (ora_block_forward(c->m, blocks[i]->layer, oc, x, seq, pos, tmp)) { free(tmp); return fail(CAKE_B200_ESTATE, "oracle block_forward failed"); }
     memcpy(x, tmp, (size_t)seq * c->cfg.hidden * 4);
   }
   free(tmp);
@@ -195,14 +213,19 @@ static int forward_f32(cake_b200_ctx *c, cake_b200_block *const *blocks, const i
 int cake_b200_forward_batch(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *idx, int n, cake_b200_cache *kc, const void *x, void *y,
                             int batch, int seq, int pos) {
   if (!c || !blocks || !idx || !kc || !x || !y || n < 1) return fail(CAKE_B200_EINVAL, "null/empty argument");
-  if (batch != kc->batch) return fail(CAKE_B200_EINVAL, "batch != cache batch");
-  if (batch != 1) return fail(CAKE_B200_EINVAL, "the emulation handles batch 1");
+  if (batch != kc->batch) { snprintf(g_err, sizeof g_err, "batch %d != cache batch %d", batch, kc->batch); return CAKE_B200_EINVAL; }
   if (seq < 1 || pos < 0) return fail(CAKE_B200_ESTATE, "bad position");
   const size_t ne = (size_t)seq * c->cfg.hidden;
   float *f = (float *)malloc(ne * 4);
-  to_f32(c, x, f, ne);
-  int rc = forward_f32(c, blocks, idx, n, kc, f, seq, pos);
-  if (!rc) from_f32(c, f, y, ne);
+  int rc = 0;
+  for (int i = 0; i < n && !rc; i++)   /* validate every row's position before anything is appended (all rows advance together) */
+    for (int b = 0; b < batch; b++)
+      if (ora_cache_len(kc->rows[b], idx[i]) != pos) { snprintf(g_err, sizeof g_err, "block %d: index_pos %d != cache length %d", idx[i], pos, ora_cache_len(kc->rows[b], idx[i])); rc = CAKE_B200_ESTATE; break; }
+  for (int b = 0; b < batch && !rc; b++) {   /* every sequence of the batch against its own cache */
+    to_f32(c, (const uint16_t *)x + (size_t)b * ne, f, ne);
+    rc = forward_f32(c, blocks, idx, n, kc, f, seq, pos, b);
+    if (!rc) from_f32(c, f, (uint16_t *)y + (size_t)b * ne, ne);
+  }
   free(f);
   return rc;
 }
@@ -261,7 +284,7 @@ int cake_b200_decode_step_host(cake_b200_ctx *c, uint32_t token_in, uint32_t *to
   ora_embed(c->m, &token_in, 1, x);
   cake_b200_block *bl[512];
   for (int i = 0; i < c->n_blocks_dec; i++) bl[i] = &g_dec_blocks[i];
-  int rc = forward_f32(c, bl, c->dec_idx, c->n_blocks_dec, c->dec_cache, x, 1, c->pos);
+  int rc = forward_f32(c, bl, c->dec_idx, c->n_blocks_dec, c->dec_cache, x, 1, c->pos, 0);
   if (!rc) {
     if (!c->last_logits) c->last_logits = (float *)malloc((size_t)c->cfg.vocab * 4);
     ora_logits(c->m, x, 1, c->last_logits);
@@ -293,7 +316,7 @@ int cake_b200_decode_logits(cake_b200_ctx *c, void *logits_host, size_t bytes) {
 
 DONE_ORACLE = {"cake_b200_last_error", "cake_b200_version", "cake_b200_ctx_create", "cake_b200_ctx_destroy", "cake_b200_sync", "cake_b200_dev_alloc",
                "cake_b200_dev_free", "cake_b200_head_load", "cake_b200_block_load", "cake_b200_block_free", "cake_b200_block_layer",
-               "cake_b200_cache_create", "cake_b200_cache_clear", "cake_b200_cache_free", "cake_b200_cache_len", "cake_b200_forward_batch",
+               "cake_b200_cache_create", "cake_b200_cache_clear", "cake_b200_cache_free", "cake_b200_cache_len", "cake_b200_cache_read", "cake_b200_forward_batch",
                "cake_b200_forward_batch_host", "cake_b200_embed", "cake_b200_logits", "cake_b200_repeat_penalty_argmax", "cake_b200_decode_build",
                "cake_b200_decode_begin", "cake_b200_decode_step_host", "cake_b200_decode_run", "cake_b200_decode_tokens", "cake_b200_decode_logits"}
 

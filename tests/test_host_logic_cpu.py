@@ -128,3 +128,21 @@ def test_master_with_tcp_worker_split_equals_the_oracle(tmp_path, monkeypatch):
         if mctx is not None:
             mctx.close()
         wctx.close()
+
+
+SMALL = dict(hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4, num_key_value_heads=2, head_dim=32)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+def test_late_gpu_case_batched_runs_on_the_emulation(tmp_path, monkeypatch, dtype):
+    """tests/test_zz_gpu_batch.py's batched case, same code, emulated library: exact (the emulation is the oracle), which
+    shows the test's own indexing / shapes / error expectation are right before it meets a GPU."""
+    from tests import cases_late
+    use_emulation(monkeypatch, tmp_path)
+    cases_late.batched_prefill_then_decode(lambda c, s, d, m: CpuContext(c, s, d, max_seq=m), dtype, 0.0, 0.0, 0.0, **SMALL)
+
+
+def test_late_gpu_case_phi_runs_on_the_emulation(tmp_path, monkeypatch):
+    from tests import cases_late
+    use_emulation(monkeypatch, tmp_path)
+    cases_late.phi_style_block(lambda c, s, d, m: CpuContext(c, s, d, max_seq=m), "bf16", 0.0, 0.0, 0.0, **SMALL)
