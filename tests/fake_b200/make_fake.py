@@ -344,6 +344,7 @@ def build(out_dir: str, oracle: bool = False) -> str:
             else:
                 params.append(f"{a} a{i}")
         stubs.append(f"{ret} {name}({', '.join(params)}) {{ {body} }}")
+    os.makedirs(out_dir, exist_ok=True)
     src = os.path.join(out_dir, "fake_b200.c")
     with open(src, "w") as f:
         f.write(hand + "\n" + "\n".join(stubs) + "\n")
