@@ -167,3 +167,68 @@ def test_master_worker_protocol_world2_gloo():
         assert p.exitcode == 0
     assert res["master"] == (True, (1, 64, 8))
     assert res["worker"] == (5, 1)   # 5 batches served, cache cleared once by Goodbye
+
+
+# ---- the same protocol with the real block class over the emulated library -------------------------------------------
+def _run_real_blocks(rank, world, port, q, so_path):
+    """rank 0: TextModelBase whose layers 2-3 are `Client`s (GlooTransport); rank 1: `Worker` with B200Transformer blocks.
+    The C ABI behind both is the oracle-backed emulation (tests/fake_b200), contexts are tests/cpu_ctx.CpuContext."""
+    import numpy as np
+    from cake_b200 import capi
+    from cake_b200.model import B200Transformer, Master, TextModelBase
+    from tests.cpu_ctx import CpuContext
+    from tests.util import checkpoint, medium_config
+    capi.SO_PATH, capi._lib = so_path, None
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = medium_config(num_hidden_layers=4, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+                        num_key_value_heads=2, head_dim=32)
+    sd = checkpoint(cfg, "bf16", seed=23, peaked=True)
+    ctx = CpuContext(cfg, sd, "bf16", max_seq=64)
+    tr = GlooTransport()
+    try:
+        if rank == 1:
+            w = Worker(ctx, 1, world, block_cls=B200Transformer, transport=tr)
+            w.serve()
+            q.put(("worker", w.served, ctx.cache.len(2)))
+        else:
+            ctx.topology = box_topology(cfg, world)
+            model = TextModelBase.load(ctx, make_remote=lambda wk, name, c: Client(wk, name, c, transport=tr))
+            assert [b.ident() for b in model.blocks] == ["local", "local", "gpu1", "gpu1"]
+            prompt = np.random.default_rng(9).integers(0, cfg.vocab_size - 1, 7).tolist()
+            toks = Master(model).generate_text(prompt, 6)["tokens"]
+            dist.broadcast_object_list([("goodbye",)], src=0)
+            ctx.cache.clear()
+            toks2 = Master(model).generate_text(prompt[:4], 3)["tokens"]
+            dist.broadcast_object_list([("shutdown",)], src=0)
+            q.put(("master", toks, toks2, prompt))
+    finally:
+        dist.destroy_process_group()
+        ctx.close()
+
+
+def test_sharded_master_and_worker_with_real_blocks_over_gloo(tmp_path):
+    from oracle import oracle as O
+    from tests.fake_b200.make_fake import build as build_fake
+    from tests.util import checkpoint, medium_config
+    so = build_fake(str(tmp_path), oracle=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_run_real_blocks, args=(r, 2, port, q, so)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict()
+    for _ in range(2):
+        item = q.get(timeout=180)
+        res[item[0]] = item[1:]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    toks, toks2, prompt = res["master"]
+    cfg = medium_config(num_hidden_layers=4, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+                        num_key_value_heads=2, head_dim=32)
+    sd = checkpoint(cfg, "bf16", seed=23, peaked=True)
+    om = O.OracleModel(cfg, sd, "bf16", max_seq=64)
+    assert toks == list(om.generate(prompt, 6)[0]) and toks2 == list(om.generate(prompt[:4], 3)[0])
+    assert res["worker"] == (6 + 3, 4 + 2)   # one batch per forward; the worker's cache holds the second prompt: 4 + 2 fed-back tokens
