@@ -51,3 +51,35 @@ def test_cpp_host_gpu_cases(emulated):
         d = emulated / f"case{int(sharded)}"
         d.mkdir()
         test_cpp_host.test_cake_run_tokens_equal_python_master(d, sharded)
+
+
+def _expand(fn):
+    """The parameter sets of a pytest-parametrized test function, as a list of kwargs."""
+    import inspect
+    combos = [dict()]
+    for m in [m for m in getattr(fn, "pytestmark", []) if m.name == "parametrize"]:
+        names = [n.strip() for n in m.args[0].split(",")]
+        combos = [dict(c, **dict(zip(names, v if len(names) > 1 else [v]))) for c in combos for v in m.args[1]]
+    return combos, "monkeypatch" in inspect.signature(fn).parameters
+
+
+def test_the_hardware_validated_parity_suite_still_runs(emulated):
+    """tests/test_gpu_parity.py (run on a B200 in round 1) executed over the emulation: a regression net for the host
+    code those tests go through (loading, forward_batch plumbing, caches, the decode loop API, repeat penalty, error
+    paths) whenever it is refactored without a GPU at hand.  Numerics are exact here by construction."""
+    import inspect
+    from tests import test_gpu_parity as T
+    ran = 0
+    for name, fn in inspect.getmembers(T, inspect.isfunction):
+        if not name.startswith("test_"):
+            continue
+        combos, wants_mp = _expand(fn)
+        for kw in combos:
+            mp = pytest.MonkeyPatch() if wants_mp else None
+            try:
+                fn(**(dict(kw, monkeypatch=mp) if wants_mp else kw))
+            finally:
+                if mp is not None:
+                    mp.undo()
+            ran += 1
+    assert ran >= 20
