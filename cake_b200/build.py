@@ -56,6 +56,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO
 
 
+def build_trace() -> str:
+    """Profiling build: the same library with -DMK_TRACE=1 (per-CTA phase records inside decode_mega_kernel), written
+    to libcake_b200_trace.so next to the product library.  Used by bench_tools/mega_trace.py only."""
+    out = os.path.join(HERE, "libcake_b200_trace.so")
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in sources()):
+        return out
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DMK_TRACE=1",
+                           "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
+                           "-I", _nccl_include(), "-I", os.path.join(ROOT, "include"), "-o", out, SRC, "-ldl"])
+    return out
+
+
 def build_host(force: bool = False) -> str:
     """The C++ host side (cake_b200/host/cake_host.hpp, cake_wire.hpp) + its drivers `cake_run` and `cake_worker`,
     linked against the C ABI."""

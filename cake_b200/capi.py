@@ -54,6 +54,7 @@ SYMBOLS = [
     ("cake_b200_decode_step_host", _I, [_VP, c_uint32, POINTER(c_uint32)]),
     ("cake_b200_decode_logits", _I, [_VP, _VP, c_size_t]),
     ("cake_b200_bench_kernel", _I, [_VP, POINTER(_VP), POINTER(_I), _I, _VP, _I, _I, POINTER(c_float)]),
+    ("cake_b200_decode_trace", _I, [_VP, POINTER(c_uint64), _I]),
 ]
 
 

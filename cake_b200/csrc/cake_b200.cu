@@ -9,6 +9,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -135,12 +138,19 @@ struct cake_b200_ctx {
   MkLayer *mk_tab_dev = nullptr, *mk_tab_host = nullptr, *g_tab_dev = nullptr;
   std::vector<const void *> mk_sig;
   unsigned long long *trace = nullptr;  // CAKE_B200_MEGA_TRACE=1
+  unsigned long long *step_trace = nullptr;  // per-step entry / input-acquired / exit stamps of the decode kernels
   unsigned *tickets = nullptr;          // per-phase work-claim counters of the megakernel
   // ring hand-off over NVLink peer memory: inbox = {counter (u64), pad, x[hidden]} in our memory, written by rank-1
   unsigned char *inbox = nullptr, *peer_inbox = nullptr;
   unsigned long long *ring_seq = nullptr;
 };
 constexpr int TOKEN_RING = 1 << 16;
+
+// Live contexts: a cache may outlive its ctx (handles are freed in any order by foreign hosts), so cache_free only
+// touches ctx state when the ctx is still registered here.
+static std::mutex g_live_mu;
+static std::set<cake_b200_ctx *> g_live_ctx;
+static std::atomic<uint64_t> g_cache_gen{1};
 
 struct cake_b200_block {
   cake_b200_ctx *ctx;
@@ -154,6 +164,7 @@ struct cake_b200_cache {
   cake_b200_ctx *ctx;
   int batch, cap;
   int device = 0;
+  uint64_t gen = 0;  // unique per cache object: part of the megakernel layer-table signature (addresses can be reused)
   std::vector<void *> k, v;
   std::vector<int> len;
   int *d_pos = nullptr;
@@ -380,6 +391,8 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
   CU(cudaMalloc(&c->tickets, sizeof(unsigned) * (4 * MK_MAX_LAYERS + 4)));
   CU(cudaMalloc(&c->ring_seq, 8));
   CU(cudaMemset(c->ring_seq, 0, 8));
+  CU(cudaMalloc(&c->step_trace, sizeof(unsigned long long) * MK_STEP_RING * 8));
+  CU(cudaMemset(c->step_trace, 0, sizeof(unsigned long long) * MK_STEP_RING * 8));
   CU(cudaMalloc(&c->mk_tab_dev, sizeof(MkLayer) * MK_MAX_LAYERS));
   CU(cudaMalloc(&c->g_tab_dev, sizeof(MkLayer) * MK_MAX_LAYERS));
   CU(cudaMallocHost(&c->mk_tab_host, sizeof(MkLayer) * MK_MAX_LAYERS));
@@ -388,9 +401,13 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
     c->use_mega = !(e && e[0] == '1');
     const char *t = getenv("CAKE_B200_MEGA_TRACE");
     if (t && t[0] == '1') {
-      CU(cudaMalloc(&c->trace, 8 * 4096));
-      CU(cudaMemset(c->trace, 0, 8 * 4096));
+      CU(cudaMalloc(&c->trace, 8 * (size_t)MK_TRACE_U64));
+      CU(cudaMemset(c->trace, 0, 8 * (size_t)MK_TRACE_U64));
     }
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    g_live_ctx.insert(c);
   }
   *out = c;
   return CAKE_B200_OK;
@@ -398,6 +415,10 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
 
 extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
   if (!c) return;
+  {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    g_live_ctx.erase(c);
+  }
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   if (c->gexec) cudaGraphExecDestroy(c->gexec);
@@ -407,7 +428,7 @@ extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
   void *bufs[] = {c->cos_t, c->sin_t, c->embed, c->ln_f, c->xa, c->xb, c->qkv, c->y, c->mm, c->logits, c->ws_ml,
                   c->ws_acc, c->part_val, c->part_idx, c->d_step, c->attn_counters, c->argmax_counter, c->d_token,
                   c->token_ring, c->d_ids, c->d_pen, c->pf_h, c->pf_qkv, c->pf_y, c->pf_x1, c->pf_gu, c->pf_mm, c->io_x,
-                  c->gbar, c->mk_tab_dev, c->g_tab_dev, c->tickets, c->ring_seq, c->inbox};
+                  c->gbar, c->mk_tab_dev, c->g_tab_dev, c->tickets, c->ring_seq, c->inbox, c->step_trace, c->trace};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (c->lm_head && c->lm_head != c->embed) cudaFree(c->lm_head);
@@ -514,6 +535,7 @@ extern "C" int cake_b200_cache_create(cake_b200_ctx *c, int batch, int max_seq, 
   if (max_seq > c->cfg.max_seq) return fail(CAKE_B200_EINVAL, "cache max_seq %d exceeds config max_seq %d (RoPE table rows)", max_seq, c->cfg.max_seq);
   CU(cudaSetDevice(c->device));
   auto *k = new cake_b200_cache{c, batch, max_seq, c->device};
+  k->gen = g_cache_gen.fetch_add(1);
   k->k.assign(c->cfg.n_layers, nullptr);
   k->v.assign(c->cfg.n_layers, nullptr);
   k->len.assign(c->cfg.n_layers, 0);
@@ -544,6 +566,20 @@ extern "C" int cake_b200_cache_clear(cake_b200_cache *k) {
 extern "C" void cake_b200_cache_free(cake_b200_cache *k) {
   if (!k) return;
   cudaSetDevice(k->device);
+  {  // drop everything in the ctx that points into this cache: the cached layer table and the decode graph
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    if (g_live_ctx.count(k->ctx)) {
+      cake_b200_ctx *c = k->ctx;
+      cudaStreamSynchronize(c->stream);
+      c->mk_sig.clear();
+      if (c->g_cache == k) {
+        if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
+        if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
+        c->g_cache = nullptr;
+        c->g_block_idx.clear();
+      }
+    }
+  }
   for (void *p : k->k)
     if (p) cudaFree(p);
   for (void *p : k->v)
@@ -732,6 +768,8 @@ static int plan_mega(cake_b200_ctx *c, cake_b200_cache *kc, bool with_head, MkPl
   a.ln_f = c->ln_f; a.lm_head = c->lm_head; a.logits = c->logits; a.part_val = c->part_val; a.part_idx = c->part_idx;
   a.argmax_counter = c->argmax_counter; a.token_out = c->d_token; a.token_ring = nullptr; a.ring_cap = TOKEN_RING;
   a.trace = c->trace;
+  a.step_trace = c->step_trace;
+  a.trace_tag = 0;
   int ns = MK_MAX_STAGES;
   const size_t limit = 227 * 1024 - 4096;  // the kernel also has ~2.2 KB of static shared memory
   while (ns > 2 && mk_smem_bytes(a.max_k, pf, mg, ns, c->es) > limit) ns--;
@@ -788,7 +826,9 @@ static int enqueue_mega_layers(cake_b200_ctx *c, cake_b200_block *const *blocks,
                                cake_b200_cache *kc, const void *x_in, void *x_out) {
   if (n > MK_MAX_LAYERS) return fail(CAKE_B200_EINVAL, "more than %d blocks in one call", MK_MAX_LAYERS);
   std::vector<const void *> sig;
-  for (int i = 0; i < n; i++) { sig.push_back(blocks[i]); sig.push_back(kc->k[block_idx[i]]); }
+  sig.push_back(kc);
+  sig.push_back(reinterpret_cast<const void *>((uintptr_t)kc->gen));
+  for (int i = 0; i < n; i++) { sig.push_back(blocks[i]); sig.push_back(kc->k[block_idx[i]]); sig.push_back(kc->v[block_idx[i]]); }
   if (sig != c->mk_sig) {  // (re)build the layer table; rare
     CU(cudaStreamSynchronize(c->stream));
     fill_mk_table(c->mk_tab_host, blocks, block_idx, n, kc);
@@ -1014,7 +1054,11 @@ extern "C" int cake_b200_head_load(cake_b200_ctx *c, const void *embed, const vo
 extern "C" int cake_b200_embed(cake_b200_ctx *c, const uint32_t *ids_host, int batch, int seq, void *x_dev) {
   if (!c || !ids_host || !x_dev || !c->embed) return fail(CAKE_B200_EINVAL, "null argument or head not loaded");
   CU(cudaSetDevice(c->device));
+  if (batch < 1 || seq < 1) return fail(CAKE_B200_EINVAL, "embed: batch and seq must be >= 1");
   const size_t n = (size_t)batch * seq;
+  for (size_t i = 0; i < n; i++)  // index_select on an out-of-range id is an error in the reference (backends/mod.rs:513-528)
+    if (ids_host[i] >= (uint32_t)c->cfg.vocab)
+      return fail(CAKE_B200_EINVAL, "token id %u at %zu out of range (vocab %d)", ids_host[i], i, c->cfg.vocab);
   if (n > c->d_ids_cap) {
     CU(cudaStreamSynchronize(c->stream));
     if (c->d_ids) cudaFree(c->d_ids);
@@ -1202,7 +1246,7 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
           MkPlan h;
           RC(plan_mega(c, kc, true, &h));
           h.a.layers = c->g_tab_dev; h.a.n_layers = 0; h.a.x_in = p2p ? inbox_x : c->xa; h.a.x_out = c->xa;
-          h.a.has_head = 1; h.a.advance = 1; h.a.token_ring = c->token_ring;
+          h.a.has_head = 1; h.a.advance = 1; h.a.token_ring = c->token_ring; h.a.trace_tag = 1;
           if (p2p) { h.a.inbox_ctr = inbox_ctr; h.a.ring_seq = c->ring_seq; }
           RC(launch_mega(c, h));
         }
@@ -1261,6 +1305,8 @@ extern "C" int cake_b200_decode_begin(cake_b200_ctx *c, uint32_t first_token, in
     if (kc->len[l] != index_pos)
       return fail(CAKE_B200_ESTATE, "block %d: index_pos %d != cache length %d", l, index_pos, kc->len[l]);
   if (index_pos >= kc->cap) return fail(CAKE_B200_ESTATE, "cache full");
+  if (c->g_rank == 0 && first_token >= (uint32_t)c->cfg.vocab)  // candle's index_select fails on an out-of-range id (text_model.rs:271)
+    return fail(CAKE_B200_EINVAL, "token id %u out of range (vocab %d)", first_token, c->cfg.vocab);
   set_int_kernel<<<1, 1, 0, c->stream>>>(kc->d_pos, index_pos);
   set_int_kernel<<<1, 1, 0, c->stream>>>(c->d_step, 0);
   set_u32_kernel<<<1, 1, 0, c->stream>>>(c->d_token, first_token);
@@ -1297,6 +1343,7 @@ extern "C" int cake_b200_decode_tokens(cake_b200_ctx *c, uint32_t *out_host, int
 extern "C" int cake_b200_decode_step_host(cake_b200_ctx *c, uint32_t token_in, uint32_t *token_out) {
   if (!c || !c->gexec || !token_out) return fail(CAKE_B200_ESTATE, "decode_build has not been called");
   CU(cudaSetDevice(c->device));
+  if (token_in >= (uint32_t)c->cfg.vocab) return fail(CAKE_B200_EINVAL, "token id %u out of range (vocab %d)", token_in, c->cfg.vocab);
   c->h_pin[32] = token_in;
   CU(cudaMemcpyAsync(c->d_token, c->h_pin + 32, 4, cudaMemcpyHostToDevice, c->stream));
   RC(cake_b200_decode_run(c, 1));
@@ -1357,10 +1404,24 @@ extern "C" int cake_b200_bench_kernel(cake_b200_ctx *c, cake_b200_block *const *
   return CAKE_B200_OK;
 }
 
+extern "C" int cake_b200_decode_trace(cake_b200_ctx *c, uint64_t *out_host, int n_steps) {
+  if (!c || !out_host || n_steps < 0 || n_steps > MK_STEP_RING || n_steps > c->steps_done)
+    return fail(CAKE_B200_EINVAL, "bad decode_trace arguments (at most %d of the steps since decode_begin)", MK_STEP_RING);
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  std::vector<unsigned long long> ring((size_t)MK_STEP_RING * 8);
+  CU(cudaMemcpy(ring.data(), c->step_trace, ring.size() * 8, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n_steps; i++) {
+    const size_t slot = (size_t)((c->steps_done - n_steps + i) % MK_STEP_RING) * 8;
+    for (int j = 0; j < 8; j++) out_host[(size_t)i * 8 + j] = ring[slot + j];
+  }
+  return CAKE_B200_OK;
+}
+
 /* profiling aid (not in the public header): copies the megakernel's phase-boundary %globaltimer stamps of
  * the last launch (CTA 0) to `out`; needs CAKE_B200_MEGA_TRACE=1 at ctx creation. */
 extern "C" int cake_b200_debug_trace(cake_b200_ctx *c, unsigned long long *out, int n) {
-  if (!c || !c->trace || n > 4096) return fail(CAKE_B200_ESTATE, "tracing is off (CAKE_B200_MEGA_TRACE=1)");
+  if (!c || !c->trace || n > MK_TRACE_U64) return fail(CAKE_B200_ESTATE, "tracing is off (CAKE_B200_MEGA_TRACE=1)");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaMemcpy(out, c->trace, (size_t)n * 8, cudaMemcpyDeviceToHost));

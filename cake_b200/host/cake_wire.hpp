@@ -31,6 +31,8 @@
 #include <stdexcept>
 #include <string>
 #include <tuple>
+#include <list>
+#include <memory>
 #include <vector>
 
 namespace cake_wire {
@@ -471,24 +473,39 @@ class WireWorker {  // worker.rs:79-597; one thread per master connection (the r
   // Accept loop (worker.rs:577-597): one thread per connection.  max_connections < 0: forever; otherwise return once
   // that many connections have been accepted and have ended.
   void serve(int max_connections = -1) {
-    std::vector<std::thread> threads;
+    // Each connection thread raises its `done` flag as its last action; the accept loop only ever joins threads
+    // whose flag is up, so a live (persistent) master connection is never waited on from here.
+    struct Conn {
+      std::thread th;
+      std::shared_ptr<std::atomic<bool>> done;
+    };
+    std::list<Conn> conns;
+    auto reap = [&conns]() {
+      for (auto it = conns.begin(); it != conns.end();) {
+        if (it->done->load(std::memory_order_acquire)) {
+          it->th.join();
+          it = conns.erase(it);
+        } else {
+          ++it;
+        }
+      }
+    };
     for (int n = 0; max_connections < 0 || n < max_connections; n++) {
       int fd = ::accept(lfd_, nullptr, nullptr);
       if (fd < 0) break;
-      threads.emplace_back([this, fd]() {
+      auto done = std::make_shared<std::atomic<bool>>(false);
+      conns.push_back(Conn{std::thread([this, fd, done]() {
         try {
           handle_master_client(fd);
         } catch (const std::exception &e) {
           fprintf(stderr, "[worker] connection ended: %s\n", e.what());
         }
         ::close(fd);
-      });
-      if (max_connections < 0 && threads.size() > 256) {  // reap finished threads now and then
-        for (auto &t : threads) t.join();
-        threads.clear();
-      }
+        done->store(true, std::memory_order_release);
+      }), done});
+      if (conns.size() > 64) reap();  // finished connections only
     }
-    for (auto &t : threads) t.join();
+    for (auto &c : conns) c.th.join();
   }
 };
 

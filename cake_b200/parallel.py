@@ -129,6 +129,10 @@ class GlooTransport:
         dist.recv(y, peer)
 
 
+class WorkerError(RuntimeError):
+    """Message::WorkerError (message.rs:240-247) surfaced on the master."""
+
+
 class Client(Forwarder):
     """A block that lives on another GPU (client.rs:13).  forward_batch ships the activation to the
     worker rank and receives the result — NCCL send/recv on the ctx stream, no host copy."""
@@ -136,6 +140,9 @@ class Client(Forwarder):
     def __init__(self, worker: str, name: str, ctx, transport=None):
         self.worker, self.name, self.ctx, self.peer = worker, name, ctx, rank_of(worker)
         self.transport = transport or NcclTransport(ctx)
+        seen = ctx.__dict__.setdefault("_client_workers", set())
+        self._primary = worker not in seen
+        seen.add(worker)
 
     @classmethod
     def load(cls, name, ctx):  # pragma: no cover - constructed through TextModelBase.load(make_remote=...)
@@ -153,10 +160,21 @@ class Client(Forwarder):
         y = self.transport.empty_like(x)
         self.transport.send(x, self.peer)
         self.transport.recv(y, self.peer)
+        # the worker always answers: the tensor, then a status (None | message) == Message::Tensor | WorkerError
+        # (worker.rs:490-520); an error never tears the session down (client.rs:120-135 turns it into Err)
+        status = [None]
+        dist.broadcast_object_list(status, src=self.peer)
+        if status[0] is not None:
+            raise WorkerError(f"worker {self.worker}: {status[0]}")
         return y
 
     def goodbye(self):
-        return None  # one Goodbye per session is broadcast by ShardedMaster.goodbye()
+        """client.rs:176-187: Goodbye clears the worker's KV cache.  The reference keeps one connection per remote
+        layer and says goodbye on each; here a worker has one session, so only the first Client of a worker sends it."""
+        import torch.distributed as dist
+        if self._primary:
+            dist.broadcast_object_list([("goodbye", self.peer)], src=0)
+        return None
 
     def layer_name(self):
         return self.name
@@ -193,21 +211,30 @@ class Worker:
             op = msg[0]
             if op[0] == "shutdown":
                 return
-            if op[0] == "goodbye":  # worker.rs:364-371
-                ctx.cache.clear()
+            if op[0] == "goodbye":  # worker.rs:364-371 (addressed to one worker, or to all when no rank is given)
+                if len(op) < 2 or op[1] is None or op[1] == self.rank:
+                    ctx.cache.clear()
             elif op[0] == "batch":
                 _, peer, b, s, shape, batch = op
                 if peer != self.rank:
+                    dist.broadcast_object_list([None], src=peer)  # the addressed worker's status message
                     continue
                 x = ctx.empty(*shape)
                 self.transport.recv(x, 0)
-                missing = [name for name, _, _ in batch if name not in self.blocks]
-                if missing:  # worker.rs:490-503: report, keep serving
-                    raise KeyError(f"worker gpu{self.rank} does not own {missing}")
-                blks = [self.blocks[name] for name, _, _ in batch]
-                y = blks[0].forward_batch(x, batch, ctx, blocks=blks)
+                err = None
+                try:  # worker.rs:490-503: any failure is reported as WorkerError and the worker keeps serving
+                    missing = [name for name, _, _ in batch if name not in self.blocks]
+                    if missing:
+                        raise KeyError(f"could not find layer {missing[0]}")
+                    blks = [self.blocks[name] for name, _, _ in batch]
+                    y = blks[0].forward_batch(x, batch, ctx, blocks=blks)
+                except Exception as e:  # noqa: BLE001 - reported to the master verbatim
+                    err = f"{type(e).__name__}: {e}"
+                    y = x  # payload of the error reply is ignored by the client
                 self.transport.send(y, 0)
-                self.served += 1
+                dist.broadcast_object_list([err], src=self.rank)
+                if err is None:
+                    self.served += 1
             elif op[0] == "decode":  # graph-captured ring decode: n steps without further control traffic
                 _, n_steps, index_pos = op
                 blks, idx = self.block_list()
@@ -255,7 +282,7 @@ class ShardedMaster:
 
     def goodbye(self) -> None:
         import torch.distributed as dist
-        dist.broadcast_object_list([("goodbye",)], src=0)
+        dist.broadcast_object_list([("goodbye", None)], src=0)
         self.ctx.cache.clear()
 
     def shutdown(self) -> None:

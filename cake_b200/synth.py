@@ -87,3 +87,49 @@ def make_checkpoint(cfg: Config, dtype: str = "bf16", seed: int = 1234, device="
     for i in range(cfg.num_hidden_layers):
         sd.update(make_layer(cfg, i, dtype, seed, device, std))
     return sd
+
+
+class LazyCheckpoint(dict):
+    """var_builder that materialises ONE block at a time on ``device`` — a 15 GB (8B) or 141 GB (70B) synthetic
+    checkpoint never exists whole; ``Forwarder::load`` pulls a layer's tensors, the previous layer is dropped.
+    Head tensors (embed / norm / lm_head) are created on first use and kept until ``drop_head()``.
+    ``host_copy=True`` also keeps a CPU copy of everything handed out in ``self.host`` (what a checker needs to see
+    the same weights).  Values are those of ``make_layer`` / ``make_head`` for (seed, device type)."""
+
+    def __init__(self, cfg: Config, dtype: str = "bf16", seed: int = 1234, device="cuda", std: float = 0.02,
+                 host_copy: bool = False, peaked: bool = False):
+        super().__init__()
+        self.cfg, self.dtype, self.seed, self.device, self.std, self.peaked = cfg, dtype, seed, device, std, peaked
+        self.host = {} if host_copy else None
+
+    def _ensure(self, k: str):
+        if k in self:
+            return
+        if ".layers." in k:
+            i = int(k.split(".layers.")[1].split(".")[0])
+            self.drop_layers()
+            new = make_layer(self.cfg, i, self.dtype, self.seed, self.device, self.std)
+        elif k.startswith(self.cfg.model_prefix + ".") or k == "lm_head.weight":
+            new = make_head(self.cfg, self.dtype, self.seed, self.device, self.std, self.peaked)
+        else:
+            return
+        self.update(new)
+        if self.host is not None:
+            for kk, t in new.items():
+                self.host[kk] = t.cpu()
+
+    def get(self, k, d=None):
+        self._ensure(k)
+        return dict.get(self, k, d)
+
+    def __getitem__(self, k):
+        self._ensure(k)
+        return dict.__getitem__(self, k)
+
+    def drop_layers(self):
+        for kk in [kk for kk in self if ".layers." in kk]:
+            del self[kk]
+
+    def drop_head(self):
+        for kk in [kk for kk in self if ".layers." not in kk]:
+            del self[kk]

@@ -167,6 +167,13 @@ int cake_b200_decode_logits(cake_b200_ctx *, void *logits_host, size_t bytes); /
 int cake_b200_bench_kernel(cake_b200_ctx *, cake_b200_block *const *blocks, const int *block_idx, int n_blocks,
                            cake_b200_cache *, int which, int reps, float *ms_per_launch);
 
+/* Per-step timeline of this rank's decode kernels for the last `n_steps` steps since cake_b200_decode_begin
+ * (n_steps <= 2048): 8 u64 per step = {entry, input acquired, exit, 0} of the layer launch followed by the same for
+ * rank 0's head-only launch when sharded (zeros otherwise); %globaltimer nanoseconds of CTA 0.  "input acquired"
+ * is when the hidden state of the previous shard arrived (== entry on a single GPU).  Replaces eyeballing the
+ * reference's per-hop log lines (worker.rs:505-530 ops/s + read/write stats).  Synchronises. */
+int cake_b200_decode_trace(cake_b200_ctx *, uint64_t *out_host, int n_steps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,9 +128,25 @@ static float dot_row_bf16_avx2(const uint16_t *w, const float *x, int K) {
 }
 #endif
 
+/* Summation-order probe (tolerance measurement, not a behaviour switch of the restatement): the reference fixes
+ * "f32 accumulate" but not the ORDER — candle's CPU gemm, cuBLAS and any GPU kernel each add the K exact products in
+ * a different order, and after 32 layers of bf16 roundings that order is visible in the logits.
+ *   0  default: 2x8 SIMD partial sums (bf16, AVX2) / 16 scalar partial sums
+ *   1  16 scalar partial sums for every dtype (a second, equally valid f32 order)
+ *   2  f64 accumulation, one rounding to f32 (the order-free limit every f32 order scatters around)
+ * tests compare logits across these modes to state how far two CORRECT implementations may differ. */
+static int g_dot_mode = 0;
+void ora_set_dot_mode(int m) { g_dot_mode = m; }
+int ora_dot_mode(void) { return g_dot_mode; }
+
 static float dot_row(const void *W, size_t off, const float *x, int K, int dt) {
+  if (g_dot_mode == 2) {
+    double s = 0.0;
+    for (int k = 0; k < K; k++) s += (double)wld(W, off + (size_t)k, dt) * (double)x[k];
+    return (float)s;
+  }
 #if defined(__AVX2__) && defined(__FMA__)
-  if (dt == ORA_BF16) return dot_row_bf16_avx2((const uint16_t *)W + off, x, K);
+  if (dt == ORA_BF16 && g_dot_mode == 0) return dot_row_bf16_avx2((const uint16_t *)W + off, x, K);
 #endif
   float acc[16];
   for (int j = 0; j < 16; j++) acc[j] = 0.f;

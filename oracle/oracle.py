@@ -89,6 +89,8 @@ def lib():
         L.ora_round.restype = cf
         L.ora_round.argtypes = [cf, ci]
         L.ora_num_threads.restype = ci
+        L.ora_set_dot_mode.argtypes = [ci]
+        L.ora_dot_mode.restype = ci
         L.ora_set_num_threads.argtypes = [ci]
         _lib = L
     return _lib
@@ -113,6 +115,11 @@ def round_to(a, dtype: str) -> np.ndarray:
     t = torch.from_numpy(_f32(a))
     from cake_b200.synth import TORCH_DTYPES
     return t.to(TORCH_DTYPES[dtype]).float().numpy()
+
+
+def set_dot_mode(mode: int) -> None:
+    """Summation-order probe of the linear layers (0 default, 1 second f32 order, 2 f64 accumulate): see cake_oracle.c."""
+    lib().ora_set_dot_mode(mode)
 
 
 # ---- op-level entry points (used by the known-answer tests) -----------------------------------

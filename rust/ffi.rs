@@ -73,6 +73,7 @@ extern "C" {
     pub fn cake_b200_cache_fill_synthetic(c: *mut cake_b200_cache, block_idx: *const c_int, n_blocks: c_int, len: c_int, seed: u32) -> c_int;
     pub fn cake_b200_bench_kernel(ctx: *mut cake_b200_ctx, blocks: *const *mut cake_b200_block, block_idx: *const c_int,
         n_blocks: c_int, cache: *mut cake_b200_cache, which: c_int, reps: c_int, ms_per_launch: *mut f32) -> c_int;
+    pub fn cake_b200_decode_trace(ctx: *mut cake_b200_ctx, out_host: *mut u64, n_steps: c_int) -> c_int;
 }
 
 /// `anyhow!(cake_b200_last_error())` — the library stringifies failures with context the same way

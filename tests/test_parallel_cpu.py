@@ -143,10 +143,20 @@ def _run(rank, world, port, q):
                 ref = 2 * ref + (i + 1)
             outs = [forward(x, p) for p in range(3)]                  # 3 sequential ops (protocol.rs: 10 sequential)
             big = forward(torch.ones(1, 64, 8), 3)                     # "large tensor" case
-            dist.broadcast_object_list([("goodbye",)], src=0)         # goodbye-then-continue
+            for b in blocks:                                           # TextModelBase::goodbye (text_model.rs:517-528):
+                b.goodbye()                                            # one Goodbye per worker, sent by its first Client
             after = forward(x, 0)
+            # worker.rs:490-503 / protocol.rs "layer not found": the worker reports the error and keeps serving
+            from cake_b200.parallel import WorkerError
+            ghost = Client("gpu1", "model.layers.99", ctx, transport=tr)
+            try:
+                ghost.forward_batch(x, [("model.layers.99", 0, 99)], ctx)
+                reported = False
+            except WorkerError as e:
+                reported = "model.layers.99" in str(e)
+            after2 = forward(x, 1)
             dist.broadcast_object_list([("shutdown",)], src=0)
-            q.put(("master", all(torch.equal(o, ref) for o in outs + [after]), tuple(big.shape)))
+            q.put(("master", reported and all(torch.equal(o, ref) for o in outs + [after, after2]), tuple(big.shape)))
     finally:
         dist.destroy_process_group()
 
@@ -166,7 +176,7 @@ def test_master_worker_protocol_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res["master"] == (True, (1, 64, 8))
-    assert res["worker"] == (5, 1)   # 5 batches served, cache cleared once by Goodbye
+    assert res["worker"] == (6, 1)   # 6 batches served (the failed one is not counted), cache cleared once by Goodbye
 
 
 # ---- the same protocol with the real block class over the emulated library -------------------------------------------
