@@ -56,14 +56,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO
 
 
-def build_trace() -> str:
-    """Profiling build: the same library with -DMK_TRACE=1 (per-CTA phase records inside decode_mega_kernel), written
-    to libcake_b200_trace.so next to the product library.  Used by bench_tools/mega_trace.py only."""
-    out = os.path.join(HERE, "libcake_b200_trace.so")
+def build_trace(defines=("-DMK_TRACE=1",), name="libcake_b200_trace.so") -> str:
+    """A/B builds of the same library with extra -D switches, written next to the product library (selected at run time with
+    CAKE_B200_LIB=<path>, bench_tools/ab.sh).  Profiling aid only; nothing in the product uses it."""
+    out = os.path.join(HERE, name)
     if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(s) for s in sources()):
         return out
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-DMK_TRACE=1",
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", *defines,
                            "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-shared", "--expt-relaxed-constexpr",
                            "-I", _nccl_include(), "-I", os.path.join(ROOT, "include"), "-o", out, SRC, "-ldl"])
     return out

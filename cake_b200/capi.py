@@ -12,7 +12,8 @@ from ctypes import POINTER, byref, c_char_p, c_float, c_int, c_size_t, c_uint32,
 from .config import CConfig
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libcake_b200.so")
+# CAKE_B200_LIB: profiling / A-B builds of the same library (bench_tools/); the product library is the in-tree default
+SO_PATH = os.environ.get("CAKE_B200_LIB") or os.path.join(_HERE, "libcake_b200.so")
 
 # every symbol include/cake_b200.h declares: (name, restype, argtypes)
 _VP, _I = c_void_p, c_int
@@ -76,6 +77,8 @@ def lib() -> ctypes.CDLL:
                 "(libcake_b200 has no CPU or PyTorch fallback)")
         L = ctypes.CDLL(SO_PATH, mode=ctypes.RTLD_GLOBAL)
         for name, res, args in SYMBOLS:
+            if os.environ.get("CAKE_B200_LIB") and not hasattr(L, name):
+                continue  # A/B against an older build of the library (bench_tools/ab.sh); the product library must export everything
             fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args

@@ -7,6 +7,7 @@
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -401,8 +402,8 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
     c->use_mega = !(e && e[0] == '1');
     const char *t = getenv("CAKE_B200_MEGA_TRACE");
     if (t && t[0] == '1') {
-      CU(cudaMalloc(&c->trace, 8 * (size_t)MK_TRACE_U64));
-      CU(cudaMemset(c->trace, 0, 8 * (size_t)MK_TRACE_U64));
+      CU(cudaMalloc(&c->trace, 8 * 4096));
+      CU(cudaMemset(c->trace, 0, 8 * 4096));
     }
   }
   {
@@ -1421,7 +1422,7 @@ extern "C" int cake_b200_decode_trace(cake_b200_ctx *c, uint64_t *out_host, int 
 /* profiling aid (not in the public header): copies the megakernel's phase-boundary %globaltimer stamps of
  * the last launch (CTA 0) to `out`; needs CAKE_B200_MEGA_TRACE=1 at ctx creation. */
 extern "C" int cake_b200_debug_trace(cake_b200_ctx *c, unsigned long long *out, int n) {
-  if (!c || !c->trace || n > MK_TRACE_U64) return fail(CAKE_B200_ESTATE, "tracing is off (CAKE_B200_MEGA_TRACE=1)");
+  if (!c || !c->trace || n > 4096) return fail(CAKE_B200_ESTATE, "tracing is off (CAKE_B200_MEGA_TRACE=1)");
   CU(cudaSetDevice(c->device));
   CU(cudaStreamSynchronize(c->stream));
   CU(cudaMemcpy(out, c->trace, (size_t)n * 8, cudaMemcpyDeviceToHost));

@@ -77,6 +77,11 @@ struct MkArgs {
   int trace_tag;
 };
 constexpr int MK_STEP_RING = 2048;
+__device__ __forceinline__ unsigned long long mk_gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 
 __host__ __device__ inline size_t mk_xs_bytes(int max_k, int es) {
   size_t b = (size_t)max_k * es;
@@ -102,33 +107,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   return v;
 }
 __device__ __forceinline__ uint4 ldcg_v4(const void *p) { return __ldcg(reinterpret_cast<const uint4 *>(p)); }
-
-// ---- fine-grained phase trace (profiling builds only: nvcc -DMK_TRACE=1 -> libcake_b200_trace.so, bench_tools/mega_trace.py).
-// One 16-u64 record per (CTA, phase 0..4 = qkv/attn/o/gate_up/down) of layer MK_TRACE_LAYER at a.trace[4096 + ...]:
-//   0 consumer enters the phase   1 x staged   2 last stage consumed   3 arrives at the grid barrier   4 passes it
-//   5 clocks warp 0 spent waiting for full stages (starved)   6 stages consumed
-//   7 producer's first issue   8 static groups issued   9 pool groups issued (end marker)
-//   10 clocks the producer spent waiting for an empty stage (ring full)   11 pool groups claimed
-//   12..15 attention: q/k/v prepared, tiles done, partials written, ticket taken
-#ifndef MK_TRACE
-#define MK_TRACE 0
-#endif
-constexpr int MK_TRACE_LAYER = 1;
-constexpr int MK_TRACE_BASE = 4096;
-constexpr int MK_TRACE_U64 = MK_TRACE_BASE + 160 * 5 * 16;
-__device__ __forceinline__ unsigned long long mk_gtime() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-#if MK_TRACE
-#define MKT(stmt) do { stmt; } while (0)
-#else
-#define MKT(stmt) do { } while (0)
-#endif
-__device__ __forceinline__ unsigned long long *mk_trec(unsigned long long *trace, int layer, int phase) {
-  return (trace && layer == MK_TRACE_LAYER) ? trace + MK_TRACE_BASE + ((size_t)blockIdx.x * 5 + phase) * 16 : nullptr;
-}
 
 struct MkRing {
   unsigned char *ring;
@@ -224,26 +202,15 @@ __device__ __forceinline__ void mk_prefetch_static(const MkGeom &g, const void *
 
 template <typename T>
 __device__ __forceinline__ void mk_produce_gemv_dyn(MkRing &rg, const MkGeom &g, const void *W, unsigned *ticket, int max_groups,
-                                                    uint64_t pol, MkPrefetch &pf, unsigned long long *tr) {
+                                                    uint64_t pol, MkPrefetch &pf) {
   constexpr int es = sizeof(T);
   const MkSplit sp = mk_split(g);
   const size_t rowb = (size_t)g.K * es;
   const unsigned char *Wb = reinterpret_cast<const unsigned char *>(W);
   int issued = 0;
-  (void)tr;
-  MKT(if (tr) tr[7] = mk_gtime());
-#if MK_TRACE
-  long long blocked = 0;
-#endif
   auto issue = [&](int grp) {
     const int row = grp * g.RS, nr = min(g.RS, g.N - row);
-#if MK_TRACE
-    const long long c0 = clock64();
-#endif
     mbar_wait(&rg.empty[rg.s], rg.ph ^ 1u);
-#if MK_TRACE
-    blocked += clock64() - c0;
-#endif
     rg.stage_row[rg.s] = row;
     mbar_arrive_expect_tx(&rg.full[rg.s], (uint32_t)(nr * rowb));
     bulk_g2s(rg.ring + (size_t)rg.s * MK_STAGE_BYTES, Wb + (size_t)row * rowb, (uint32_t)(nr * rowb), &rg.full[rg.s], pol);
@@ -254,10 +221,6 @@ __device__ __forceinline__ void mk_produce_gemv_dyn(MkRing &rg, const MkGeom &g,
     issue(grp);
     if (pf.a->l2_prefetch == 1) pf.step();  // keep the L2 prefetch MK_PF_AHEAD static groups ahead of the load cursor
   }
-  MKT(if (tr) tr[8] = mk_gtime());
-#if MK_TRACE
-  const int n_static = issued;
-#endif
   if (sp.pool_start < sp.n_groups && issued < max_groups) {
     unsigned next = atomicAdd(ticket, 1u);
     while (sp.pool_start + (int)next < sp.n_groups) {
@@ -272,32 +235,20 @@ __device__ __forceinline__ void mk_produce_gemv_dyn(MkRing &rg, const MkGeom &g,
   rg.stage_row[rg.s] = -1;
   mbar_arrive(&rg.full[rg.s]);
   rg.advance();
-  MKT(if (tr) { tr[9] = mk_gtime(); tr[10] = (unsigned long long)blocked; tr[11] = (unsigned long long)(issued - n_static); });
 }
 
 template <typename T>
-__device__ __forceinline__ void mk_produce_gemv(MkRing &rg, const MkGeom &g, const void *W, int G, uint64_t pol, unsigned long long *tr) {
+__device__ __forceinline__ void mk_produce_gemv(MkRing &rg, const MkGeom &g, const void *W, int G, uint64_t pol) {
   constexpr int es = sizeof(T);
   int r0, r1;
   mk_rows(g.N, G, r0, r1);
-  (void)tr;
-  MKT(if (tr) tr[7] = mk_gtime());
-#if MK_TRACE
-  long long blocked = 0;
-#endif
   const int nchunk = g.K / g.KC;
   const size_t seg = (size_t)g.KC * es;
   const unsigned char *Wb = reinterpret_cast<const unsigned char *>(W);
   for (int row = r0; row < r1; row += g.RS) {
     const int nr = min(g.RS, r1 - row);
     for (int j = 0; j < nchunk; j++) {
-#if MK_TRACE
-      const long long c0 = clock64();
-#endif
       mbar_wait(&rg.empty[rg.s], rg.ph ^ 1u);
-#if MK_TRACE
-      blocked += clock64() - c0;
-#endif
       unsigned char *dst = rg.ring + (size_t)rg.s * MK_STAGE_BYTES;
       mbar_arrive_expect_tx(&rg.full[rg.s], (uint32_t)(nr * seg));
       if (nchunk == 1) {
@@ -309,7 +260,6 @@ __device__ __forceinline__ void mk_produce_gemv(MkRing &rg, const MkGeom &g, con
       rg.advance();
     }
   }
-  MKT(if (tr) { tr[8] = tr[9] = mk_gtime(); tr[10] = (unsigned long long)blocked; tr[11] = 0; });
 }
 
 struct MkAttnItem {
@@ -431,13 +381,7 @@ struct MkEpi {
 
 template <typename T, int EPI>
 __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, const T *xs, float *partial, int *loc_row,
-                                                float *scratch, const MkEpi &e, int ct, int warp, int lane,
-                                                unsigned long long *tr = nullptr) {
-  (void)tr;
-#if MK_TRACE
-  long long starved = 0;
-  int nst = 0;
-#endif
+                                                float *scratch, const MkEpi &e, int ct, int warp, int lane) {
   constexpr int G = (EPI == EPI_SWIGLU) ? 2 : 1;
   const int RS = g.RS, WPR = g.WPR, RPW = g.RPW, N = g.N;
   const int nchunk = g.K / g.KC;
@@ -461,14 +405,7 @@ __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, con
     const bool v3 = lane + 96 < nvec, v2 = lane + 64 < nvec, v1 = lane + 32 < nvec, v0 = lane < nvec;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     while (true) {
-#if MK_TRACE
-      const long long c0 = clock64();
-#endif
       mbar_wait(&rg.full[rg.s], rg.ph);
-#if MK_TRACE
-      starved += clock64() - c0;
-      nst++;
-#endif
       const int row = rg.stage_row[rg.s];
       if (row >= 0) {
         const uint4 *st = reinterpret_cast<const uint4 *>(rg.ring + (size_t)rg.s * MK_STAGE_BYTES) + ks * nvec + lane;
@@ -508,14 +445,7 @@ __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, con
 #pragma unroll
       for (int r = 0; r < 4; r++) acc[r][0] = acc[r][1] = 0.f;
       for (int j = 0; j < nchunk; j++) {
-#if MK_TRACE
-        const long long c0 = clock64();
-#endif
         mbar_wait(&rg.full[rg.s], rg.ph);
-#if MK_TRACE
-        starved += clock64() - c0;
-        nst++;
-#endif
         const uint4 *st = reinterpret_cast<const uint4 *>(rg.ring + (size_t)rg.s * MK_STAGE_BYTES);
         const uint4 *xc = xsv + (size_t)j * segv + ks * nvec;
 #pragma unroll 2
@@ -546,7 +476,6 @@ __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, con
       }
     }
   }
-  MKT(if (tr && ct == 0) { tr[2] = mk_gtime(); tr[5] = (unsigned long long)starved; tr[6] = (unsigned long long)nst; });
   named_bar_sync(1, MK_CT);
   // local row index li -> global row (dynamic: group list; static: contiguous range)
   const int n_local = dyn ? nloc * RS : nrows;
@@ -684,10 +613,14 @@ __device__ __forceinline__ void mk_norm_rope(float *buf, const T *norm_w, float 
 template <typename T, int HD, int G>
 __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, const MkLayer &L, int pos, unsigned char *scr,
                                                 const float *rope_cs, int ct, int warp, int lane, unsigned long long *tr) {
-  auto stamp = [&](int i) {  // profiling builds: tr[12..15] = q/k/v prepared, tiles done, partials written, ticket taken
-    (void)i;
-    MKT(if (tr && ct == 0 && i >= 12) tr[i] = mk_gtime());
+  auto stamp = [&](int i) {
+    if (tr && ct == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      tr[i] = t;
+    }
   };
+  stamp(0);
   constexpr int LPR = HD / 8;            // lanes per cached row (16 B each); HD in {16,64,128} -> 2, 8, 16
   constexpr int RPWI = 32 / LPR;         // rows per warp per iteration
   constexpr int NW = MK_CW;
@@ -734,7 +667,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
   }
   if (ct < ATTN_MAX_G) { m_run[ct] = -INFINITY; l_run[ct] = 0.f; }
   named_bar_sync(1, MK_CT);
-  stamp(12);
+  stamp(1);
 
   const int grp = lane / LPR, gl = lane % LPR;  // row group within the warp / lane within the row
   float qreg[G][8];
@@ -766,6 +699,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     Vs = reinterpret_cast<T *>(rg.ring + (size_t)sv * MK_STAGE_BYTES);
     mbar_wait(&rg.full[sk], phk);
     mbar_wait(&rg.full[sv], phv);
+    stamp(2);
     if (owner && pos >= t0 && pos < t0 + tn) {  // drop the appended row into its slot of the staged tiles
       const int slot = pos - t0;
       for (int d = ct; d < HD; d += MK_CT) {
@@ -806,6 +740,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
       }
     }
     named_bar_sync(1, MK_CT);
+    stamp(3);
     // ---- online softmax bookkeeping, one warp per head ---------------------------------------------
     for (int g = warp; g < G; g += NW) {
       float mx = -INFINITY;
@@ -827,6 +762,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
       }
     }
     named_bar_sync(1, MK_CT);
+    stamp(4);
     // ---- PV: a lane owns dims gl*8..+8 of every head; one 16-byte V load feeds 8*G FMAs ------------
 #pragma unroll
     for (int g = 0; g < G; g++) {
@@ -845,8 +781,8 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
       }
     }
     named_bar_sync(1, MK_CT);  // every warp is done with this tile's K, V and probabilities
+    stamp(5);
   }
-  stamp(13);
 
   // ---- combine the row groups: lanes of a warp first (shuffles), then the 16 warps through the (dead)
   //      K/V stage buffers of the last tile -----------------------------------------------------------
@@ -889,7 +825,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     a.ws_ml[((size_t)(kvh * G + ct) * a.nsplit + split) * 2 + 0] = m_run[ct];
     a.ws_ml[((size_t)(kvh * G + ct) * a.nsplit + split) * 2 + 1] = l_run[ct];
   }
-  stamp(14);
+  stamp(6);
   named_bar_sync(1, MK_CT);
   if (ct == 0) {
     // acq_rel at gpu scope: releases the partials every thread of this CTA wrote before the bar.sync (cumulative)
@@ -899,7 +835,7 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
     is_last = (ticket == (unsigned)a.nsplit - 1);
   }
   named_bar_sync(1, MK_CT);
-  stamp(15);
+  stamp(7);
   if (!is_last) return;
   for (int g = warp; g < G; g += NW) {
     const int h = kvh * G + g;
@@ -964,25 +900,23 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
       const uint64_t pol_w = policy_evict_first(), pol_kv = policy_evict_last();
       MkPrefetch pf{&a, 0, 0, 0, (int)sizeof(T)};
       if (a.l2_prefetch == 1) for (int i = 0; i < MK_PF_AHEAD; i++) pf.step();
-      auto produce = [&](const MkGeom &g, const void *W, int gran, int phase, unsigned long long *tr) {
-        if (mk_is_dynamic(g)) mk_produce_gemv_dyn<T>(rg, g, W, a.tickets + phase, a.max_groups, pol_w, pf, tr);
-        else mk_produce_gemv<T>(rg, g, W, gran, pol_w, tr);
+      auto produce = [&](const MkGeom &g, const void *W, int gran, int phase) {
+        if (mk_is_dynamic(g)) mk_produce_gemv_dyn<T>(rg, g, W, a.tickets + phase, a.max_groups, pol_w, pf);
+        else mk_produce_gemv<T>(rg, g, W, gran, pol_w);
       };
       for (int l = 0; l < a.n_layers; l++) {
         const MkLayer L = a.layers[l];
-        produce(a.g_qkv, L.wqkv, 1, 4 * l + 0, mk_trec(a.trace, l, 0));
-        MKT(if (mk_trec(a.trace, l, 1)) mk_trec(a.trace, l, 1)[7] = mk_gtime());
+        produce(a.g_qkv, L.wqkv, 1, 4 * l + 0);
         mk_produce_attn<T>(rg, a, L, pos, pol_kv);
-        MKT(if (mk_trec(a.trace, l, 1)) mk_trec(a.trace, l, 1)[9] = mk_gtime());
         if (a.l2_prefetch == 2) {
           mk_prefetch_static(a.g_o, L.wo, (int)sizeof(T), 0, 1 << 20);
           mk_prefetch_static(a.g_gu, L.wgu, (int)sizeof(T), 0, 10);
         }
-        produce(a.g_o, L.wo, 1, 4 * l + 1, mk_trec(a.trace, l, 2));
-        produce(a.g_gu, L.wgu, 2, 4 * l + 2, mk_trec(a.trace, l, 3));
-        produce(a.g_down, L.wd, 1, 4 * l + 3, mk_trec(a.trace, l, 4));
+        produce(a.g_o, L.wo, 1, 4 * l + 1);
+        produce(a.g_gu, L.wgu, 2, 4 * l + 2);
+        produce(a.g_down, L.wd, 1, 4 * l + 3);
       }
-      if (a.has_head) produce(a.g_head, a.lm_head, 1, 4 * a.n_layers, nullptr);
+      if (a.has_head) produce(a.g_head, a.lm_head, 1, 4 * a.n_layers);
     }
     return;
   }
@@ -1040,65 +974,47 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
   for (int l = 0; l < a.n_layers; l++) {
     const MkLayer L = a.layers[l];
     T *dst = reinterpret_cast<T *>((l == a.n_layers - 1) ? a.x_out : a.xa);
-#if MK_TRACE
-    unsigned long long *tq = mk_trec(a.trace, l, 0), *ta = mk_trec(a.trace, l, 1), *to = mk_trec(a.trace, l, 2),
-                       *tg = mk_trec(a.trace, l, 3), *td = mk_trec(a.trace, l, 4);
-    if (ct != 0) tq = ta = to = tg = td = nullptr;
-#define TS(rec, i) do { if (rec) (rec)[i] = mk_gtime(); } while (0)
-#else
-    unsigned long long *const tq = nullptr, *const ta = nullptr, *const to = nullptr, *const tg = nullptr, *const td = nullptr;
-#define TS(rec, i) do { } while (0)
-#endif
     // rms_1 + qkv (+bias)
-    TS(tq, 0);
     mk_stage_x<T>(xs, cur, L.ln1, a.hidden, a.eps, scratch, ct, warp, lane);
-    TS(tq, 1);
     e = MkEpi{};
     e.bias = L.bqkv;
     e.out = a.qkv;
-    mk_consume_gemv<T, EPI_PLAIN>(rg, a.g_qkv, xs, partial, loc_row, scratch, e, ct, warp, lane, tq);
-    TS(tq, 3);
+    mk_consume_gemv<T, EPI_PLAIN>(rg, a.g_qkv, xs, partial, loc_row, scratch, e, ct, warp, lane);
     gsync();
-    TS(tq, 4);
     // qk-norm, RoPE, KV append, attention
-    TS(ta, 0);
-    mk_consume_attn<T, HD, G>(rg, a, L, pos, reinterpret_cast<unsigned char *>(xs), rope_cs, ct, warp, lane, ta);
-    TS(ta, 3);
+    mk_consume_attn<T, HD, G>(rg, a, L, pos, reinterpret_cast<unsigned char *>(xs), rope_cs, ct, warp, lane,
+                           (a.trace && blockIdx.x == 0 && l == 1) ? a.trace + 2048 : nullptr);
     gsync();
-    TS(ta, 4);
     // o_proj + residual
-    TS(to, 0);
     mk_stage_x<T>(xs, a.y, nullptr, a.n_heads * a.hd, a.eps, scratch, ct, warp, lane);
-    TS(to, 1);
     e = MkEpi{};
     e.residual = cur;
     e.out = a.xb;
-    mk_consume_gemv<T, EPI_RESIDUAL>(rg, a.g_o, xs, partial, loc_row, scratch, e, ct, warp, lane, to);
-    TS(to, 3);
+    mk_consume_gemv<T, EPI_RESIDUAL>(rg, a.g_o, xs, partial, loc_row, scratch, e, ct, warp, lane);
     gsync();
-    TS(to, 4);
     // rms_2 + gate_up + silu*mul
-    TS(tg, 0);
     mk_stage_x<T>(xs, a.xb, L.ln2, a.hidden, a.eps, scratch, ct, warp, lane);
-    TS(tg, 1);
     e = MkEpi{};
     e.out = a.mm;
-    mk_consume_gemv<T, EPI_SWIGLU>(rg, a.g_gu, xs, partial, loc_row, scratch, e, ct, warp, lane, tg);
-    TS(tg, 3);
+    mk_consume_gemv<T, EPI_SWIGLU>(rg, a.g_gu, xs, partial, loc_row, scratch, e, ct, warp, lane);
+    if (a.trace && l == 1 && ct == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.trace[2304 + blockIdx.x] = t;
+    }
     gsync();
-    TS(tg, 4);
+    if (a.trace && l == 1 && ct == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      a.trace[2560 + blockIdx.x] = t;
+    }
     // down + residual
-    TS(td, 0);
     mk_stage_x<T>(xs, a.mm, nullptr, a.inter, a.eps, scratch, ct, warp, lane);
-    TS(td, 1);
     e = MkEpi{};
     e.residual = a.xb;
     e.out = dst;
-    mk_consume_gemv<T, EPI_RESIDUAL>(rg, a.g_down, xs, partial, loc_row, scratch, e, ct, warp, lane, td);
-    TS(td, 3);
+    mk_consume_gemv<T, EPI_RESIDUAL>(rg, a.g_down, xs, partial, loc_row, scratch, e, ct, warp, lane);
     if (l < a.n_layers - 1 || a.has_head) gsync();
-    TS(td, 4);
-#undef TS
     cur = dst;
   }
   if (a.has_head) {

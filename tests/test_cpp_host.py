@@ -65,6 +65,8 @@ def test_cake_run_tokens_equal_python_master(tmp_path, sharded):
     ref = Master(TextModelBase.load(ctx)).generate_text(prompt, 12)["tokens"]
     ctx.close()
     assert toks == ref
+    from oracle import oracle as O   # and both equal the oracle's greedy tokens
+    assert toks == list(O.OracleModel(cfg, sd, "bf16", max_seq=cfg.max_seq_len).generate(prompt, 12)[0])
 
 
 @pytest.mark.parametrize("damage", ["truncate", "offsets", "header_len", "not_json"])

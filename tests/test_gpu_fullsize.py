@@ -33,13 +33,13 @@ def test_llama3_8b_block_matches_oracle_prefill_and_decode():
     ctx.sync()
     e = max_ulp_err(to_np(y[0]), y_ref, "bf16")
     print(f"L8 block prefill(48): max {e:.2f} ulp, mean {mean_ulp_err(to_np(y[0]), y_ref, 'bf16'):.3f} ulp")
-    assert e <= 4.0 and mean_ulp_err(to_np(y[0]), y_ref, "bf16") <= 0.25
+    assert e <= 3.0 and mean_ulp_err(to_np(y[0]), y_ref, "bf16") <= 0.25
     for t in range(48, 52):                                             # decode: persistent megakernel
         y_ref = om.block_forward(0, x[0, t:t + 1].float().numpy(), t, oc)
         y = blk.forward(ctx.to_device(x[:, t:t + 1]), t, 0, ctx)
         ctx.sync()
         e = max_ulp_err(to_np(y[0]), y_ref, "bf16")
-        assert e <= 4.0, f"decode @{t}: {e} ulp"
+        assert e <= 3.0, f"decode @{t}: {e} ulp"
     k, v = ctx.cache.kv(0)
     ko, vo = oc.kv(0)
     assert max_ulp_err(to_np(k[0]), ko[:, :52], "bf16") <= 2.0
@@ -70,7 +70,7 @@ def test_llama3_8b_decode_equals_prefill_at_depth():
         y = blks[0].forward_batch(x[:, t:t + 1], batch(t), ctx, blocks=blks)
         ctx.sync()
         e = max_ulp_err(to_np(y[0, 0]), to_np(full[0, t]), "bf16")
-        assert e <= 4.0, f"position {t}: {e} ulp"
+        assert e <= 3.0, f"position {t}: {e} ulp"
     # determinism of the whole path: a second identical run is bit-equal
     ctx.cache.clear()
     again = blks[0].forward_batch(x, batch(0), ctx, blocks=blks)
@@ -110,9 +110,9 @@ def test_qwen3_0_6b_config0_f16_greedy_against_oracle():
         margin = float(srt[-1] - srt[-2])
         if O.argmax(lg) != ref_toks[step]:
             flips += 1
-            assert margin <= 2 * 8.0 * ulp_at_scale(ref_logits[step], "f16"), f"step {step}: token flip with margin {margin}"
+            assert margin <= 2 * 4.0 * ulp_at_scale(ref_logits[step], "f16"), f"step {step}: token flip with margin {margin}"
     print(f"Qwen3-0.6B-shaped f16: worst logits err {worst:.2f} ulp over 32 greedy steps, in-margin flips {flips}")
-    assert worst <= 8.0
+    assert worst <= 4.0
     # and the whole greedy loop through the decode graph reproduces its own step-wise tokens
     model.prepare_prompt(prompt)
     a = [model.next_token(i).id for i in range(8)]
@@ -144,13 +144,13 @@ def test_llama3_70b_layer_geometry_matches_oracle():
     y_ref = om.block_forward(0, x[0, :17].float().numpy(), 0, oc)
     y = blk.forward(ctx.to_device(x[:, :17]), 0, 0, ctx)
     ctx.sync()
-    assert max_ulp_err(to_np(y[0]), y_ref, "bf16") <= 4.0
+    assert max_ulp_err(to_np(y[0]), y_ref, "bf16") <= 3.0
     for t in range(17, 20):
         y_ref = om.block_forward(0, x[0, t:t + 1].float().numpy(), t, oc)
         y = blk.forward(ctx.to_device(x[:, t:t + 1]), t, 0, ctx)
         ctx.sync()
         e = max_ulp_err(to_np(y[0]), y_ref, "bf16")
-        assert e <= 4.0, f"decode @{t}: {e} ulp"
+        assert e <= 3.0, f"decode @{t}: {e} ulp"
     ctx.close()
 
 
@@ -181,5 +181,5 @@ def test_llama3_8b_decode_at_2500_context_multi_tile_attention():
         y = blk.forward(ctx.to_device(x[:, i:i + 1]), L0 + i, 0, ctx)
         ctx.sync()
         e = max_ulp_err(to_np(y[0]), y_ref, "bf16")
-        assert e <= 4.0, f"decode @{L0 + i}: {e} ulp"
+        assert e <= 3.0, f"decode @{L0 + i}: {e} ulp"
     ctx.close()

@@ -78,6 +78,12 @@ def test_llama3_8b_all_32_layers_decode_at_2k_context_matches_oracle():
         e = max_ulp_err(to_np(y[0]), xs[l + 1], "bf16")
         worst_block = max(worst_block, e)
         assert e <= BLOCK_ULP, f"layer {l}: block output off by {e} ulp"
+        if l % 8 == 0 or l == nl - 1:   # the K / V row this block appended at position 2048 (cache.rs:184-210)
+            k, v = ctx.cache.kv(l)
+            ko, vo = oc.kv(l)
+            ek = max_ulp_err(to_np(k[0][:, CTX_LEN:CTX_LEN + 1]), ko[:, CTX_LEN:CTX_LEN + 1], "bf16")
+            ev = max_ulp_err(to_np(v[0][:, CTX_LEN:CTX_LEN + 1]), vo[:, CTX_LEN:CTX_LEN + 1], "bf16")
+            assert ek <= 2.0 and ev <= 2.0, f"layer {l}: appended K/V row off by {ek} / {ev} ulp"
     print(f"32 blocks at KV {CTX_LEN}, each fed the oracle's input: worst {worst_block:.2f} ulp")
     ctx.cache.clear()
     ctx.cache.fill_synthetic(list(range(nl)), CTX_LEN, 7)   # same pattern again (the block pass appended a row)

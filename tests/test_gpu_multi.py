@@ -76,3 +76,67 @@ def test_two_gpu_ring_equals_single_gpu():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert toks == ref
+
+
+def _rank_70b(rank, world, port, q):
+    """BASELINE configs[3] widths (Llama-3-70B: H=8192, I=28672, 64/8 heads of 128 -> 8 query heads per kv head, 16 KB and
+    split 56 KB weight rows), 2 layers = one per rank, vocabulary cut to 4096 rows to keep the test small."""
+    import torch.distributed as dist
+    from cake_b200.config import llama3_70b
+    from cake_b200.model import Context
+    from cake_b200.parallel import ShardedMaster, Worker, init_comm
+    from cake_b200.synth import make_checkpoint
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    cfg = llama3_70b(max_seq=128)
+    cfg.num_hidden_layers, cfg.vocab_size = 2, 4096
+    sd = make_checkpoint(cfg, "bf16", seed=70, peaked=True)
+    prompt = np.random.default_rng(3).integers(0, cfg.vocab_size, 9).tolist()
+    n_new = 8
+    ctx = Context(cfg, sd, "bf16", device=rank, max_seq=128)
+    init_comm(ctx, rank, world)
+    if rank == 0:
+        master = ShardedMaster(ctx, world)
+        model = master.model
+        assert [b.ident() for b in model.blocks] == ["local", "gpu1"]
+        model.prepare_prompt(prompt)
+        toks = [model.next_token(i).id for i in range(3)]      # prefill + 2 decode steps through Client.forward_batch
+        lg = model.last_logits.float().cpu().numpy()           # logits of the third step
+        master.decode_build()
+        toks += master.decode_greedy(toks[-1], n_new - 3)       # fused NVLink hand-off inside the decode kernels
+        master.goodbye()
+        master.shutdown()
+        q.put(("tokens", prompt, toks, lg))
+    else:
+        Worker(ctx, rank, world).serve()
+    ctx.sync()
+    dist.destroy_process_group()
+    ctx.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpu_ring_at_70b_widths_matches_oracle():
+    from cake_b200.config import llama3_70b
+    from cake_b200.synth import make_checkpoint
+    from oracle import oracle as O
+    from tests.util import max_ulp_err
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_rank_70b, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    cfg = llama3_70b(max_seq=128)
+    cfg.num_hidden_layers, cfg.vocab_size = 2, 4096
+    sd = make_checkpoint(cfg, "bf16", seed=70, peaked=True)      # same seed -> the same tensors as in the ranks
+    om = O.OracleModel(cfg, sd, "bf16", max_seq=128)
+    _, prompt, toks, lg = q.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref_toks, ref_logits = om.generate(prompt, 8)
+    e = max_ulp_err(lg, ref_logits[2], "bf16")
+    print(f"70B widths x 2 layers over 2 GPUs: tokens {toks} oracle {list(ref_toks)}, logits error at step 2: {e:.2f} ulp")
+    assert e <= 4.0
+    assert toks == list(ref_toks)

@@ -6,9 +6,9 @@ shapes/determinism only — plus the numeric comparison the reference never had.
 Tolerance (written here, stated in DESIGN.md): floating point, dtype D in {bf16, f16}.  GPU and oracle
 round at the same points but accumulate fp32 sums in different orders, so a value that lands near a
 rounding boundary can differ by 1 ulp of D and the flip propagates.  Bars:
-  one block:            max |err| <= 4 ulp of D at the tensor's scale (tests/util.py ulp_at_scale), i.e.
-                        bf16: 2^-5 * 2^floor(log2 max|ref|), f16: 2^-8 * ...; mean |err| <= 0.25 ulp
-  final logits (<=4 layers): <= 8 ulp;  greedy token ids: bit-exact whenever the oracle's top-1/top-2
+  one block:            max |err| <= 3 ulp of D at the tensor's scale (tests/util.py ulp_at_scale), i.e.
+                        bf16: 3 * 2^-7 * 2^floor(log2 max|ref|), f16: 3 * 2^-10 * ...; mean |err| <= 0.25 ulp
+  final logits (<=4 layers): <= 4 ulp;  greedy token ids: bit-exact whenever the oracle's top-1/top-2
   margin exceeds the logit tolerance (margins are printed; flips inside the margin are reported).
 """
 import numpy as np
@@ -21,8 +21,8 @@ from tests.util import checkpoint, max_ulp_err, mean_ulp_err, medium_config, ran
 
 pytestmark = pytest.mark.gpu
 
-BLOCK_TOL_ULP = 4.0
-LOGIT_TOL_ULP = 8.0
+BLOCK_TOL_ULP = 3.0   # measured on hardware: 1-2 ulp
+LOGIT_TOL_ULP = 4.0   # <= 4 layers; measured <= 3 (the 32-layer bar is derived from the order sensitivity, test_gpu_l8_full.py)
 
 
 def _ctx(cfg, sd, dtype, max_seq=None):
@@ -30,7 +30,15 @@ def _ctx(cfg, sd, dtype, max_seq=None):
     return Context(cfg, sd, dtype, device=0, max_seq=max_seq)
 
 
+def _llama31_scaling():
+    from cake_b200.config import RopeScaling
+    # Llama-3.1 style scaling (cache.rs:49-80) with a short original context so that all three frequency bands
+    # (kept / interpolated / divided by the factor) occur within head_dim 64
+    return RopeScaling(factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0, original_max_position_embeddings=64, rope_type="llama3")
+
+
 CONFIGS = {
+    "medium_rope_llama3": lambda: medium_config(rope_scaling=_llama31_scaling(), rope_theta=10000.0),
     "ref_tiny": lambda: reference_test_config(),                       # helpers.rs:8-44 (hd=16, GQA 4:2)
     "ref_tiny_qknorm": lambda: reference_test_config(use_qk_norm=True),  # test_blocks.rs:920-933
     "ref_tiny_bias": lambda: reference_test_config(use_qkv_bias=True),   # test_attention.rs bias case

@@ -195,6 +195,10 @@ def test_gpu_master_loads_from_disk(tmp_path):
     got, vb = open_model(str(tmp_path))
     from_disk, from_memory = run(got, vb), run(cfg, sd)
     assert len(from_disk) == 12 and from_disk == from_memory
+    # ... and both are the ORACLE's greedy tokens for the checkpoint read back from disk (not only self-consistent)
+    from oracle.oracle import OracleModel
+    want = list(OracleModel(got, vb, "bf16", max_seq=64).generate(prompt, 12)[0])
+    assert from_disk == want
 
 
 def test_wrong_shapes_are_refused_before_anything_is_copied():

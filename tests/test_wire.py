@@ -349,6 +349,13 @@ def test_gpu_worker_behind_the_wire_equals_local_blocks():
         blks = [blocks[n] for n, _, _ in batch]
         y_local = blks[0].forward_batch(ctx.to_device(x), batch, ctx, blocks=blks)
         ctx.sync()
+        # the oracle's layers 2-3 on the same input: what travels over the wire is checked against the checker, not
+        # only against the same kernels run in-process
+        from oracle import oracle as O
+        from tests.util import max_ulp_err
+        om = O.OracleModel(cfg, sd, "bf16", max_seq=64)
+        y_ref = om.forward_layers(x[0].float().numpy(), 2, 4, 0, om.new_cache(64))
+        assert max_ulp_err(y_local[0].float().cpu().numpy(), y_ref, "bf16") <= 3.0
         y_local = y_local.cpu().view(torch.uint16).numpy()
         ctx.cache.clear()
         w = WireWorker(B200Backend(ctx, blocks)).start()
@@ -462,6 +469,8 @@ def test_gpu_master_with_tcp_worker_generates_the_same_tokens(tmp_path):
         got = Master(model).generate_text(prompt, 10)["tokens"]
         model.goodbye()
         assert got == want and len(clients) == 2 and w.connections == 2
+        from oracle import oracle as O   # the split run equals the oracle's tokens, not just the unsplit CUDA run
+        assert got == list(O.OracleModel(cfg, sd, "bf16", max_seq=64).generate(prompt, 10)[0])
     finally:
         for c in clients:
             c.close()

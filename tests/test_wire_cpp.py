@@ -191,6 +191,14 @@ def test_gpu_cpp_worker_equals_local_blocks(tmp_path):
         step = [(cfg.layer_name(i), 5, i) for i in (2, 3)]
         y1_local = blks[0].forward_batch(ctx.to_device(x1), step, ctx, blocks=blks)
         ctx.sync()
+        # both results against the oracle's layers 2-3 (prefill of 5, then the decode step at position 5)
+        from oracle import oracle as O
+        from tests.util import max_ulp_err
+        om = O.OracleModel(cfg, sd, "bf16", max_seq=64)
+        oc = om.new_cache(64)
+        assert max_ulp_err(torch.from_numpy(y_local.copy()).view(torch.bfloat16)[0].float().numpy(),
+                           om.forward_layers(x[0].float().numpy(), 2, 4, 0, oc), "bf16") <= 3.0
+        assert max_ulp_err(y1_local[0].float().cpu().numpy(), om.forward_layers(x1[0].float().numpy(), 2, 4, 5, oc), "bf16") <= 3.0
         y1_local = y1_local.cpu().view(torch.uint16).numpy()
     finally:
         ctx.close()
