@@ -20,7 +20,8 @@ Besides the headline metric the line carries (N = 1 unless noted):
   parity     the first decoded tokens / logits of this very model checked against the oracle (every N), and the
              sha256 of all W+K greedy tokens — identical for every N because the kernels are order-deterministic
   config0    BASELINE configs[0]: Qwen3-0.6B (f16) greedy 32 tokens, GPU tok/s beside the oracle port on the host
-  config3    BASELINE configs[3]: Llama-3-70B bf16 sharded over the 8 GPUs (only when N = 8, or --model 70b)
+  config3    BASELINE configs[3]: Llama-3-70B bf16 sharded over the 8 GPUs (only when N = 8, or --model 70b);
+             config3_one_gpu at N = 1: the same model on ONE B200 (139 GB of weights fit its 180 GB)
   config4    BASELINE configs[4]: Llama-3-8B bs=32 x 4096 prefill with its own tensor-bound roofline object
 """
 from __future__ import annotations
@@ -312,7 +313,7 @@ def run_reference(args):
         "e2e": {"value": res["value"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "host": res["host"],
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -893,7 +894,7 @@ def run_cuda(args):
         if rank == 0:
             line = prefill_leg(env, reps=max(1, min(args.steps, 5)))
             line.update({"n_gpus": 1, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic"})
-            print(json.dumps(line), flush=True)
+            emit(line)
         return
     parity = not args.no_parity and args.model == "8b"
     line = decode_leg(env, args.model, K, W, args.e2e_steps, parity=parity, isolated=(world == 1 and not args.no_isolated),
@@ -901,7 +902,7 @@ def run_cuda(args):
     # ---- further BASELINE configs riding on the same line -------------------------------------------------------
     if extras != "none" and args.model == "8b":
         if world == 8 or (extras == "all" and world > 1):
-            guard = threading.Timer(420.0, lambda: (rank == 0 and print(json.dumps(line), flush=True), os._exit(0)))
+            guard = threading.Timer(420.0, lambda: (rank == 0 and emit(line), os._exit(0)))
             guard.daemon = True
             guard.start()       # a hung 70B leg must not cost the 8B line
             try:
@@ -916,18 +917,43 @@ def run_cuda(args):
                     line["config3"] = {"error": str(e)}
             guard.cancel()
         if world == 1 and rank == 0:
+            try:  # 139 GB of bf16 weights + KV fit one 180 GB B200: the 70B model without the pipeline (context for config3)
+                c3 = decode_leg(env, "70b", min(K, 16), 3, 4, parity=False, isolated=False, cpu_leg=False)
+                line["config3_one_gpu"] = {k: c3[k] for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "config", "e2e",
+                                                              "gpu_launches", "roofline", "token_roofline", "tokens_sha") if k in c3}
+                line["config3_one_gpu"]["frac_of_single_stream_ceiling"] = c3["value"] / c3["token_roofline"]["roofline_tok_s_single_stream"]
+            except Exception as e:  # noqa: BLE001
+                line["config3_one_gpu"] = {"error": f"{type(e).__name__}: {e}"}
             for name, fn in (("config0", config0_leg), ("config4", prefill_leg)):
                 try:
                     line[name] = fn(env)
                 except Exception as e:  # noqa: BLE001
                     line[name] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
     if env.sampler:
         env.sampler.close()
     if world > 1:
         env.dist.barrier()
         env.dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, warnings): route fd 1
+    to stderr for the whole run and keep a private handle for the result line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -945,6 +971,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the first tokens")
     ap.add_argument("--no-isolated", action="store_true", help="skip the stand-alone per-op kernel timings")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

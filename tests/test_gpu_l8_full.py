@@ -121,10 +121,17 @@ def test_llama3_8b_all_32_layers_decode_at_2k_context_matches_oracle():
         gpu_toks.append(int(nxt.value))
         ref_toks.append(ref_tok)
         tok_in = ref_tok   # teacher-forced on the oracle's sequence so that later steps stay comparable
-    # the appended K/V rows of the last layer are the oracle's too
-    k, v = ctx.cache.kv(nl - 1)
-    ko, vo = oc.kv(nl - 1)
+    # the K/V rows appended during the free-running steps: layer 0's depend on the embedding row only (same bar as a
+    # single block); the last layer's inherit the hidden-state drift of 31 layers and are held to the logits' bar
+    k, v = ctx.cache.kv(0)
+    ko, vo = oc.kv(0)
     assert max_ulp_err(to_np(k[0][:, CTX_LEN:CTX_LEN + n_steps]), ko[:, CTX_LEN:CTX_LEN + n_steps], "bf16") <= 2.0
     assert max_ulp_err(to_np(v[0][:, CTX_LEN:CTX_LEN + n_steps]), vo[:, CTX_LEN:CTX_LEN + n_steps], "bf16") <= 2.0
+    k, v = ctx.cache.kv(nl - 1)
+    ko, vo = oc.kv(nl - 1)
+    ek = max_ulp_err(to_np(k[0][:, CTX_LEN:CTX_LEN + n_steps]), ko[:, CTX_LEN:CTX_LEN + n_steps], "bf16")
+    ev = max_ulp_err(to_np(v[0][:, CTX_LEN:CTX_LEN + n_steps]), vo[:, CTX_LEN:CTX_LEN + n_steps], "bf16")
+    print(f"appended K/V rows of layer {nl - 1} after 31 layers of drift: {ek:.2f} / {ev:.2f} ulp (bar {bar:.2f})")
+    assert ek <= bar and ev <= bar
     print(f"L8 x 32 layers @ {CTX_LEN}: tokens gpu {gpu_toks} oracle {ref_toks}, worst logits error {worst:.2f} ulp")
     ctx.close()
