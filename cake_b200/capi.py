@@ -59,6 +59,17 @@ SYMBOLS = [
 ]
 
 
+class CSampling(ctypes.Structure):
+    """``cake_b200_sampling`` (include/cake_b200.h)."""
+    _fields_ = [("kind", c_int), ("top_k", c_int), ("temperature", c_float), ("top_p", c_float), ("seed", c_uint64)]
+
+
+SYMBOLS += [
+    ("cake_b200_sample", _I, [_VP, _VP, POINTER(CSampling), c_float, POINTER(c_uint32), _I, c_uint64, POINTER(c_float), POINTER(c_uint32)]),
+    ("cake_b200_decode_set_sampling", _I, [_VP, POINTER(CSampling)]),
+]
+
+
 class CakeB200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"cake_b200 error {code}: {msg}")

@@ -24,6 +24,7 @@
 #include "gemm_tc.cuh"
 #include "gemv.cuh"
 #include "prefill.cuh"
+#include "sample.cuh"
 
 using namespace cake;
 typedef __nv_bfloat16 bf16;
@@ -110,6 +111,8 @@ struct cake_b200_ctx {
   int *part_idx = nullptr, *d_step = nullptr;
   unsigned *attn_counters = nullptr, *argmax_counter = nullptr;
   uint32_t *d_token = nullptr, *token_ring = nullptr, *d_ids = nullptr, *d_pen = nullptr;
+  float *samp_p = nullptr, *samp_noise = nullptr;  // sampler scratch: probabilities (vocab) / supplied uniforms
+  cake_b200_sampling sampling{};                   // sampler of the decode graph (kind 0 = greedy)
   size_t d_ids_cap = 0, d_pen_cap = 0;
   uint32_t *h_pin = nullptr;  // pinned staging (tokens)
   void *h_pin_x = nullptr;
@@ -429,7 +432,8 @@ extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
   void *bufs[] = {c->cos_t, c->sin_t, c->embed, c->ln_f, c->xa, c->xb, c->qkv, c->y, c->mm, c->logits, c->ws_ml,
                   c->ws_acc, c->part_val, c->part_idx, c->d_step, c->attn_counters, c->argmax_counter, c->d_token,
                   c->token_ring, c->d_ids, c->d_pen, c->pf_h, c->pf_qkv, c->pf_y, c->pf_x1, c->pf_gu, c->pf_mm, c->io_x,
-                  c->gbar, c->mk_tab_dev, c->g_tab_dev, c->tickets, c->ring_seq, c->inbox, c->step_trace, c->trace};
+                  c->gbar, c->mk_tab_dev, c->g_tab_dev, c->tickets, c->ring_seq, c->inbox, c->step_trace, c->trace,
+                  c->samp_p, c->samp_noise};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (c->lm_head && c->lm_head != c->embed) cudaFree(c->lm_head);
@@ -1095,33 +1099,12 @@ extern "C" int cake_b200_logits(cake_b200_ctx *c, const void *x_dev, int batch, 
   return CAKE_B200_OK;
 }
 
+static int apply_repeat_penalty(cake_b200_ctx *c, void *logits_dev, float penalty, const uint32_t *ctx_tokens_host, int n_tokens);
 extern "C" int cake_b200_repeat_penalty_argmax(cake_b200_ctx *c, void *logits_dev, float penalty,
                                                const uint32_t *ctx_tokens_host, int n_tokens, uint32_t *argmax_host) {
   if (!c || !logits_dev || !argmax_host) return fail(CAKE_B200_EINVAL, "null argument");
   CU(cudaSetDevice(c->device));
-  // text_model.rs:66-72: de-duplicate, keeping first occurrences
-  std::vector<uint32_t> uniq;
-  for (int i = 0; i < n_tokens; i++) {
-    bool dup = false;
-    for (uint32_t u : uniq) dup |= (u == ctx_tokens_host[i]);
-    if (!dup) uniq.push_back(ctx_tokens_host[i]);
-  }
-  if (!uniq.empty() && penalty != 1.0f) {
-    if (uniq.size() > c->d_pen_cap) {
-      CU(cudaStreamSynchronize(c->stream));
-      if (c->d_pen) cudaFree(c->d_pen);
-      CU(cudaMalloc(&c->d_pen, uniq.size() * 4));
-      c->d_pen_cap = uniq.size();
-    }
-    CU(cudaMemcpyAsync(c->d_pen, uniq.data(), uniq.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));  // uniq is a stack-owned pageable buffer
-    RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
-      typedef typename decltype(tag_)::type T;
-      repeat_penalty_kernel<T><<<(unsigned)((uniq.size() + 127) / 128), 128, 0, c->stream>>>((T *)logits_dev, c->cfg.vocab, penalty, c->d_pen, (int)uniq.size());
-      return CAKE_B200_OK;
-    }));
-    c->launches++;
-  }
+  RC(apply_repeat_penalty(c, logits_dev, penalty, ctx_tokens_host, n_tokens));
   RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
       typedef typename decltype(tag_)::type T;
     argmax_kernel<T><<<1, 1024, 0, c->stream>>>((const T *)logits_dev, c->cfg.vocab, c->d_token);
@@ -1131,6 +1114,86 @@ extern "C" int cake_b200_repeat_penalty_argmax(cake_b200_ctx *c, void *logits_de
   CU(cudaMemcpyAsync(c->h_pin, c->d_token, 4, cudaMemcpyDeviceToHost, c->stream));
   CU(cudaStreamSynchronize(c->stream));
   *argmax_host = c->h_pin[0];
+  return CAKE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ samplers (sample.cuh)
+static int check_sampling(const cake_b200_ctx *c, const cake_b200_sampling *s) {
+  if (s->kind < 0 || s->kind > 5) return fail(CAKE_B200_EINVAL, "sampling kind %d unknown (0..5)", s->kind);
+  if ((s->kind == SAMPLE_TOPK || s->kind == SAMPLE_TOPK_TOPP) && (s->top_k < 1 || (s->top_k > SAMPLE_MAX_K && s->top_k < c->cfg.vocab)))
+    return fail(CAKE_B200_EINVAL, "top_k %d unsupported (1..%d, or >= vocab)", s->top_k, SAMPLE_MAX_K);
+  return CAKE_B200_OK;
+}
+static int samp_reserve(cake_b200_ctx *c) {
+  if (!c->samp_p) CU(cudaMalloc(&c->samp_p, (size_t)c->cfg.vocab * 4 + 16));
+  return CAKE_B200_OK;
+}
+static SampleArgs to_args(const cake_b200_sampling &s) { return SampleArgs{s.kind, s.top_k, s.temperature, s.top_p, (unsigned long long)s.seed}; }
+
+static int apply_repeat_penalty(cake_b200_ctx *c, void *logits_dev, float penalty, const uint32_t *ctx_tokens_host, int n_tokens) {
+  // text_model.rs:66-72: de-duplicate, keeping first occurrences
+  std::vector<uint32_t> uniq;
+  for (int i = 0; i < n_tokens; i++) {
+    bool dup = false;
+    for (uint32_t u : uniq) dup |= (u == ctx_tokens_host[i]);
+    if (!dup) uniq.push_back(ctx_tokens_host[i]);
+  }
+  if (uniq.empty() || penalty == 1.0f) return CAKE_B200_OK;
+  if (uniq.size() > c->d_pen_cap) {
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->d_pen) cudaFree(c->d_pen);
+    CU(cudaMalloc(&c->d_pen, uniq.size() * 4));
+    c->d_pen_cap = uniq.size();
+  }
+  CU(cudaMemcpyAsync(c->d_pen, uniq.data(), uniq.size() * 4, cudaMemcpyHostToDevice, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // uniq is a stack-owned pageable buffer
+  RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+    typedef typename decltype(tag_)::type T;
+    repeat_penalty_kernel<T><<<(unsigned)((uniq.size() + 127) / 128), 128, 0, c->stream>>>((T *)logits_dev, c->cfg.vocab, penalty, c->d_pen, (int)uniq.size());
+    return CAKE_B200_OK;
+  }));
+  c->launches++;
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_sample(cake_b200_ctx *c, void *logits_dev, const cake_b200_sampling *s, float repeat_penalty,
+                                const uint32_t *ctx_tokens_host, int n_tokens, uint64_t step, const float *noise_host,
+                                uint32_t *token_host) {
+  if (!c || !logits_dev || !s || !token_host || n_tokens < 0 || (n_tokens > 0 && !ctx_tokens_host)) return fail(CAKE_B200_EINVAL, "null argument");
+  RC(check_sampling(c, s));
+  CU(cudaSetDevice(c->device));
+  RC(samp_reserve(c));
+  RC(apply_repeat_penalty(c, logits_dev, repeat_penalty, ctx_tokens_host, n_tokens));
+  const float *noise_dev = nullptr;
+  if (noise_host) {
+    const size_t n = (s->kind == SAMPLE_GUMBEL) ? (size_t)c->cfg.vocab : 1;
+    if (!c->samp_noise) CU(cudaMalloc(&c->samp_noise, (size_t)c->cfg.vocab * 4 + 16));
+    CU(cudaMemcpyAsync(c->samp_noise, noise_host, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    noise_dev = c->samp_noise;
+  }
+  set_int_kernel<<<1, 1, 0, c->stream>>>((int *)(c->samp_p + c->cfg.vocab), (int)(step & 0x7fffffff));  // the draw's counter
+  RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+    typedef typename decltype(tag_)::type T;
+    sample_kernel<T><<<1, SAMPLE_THREADS, 0, c->stream>>>((const T *)logits_dev, c->cfg.vocab, to_args(*s), c->samp_p, noise_dev,
+                                                          (const int *)(c->samp_p + c->cfg.vocab), 0, c->d_token, nullptr, 1);
+    return CAKE_B200_OK;
+  }));
+  c->launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(c->h_pin, c->d_token, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  *token_host = c->h_pin[0];
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_decode_set_sampling(cake_b200_ctx *c, const cake_b200_sampling *s) {
+  if (!c) return fail(CAKE_B200_EINVAL, "null argument");
+  if (!s) { c->sampling = cake_b200_sampling{}; return CAKE_B200_OK; }
+  RC(check_sampling(c, s));
+  CU(cudaSetDevice(c->device));
+  RC(samp_reserve(c));  // no allocation inside the graph capture of decode_build
+  c->sampling = *s;
   return CAKE_B200_OK;
 }
 
@@ -1250,6 +1313,15 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
           h.a.has_head = 1; h.a.advance = 1; h.a.token_ring = c->token_ring; h.a.trace_tag = 1;
           if (p2p) { h.a.inbox_ctr = inbox_ctr; h.a.ring_seq = c->ring_seq; }
           RC(launch_mega(c, h));
+        }
+        if (c->sampling.kind != SAMPLE_ARGMAX && c->sampling.temperature > 0.f) {
+          // non-greedy: a sampler kernel behind the decode kernel re-draws the token from the logits it left behind
+          // (256 KB, L2-hot) and overwrites d_token / the ring slot of this step; the step counter was already advanced
+          RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+            typedef typename decltype(tag_)::type T;
+            return launch_pdl(c, sample_kernel<T>, dim3(1), dim3(SAMPLE_THREADS), 0, (const T *)c->logits, c->cfg.vocab, to_args(c->sampling),
+                              c->samp_p, (const float *)nullptr, (const int *)c->d_step, -1, c->d_token, c->token_ring, (int)TOKEN_RING);
+          }));
         }
       } else {
         if (!p2p) RC(cake_b200_recv(c, c->xa, xbytes, rank - 1));

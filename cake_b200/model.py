@@ -244,8 +244,12 @@ class Token:
 class TextModelBase:
     """text_model.rs:133-530 for token-id prompts (tokenizer / chat template stay in the caller)."""
 
-    def __init__(self, ctx: Context, blocks: List[Forwarder], repeat_penalty: float = 1.0, repeat_last_n: int = 128):
+    def __init__(self, ctx: Context, blocks: List[Forwarder], repeat_penalty: float = 1.0, repeat_last_n: int = 128,
+                 temperature: float = 0.0, top_k: Optional[int] = None, top_p: Optional[float] = None, seed: int = 299792458):
+        """temperature / top_k / top_p / seed: the reference's Args that create_logits_processor reads
+        (text_model.rs:102-118): temperature <= 0 -> ArgMax, else GumbelSoftmax | TopK | TopP | TopKThenTopP."""
         self.ctx, self.blocks = ctx, blocks
+        self.sampling = sampling_from_args(temperature, top_k, top_p, seed)
         self.tokens: List[int] = []
         self.index_pos = 0
         self.generated = 0
@@ -327,7 +331,11 @@ class TextModelBase:
             gen = self.tokens[self.prompt_len:]
             pen = gen[max(0, len(gen) - self.repeat_last_n):]
         arr = (c_uint32 * max(1, len(pen)))(*pen)
-        check(lib().cake_b200_repeat_penalty_argmax(self.ctx.h, ptr(logits), self.repeat_penalty, arr, len(pen), byref(out)))
+        if self.sampling.kind == 0:
+            check(lib().cake_b200_repeat_penalty_argmax(self.ctx.h, ptr(logits), self.repeat_penalty, arr, len(pen), byref(out)))
+        else:  # the sampled token is drawn on the device: only 4 bytes come back (never the 256 KB of logits)
+            check(lib().cake_b200_sample(self.ctx.h, ptr(logits), byref(self.sampling), self.repeat_penalty, arr, len(pen),
+                                         self.generated, None, byref(out)))
         self.last_logits = logits
         tok = int(out.value)
         self.generated += 1
@@ -351,6 +359,9 @@ class TextModelBase:
 
     def decode_build(self, rank: int = 0, world: int = 1, blocks: Optional[List[B200Transformer]] = None,
                      block_idx: Optional[List[int]] = None) -> None:
+        if rank == 0 and (self.sampling.kind != 0 or getattr(self, "_sampling_set", False)):
+            check(lib().cake_b200_decode_set_sampling(self.ctx.h, byref(self.sampling)))
+            self._sampling_set = True
         if blocks is None:
             hs, idx = self.local_handles()
             n = len(self.blocks)
@@ -373,6 +384,21 @@ class TextModelBase:
         self.tokens.extend(toks)
         self.generated += n_steps
         return toks
+
+
+def sampling_from_args(temperature: float, top_k: Optional[int], top_p: Optional[float], seed: int) -> "capi.CSampling":
+    """text_model.rs:102-118 create_logits_processor."""
+    if temperature is None or temperature <= 0.0:
+        kind = 0
+    elif top_k is None and top_p is None:
+        kind = 5
+    elif top_p is None:
+        kind = 2
+    elif top_k is None:
+        kind = 3
+    else:
+        kind = 4
+    return capi.CSampling(kind, int(top_k or 0), float(temperature or 0.0), float(top_p or 0.0), int(seed))
 
 
 def _topology_owner(topology: dict, layer_name: str) -> Optional[str]:

@@ -158,6 +158,29 @@ int cake_b200_decode_tokens(cake_b200_ctx *, uint32_t *out_host, int n);   /* la
 int cake_b200_decode_step_host(cake_b200_ctx *, uint32_t token_in, uint32_t *token_out);
 int cake_b200_decode_logits(cake_b200_ctx *, void *logits_host, size_t bytes); /* logits (vocab) of the last step, D; synchronises */
 
+/* ---- sampling on the device (text_model.rs:102-118 create_logits_processor, :429-460) ------------------------------
+ * The reference picks a candle_transformers::generation::Sampling from (temperature, top_k, top_p): temperature <= 0
+ * -> ArgMax; else (None, None) -> GumbelSoftmax, (k, None) -> TopK, (None, p) -> TopP, (k, p) -> TopKThenTopP ("All" =
+ * plain multinomial is what TopK/TopP degrade to for k >= vocab / p outside (0,1)).  Only the 4-byte token leaves the GPU.
+ * kind: 0 ArgMax, 1 All, 2 TopK, 3 TopP, 4 TopKThenTopP, 5 GumbelSoftmax.  top_k <= 1024. */
+typedef struct cake_b200_sampling {
+  int kind, top_k;
+  float temperature, top_p;
+  uint64_t seed; /* LogitsProcessor::from_sampling(seed, ..): keys a counter-based Philox stream (candle's own RNG stream
+                    cannot be reproduced; see csrc/sample.cuh) */
+} cake_b200_sampling;
+/* next_token's tail in one call: repeat penalty over ctx_tokens_host (text_model.rs:60-99; skipped when penalty == 1 or
+ * n_tokens == 0, applied IN PLACE to logits_dev), then one draw.  `step` selects the random numbers of this draw;
+ * noise_host (nullable) supplies the uniforms in [0,1) instead — vocab floats for GumbelSoftmax, one float otherwise
+ * (how the parity tests pin the arithmetic).  Synchronises. */
+int cake_b200_sample(cake_b200_ctx *, void *logits_dev, const cake_b200_sampling *, float repeat_penalty,
+                     const uint32_t *ctx_tokens_host, int n_tokens, uint64_t step, const float *noise_host,
+                     uint32_t *token_host);
+/* Sampler of the graph-captured decode loop (call before cake_b200_decode_build; NULL or kind 0 = greedy, the default):
+ * a sampler kernel runs behind the decode kernel of rank 0, reads the logits it left in HBM/L2 and overwrites the greedy
+ * token; the draw of step s uses (seed, s).  No repeat penalty inside the graph. */
+int cake_b200_decode_set_sampling(cake_b200_ctx *, const cake_b200_sampling *);
+
 /* ---- measurement aid (bench.py roofline leg) ---------------------------------------------------- */
 /* Times ONE of the decode kernels of the given blocks in isolation with CUDA events on the ctx stream:
  * `reps` rounds over the blocks, back to back (which: 0 qkv GEMV, 1 o_proj GEMV, 2 gate_up GEMV,

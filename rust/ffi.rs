@@ -74,6 +74,20 @@ extern "C" {
     pub fn cake_b200_bench_kernel(ctx: *mut cake_b200_ctx, blocks: *const *mut cake_b200_block, block_idx: *const c_int,
         n_blocks: c_int, cache: *mut cake_b200_cache, which: c_int, reps: c_int, ms_per_launch: *mut f32) -> c_int;
     pub fn cake_b200_decode_trace(ctx: *mut cake_b200_ctx, out_host: *mut u64, n_steps: c_int) -> c_int;
+    pub fn cake_b200_sample(ctx: *mut cake_b200_ctx, logits_dev: *mut c_void, sampling: *const cake_b200_sampling, repeat_penalty: f32,
+        ctx_tokens_host: *const u32, n_tokens: c_int, step: u64, noise_host: *const f32, token_host: *mut u32) -> c_int;
+    pub fn cake_b200_decode_set_sampling(ctx: *mut cake_b200_ctx, sampling: *const cake_b200_sampling) -> c_int;
+}
+
+/// `cake_b200_sampling` (include/cake_b200.h): the Sampling enum of candle_transformers::generation flattened.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct cake_b200_sampling {
+    pub kind: c_int,
+    pub top_k: c_int,
+    pub temperature: f32,
+    pub top_p: f32,
+    pub seed: u64,
 }
 
 /// `anyhow!(cake_b200_last_error())` — the library stringifies failures with context the same way
