@@ -50,6 +50,9 @@ class Config:
     sliding_window: Optional[int] = None
     fused_qkv_proj: bool = False      # Phi-3/4: one 'qkv_proj' tensor = cat(q, k, v) (attention.rs:90-94)
     fused_gate_up_proj: bool = False  # Phi-3/4: one 'gate_up_proj' tensor = cat(gate, up) (mlp.rs:38-40)
+    use_gelu_mlp: bool = False        # config.rs:133: gelu_tanh(gate) * up (mlp.rs:25-26)
+    embed_scale: Optional[float] = None   # config.rs:136: embeddings scaled before the blocks (text_model.rs:274-276)
+    residual_rms_norm: bool = False   # config.rs:113: norm weights stored as deltas; (1 + w) in f32 at LOAD time (config.rs:155-173)
 
     @property
     def hd(self) -> int:
@@ -174,16 +177,15 @@ class CConfig(ctypes.Structure):
         ("rope_factor", ctypes.c_float), ("rope_low", ctypes.c_float), ("rope_high", ctypes.c_float),
         ("rope_orig_max", ctypes.c_int),
         ("dtype", ctypes.c_int),
+        ("sliding_window", ctypes.c_int), ("use_gelu_mlp", ctypes.c_int), ("embed_scale", ctypes.c_float),
     ]
 
     @staticmethod
     def from_config(c: Config, dtype: str = "bf16", max_seq: Optional[int] = None) -> "CConfig":
         rs = c.rope_scaling
         llama3 = bool(rs and rs.rope_type == "llama3" and rs.original_max_position_embeddings > 0)
-        if c.sliding_window and c.sliding_window < (max_seq or c.max_seq_len):
-            # cache.rs:173-205 trims K/V to the window; the cache here is append-only
-            raise ValueError(f"sliding_window={c.sliding_window} < max_seq={max_seq or c.max_seq_len}: the windowed "
-                             "KV trim (cache.rs:173-205) is not built; cap max_seq at the window")
+        # cache.rs:173-205 limit = min(window, max_seq_len); a window that never bites is passed as 0
+        win = int(c.sliding_window) if (c.sliding_window and c.sliding_window < (max_seq or c.max_seq_len)) else 0
         return CConfig(
             c.hidden_size, c.intermediate_size, c.num_attention_heads, c.num_key_value_heads, c.hd,
             c.num_hidden_layers, c.vocab_size, max_seq or c.max_seq_len,
@@ -193,6 +195,7 @@ class CConfig(ctypes.Structure):
             rs.factor if llama3 else 1.0, rs.low_freq_factor if llama3 else 1.0,
             rs.high_freq_factor if llama3 else 4.0, rs.original_max_position_embeddings if llama3 else 0,
             DTYPES[dtype],
+            win, int(c.use_gelu_mlp), float(c.embed_scale or 0.0),
         )
 
 

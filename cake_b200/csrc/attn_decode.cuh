@@ -37,6 +37,7 @@ struct AttnDecodeArgs {
   const int *d_pos;     // device-resident position of this token (== cache length before append)
   int n_heads, n_kv, cap, rot, nsplit;
   float eps, scale;
+  int window;  // cache.rs:173-205 sliding window (0 = full context)
 };
 
 __host__ __device__ inline size_t attn_smem_bytes(int hd, int es) {
@@ -108,18 +109,20 @@ __global__ void __launch_bounds__(ATTN_THREADS) attn_decode_kernel(const AttnDec
   pdl_launch_dependents();
   pdl_wait();
 
-  const int pos = *a.d_pos;
-  const int Tn = pos + 1;  // KV length after the append
+  const int apos = *a.d_pos;  // absolute position (RoPE); the cache row indices below are relative to the window start
+  const int ws = (a.window > 0 && apos + 1 > a.window) ? apos + 1 - a.window : 0;  // cache.rs:173-205
+  const int pos = apos - ws;
+  const int Tn = pos + 1;  // visible KV length after the append
   int per = (Tn + a.nsplit - 1) / a.nsplit;
   per = (per + 7) & ~7;
   const int s0 = min(Tn, split * per), s1 = min(Tn, s0 + per);
   const bool owner = (pos >= s0 && pos < s1);
 
   const T *qkv = reinterpret_cast<const T *>(a.qkv);
-  const T *cosr = reinterpret_cast<const T *>(a.cos_t) + (size_t)pos * (a.rot / 2);
-  const T *sinr = reinterpret_cast<const T *>(a.sin_t) + (size_t)pos * (a.rot / 2);
-  T *kc = reinterpret_cast<T *>(a.kcache) + (size_t)kvh * a.cap * HD;
-  T *vc = reinterpret_cast<T *>(a.vcache) + (size_t)kvh * a.cap * HD;
+  const T *cosr = reinterpret_cast<const T *>(a.cos_t) + (size_t)apos * (a.rot / 2);
+  const T *sinr = reinterpret_cast<const T *>(a.sin_t) + (size_t)apos * (a.rot / 2);
+  T *kc = reinterpret_cast<T *>(a.kcache) + ((size_t)kvh * a.cap + ws) * HD;
+  T *vc = reinterpret_cast<T *>(a.vcache) + ((size_t)kvh * a.cap + ws) * HD;
   __syncthreads();  // barrier init visible
 
   // ---- TMA: stage the first tile of cached K/V rows (everything except the row being appended) ------

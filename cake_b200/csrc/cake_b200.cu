@@ -106,7 +106,7 @@ struct cake_b200_ctx {
   // head
   void *embed = nullptr, *ln_f = nullptr, *lm_head = nullptr;
   // decode workspaces
-  void *xa = nullptr, *xb = nullptr, *qkv = nullptr, *y = nullptr, *mm = nullptr, *logits = nullptr;
+  void *xa = nullptr, *xb = nullptr, *x0 = nullptr, *qkv = nullptr, *y = nullptr, *mm = nullptr, *logits = nullptr;
   float *ws_ml = nullptr, *ws_acc = nullptr, *part_val = nullptr;
   int *part_idx = nullptr, *d_step = nullptr;
   unsigned *attn_counters = nullptr, *argmax_counter = nullptr;
@@ -373,6 +373,7 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
   if (c->nsplit > ATTN_MAX_SPLIT) c->nsplit = ATTN_MAX_SPLIT;
   CU(cudaMalloc(&c->xa, (size_t)H * 2));
   CU(cudaMalloc(&c->xb, (size_t)H * 2));
+  CU(cudaMalloc(&c->x0, (size_t)H * 2));
   CU(cudaMalloc(&c->qkv, (size_t)c->nqkv * 2));
   CU(cudaMalloc(&c->y, (size_t)nh * hd * 2));
   CU(cudaMalloc(&c->mm, (size_t)I * 2));
@@ -433,7 +434,7 @@ extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
                   c->ws_acc, c->part_val, c->part_idx, c->d_step, c->attn_counters, c->argmax_counter, c->d_token,
                   c->token_ring, c->d_ids, c->d_pen, c->pf_h, c->pf_qkv, c->pf_y, c->pf_x1, c->pf_gu, c->pf_mm, c->io_x,
                   c->gbar, c->mk_tab_dev, c->g_tab_dev, c->tickets, c->ring_seq, c->inbox, c->step_trace, c->trace,
-                  c->samp_p, c->samp_noise};
+                  c->samp_p, c->samp_noise, c->x0};
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (c->lm_head && c->lm_head != c->embed) cudaFree(c->lm_head);
@@ -651,6 +652,7 @@ static int enqueue_attn(cake_b200_ctx *c, const cake_b200_block *b, cake_b200_ca
   a.counters = c->attn_counters; a.d_pos = kc->d_pos; a.n_heads = f.n_heads; a.n_kv = f.n_kv_heads;
   a.cap = kc->cap; a.rot = c->rot; a.nsplit = c->nsplit; a.eps = f.rms_eps;
   a.scale = (float)(1.0 / sqrt((double)f.head_dim));
+  a.window = f.sliding_window;
   dim3 grid(c->nsplit, f.n_kv_heads), block(ATTN_THREADS);
   const size_t smem = attn_smem_bytes(f.head_dim, c->es);
   return DISPATCH_T(f.dtype, T_LAMBDA {
@@ -674,7 +676,7 @@ static int enqueue_oproj(cake_b200_ctx *c, const cake_b200_block *b, const void 
 static int enqueue_gate_up(cake_b200_ctx *c, const cake_b200_block *b, const void *x1) {
   // rms_2 + gate_up + silu*mul                                     transformer.rs:129, mlp.rs:22-28
   GemvArgs a{};
-  a.W = b->wgu; a.x = x1; a.norm_w = b->ln2; a.out = c->mm; a.eps = c->cfg.rms_eps; a.N = 2 * c->cfg.inter;
+  a.W = b->wgu; a.x = x1; a.norm_w = b->ln2; a.out = c->mm; a.eps = c->cfg.rms_eps; a.N = 2 * c->cfg.inter; a.act = c->cfg.use_gelu_mlp ? 1 : 0;
   a.K = c->cfg.hidden;
   return launch_gemv<EPI_SWIGLU>(c, a);
 }
@@ -775,6 +777,8 @@ static int plan_mega(cake_b200_ctx *c, cake_b200_cache *kc, bool with_head, MkPl
   a.trace = c->trace;
   a.step_trace = c->step_trace;
   a.trace_tag = 0;
+  a.act = f.use_gelu_mlp ? 1 : 0;
+  a.window = f.sliding_window;
   int ns = MK_MAX_STAGES;
   const size_t limit = 227 * 1024 - 4096;  // the kernel also has ~2.2 KB of static shared memory
   while (ns > 2 && mk_smem_bytes(a.max_k, pf, mg, ns, c->es) > limit) ns--;
@@ -897,7 +901,7 @@ static int gemm_tc_T(cake_b200_ctx *c, const void *A, const void *W, const void 
   CUtensorMap ma, mb;
   RC(make_tmap(&ma, A, (uint64_t)M, (uint64_t)K, c->cfg.dtype, TC_BM));
   RC(make_tmap(&mb, W, (uint64_t)N, (uint64_t)K, c->cfg.dtype, TC_BN));
-  TcParams p{bias, res, C, M, N, K};
+  TcParams p{bias, res, C, M, N, K, c->cfg.use_gelu_mlp ? 1 : 0};
   const int tiles = ((M + TC_BM - 1) / TC_BM) * (N / TC_BN);
   dim3 grid(tiles < c->sm_count ? tiles : c->sm_count), block(TC_THREADS);
   return launch_pdl(c, gemm_tc_kernel<T, EPI>, grid, block, (size_t)TC_SMEM_BYTES, ma, mb, p);
@@ -935,6 +939,16 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
   const cake_b200_config &f = c->cfg;
   const int H = f.hidden, I = f.inter, hd = f.head_dim, sq = f.n_heads * hd, M = B * S;
   RC(pf_reserve(c, (size_t)M));
+  // cache.rs:173-205: a call on a non-empty cache sees the last `window` positions of cat(cache, new) — every query of
+  // the chunk the same old rows [ws, pos0) — while the first call (pos0 == 0) attends over everything it stores.  The
+  // attention kernels only see row indices relative to ws (base pointers advanced by ws rows); K/V append is unaffected.
+  int ws = 0;
+  if (f.sliding_window > 0 && pos0 > 0 && pos0 + S > f.sliding_window) {
+    ws = pos0 + S - f.sliding_window;
+    if (ws > pos0) return fail(CAKE_B200_EINVAL, "a chunk of %d tokens on a non-empty cache exceeds the sliding window %d", S, f.sliding_window);
+  }
+  const size_t wsoff = (size_t)ws * hd;
+  const int apos0 = pos0 - ws;
   const char *env_tc = getenv("CAKE_B200_NO_TC");
   const bool use_tc = !(env_tc && env_tc[0] == '1');  // CAKE_B200_NO_TC=1: CUDA-core GEMM (A/B testing aid)
   return DISPATCH_T(f.dtype, T_LAMBDA {
@@ -957,15 +971,15 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
         const float sc = (float)(1.0 / sqrt((double)hd));
         if (hd == 128)
           RC(launch_pdl(c, attn_prefill_mma_kernel<T, 128>, grid, block, (size_t)5 * FA_BN * 128 * 2, (const T *)c->pf_qkv,
-                        (const T *)kc->k[l], (const T *)kc->v[l], (T *)c->pf_y, S, f.n_heads, f.n_kv_heads, kc->cap, pos0, sc));
+                        (const T *)kc->k[l] + wsoff, (const T *)kc->v[l] + wsoff, (T *)c->pf_y, S, f.n_heads, f.n_kv_heads, kc->cap, apos0, sc));
         else
           RC(launch_pdl(c, attn_prefill_mma_kernel<T, 64>, grid, block, (size_t)5 * FA_BN * 64 * 2, (const T *)c->pf_qkv,
-                        (const T *)kc->k[l], (const T *)kc->v[l], (T *)c->pf_y, S, f.n_heads, f.n_kv_heads, kc->cap, pos0, sc));
+                        (const T *)kc->k[l] + wsoff, (const T *)kc->v[l] + wsoff, (T *)c->pf_y, S, f.n_heads, f.n_kv_heads, kc->cap, apos0, sc));
       } else {
         const long items = (long)M * f.n_heads;
         RC(launch_pdl(c, attn_prefill_v0_kernel<T>, dim3((unsigned)((items + 3) / 4)), dim3(128), 0, (const T *)c->pf_qkv,
-                      (const T *)kc->k[l], (const T *)kc->v[l], (T *)c->pf_y, B, S, f.n_heads, f.n_kv_heads, hd, kc->cap,
-                      pos0, (float)(1.0 / sqrt((double)hd))));
+                      (const T *)kc->k[l] + wsoff, (const T *)kc->v[l] + wsoff, (T *)c->pf_y, B, S, f.n_heads, f.n_kv_heads, hd, kc->cap,
+                      apos0, (float)(1.0 / sqrt((double)hd))));
       }
       if (use_tc && tc_gemm_ok(M, H, sq)) RC((gemm_tc_T<T, TCE_RESIDUAL>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq)));
       else RC(gemm_T<T>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq));
@@ -974,7 +988,7 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
         RC((gemm_tc_T<T, TCE_SWIGLU>(c, c->pf_h, b->wgu, nullptr, nullptr, c->pf_mm, M, 2 * I, H)));
       } else {
         RC(gemm_T<T>(c, c->pf_h, b->wgu, nullptr, nullptr, c->pf_gu, M, 2 * I, H));
-        RC(launch_pdl(c, swiglu_rows_kernel<T>, dim3(c->sm_count * 4), dim3(256), 0, (const T *)c->pf_gu, (T *)c->pf_mm, (size_t)M * I));
+        RC(launch_pdl(c, swiglu_rows_kernel<T>, dim3(c->sm_count * 4), dim3(256), 0, (const T *)c->pf_gu, (T *)c->pf_mm, (size_t)M * I, f.use_gelu_mlp ? 1 : 0));
       }
       if (use_tc && tc_gemm_ok(M, H, I)) RC((gemm_tc_T<T, TCE_RESIDUAL>(c, c->pf_mm, b->wd, nullptr, c->pf_x1, x_out, M, H, I)));
       else RC(gemm_T<T>(c, c->pf_mm, b->wd, nullptr, c->pf_x1, x_out, M, H, I));
@@ -1075,7 +1089,7 @@ extern "C" int cake_b200_embed(cake_b200_ctx *c, const uint32_t *ids_host, int b
   RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
       typedef typename decltype(tag_)::type T;
     return launch_pdl(c, embed_kernel<T>, dim3((unsigned)n), dim3(128), 0, (const T *)c->embed, (const uint32_t *)c->d_ids,
-                      (T *)x_dev, (int)n, c->cfg.hidden, c->cfg.vocab);
+                      (T *)x_dev, (int)n, c->cfg.hidden, c->cfg.vocab, c->cfg.embed_scale);
   }));
   return CAKE_B200_OK;
 }
@@ -1298,6 +1312,14 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
       if (rank == 0) {
         RC(plan_mega(c, kc, world == 1, &p));
         p.a.layers = c->g_tab_dev; p.a.n_layers = n_blocks; p.a.x_in = nullptr; p.a.x_out = c->xa;
+        if (c->cfg.embed_scale != 0.f) {  // text_model.rs:274-276: the scaled embedding row is materialised first
+          RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
+            typedef typename decltype(tag_)::type T;
+            return launch_pdl(c, embed_kernel<T>, dim3(1), dim3(128), 0, (const T *)c->embed, (const uint32_t *)c->d_token,
+                              (T *)c->x0, 1, c->cfg.hidden, c->cfg.vocab, c->cfg.embed_scale);
+          }));
+          p.a.x_in = c->x0;
+        }
         p.a.has_head = (world == 1); p.a.advance = (world == 1); p.a.token_ring = c->token_ring;
         if (p2p) { p.a.x_out = peer_x; p.a.peer_ctr = peer_ctr; p.a.ring_seq = c->ring_seq; }
         if (n_blocks > 0 || world == 1) RC(launch_mega(c, p));
@@ -1339,7 +1361,7 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
       RC(DISPATCH_T(c->cfg.dtype, T_LAMBDA {
       typedef typename decltype(tag_)::type T;
         return launch_pdl(c, embed_kernel<T>, dim3(1), dim3(128), 0, (const T *)c->embed, (const uint32_t *)c->d_token,
-                          (T *)c->xa, 1, c->cfg.hidden, c->cfg.vocab);
+                          (T *)c->xa, 1, c->cfg.hidden, c->cfg.vocab, c->cfg.embed_scale);
       }));
     } else {
       RC(cake_b200_recv(c, c->xa, xbytes, rank - 1));

@@ -37,6 +37,14 @@ template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b
   return (uint32_t)(*reinterpret_cast<uint16_t *>(&x)) | ((uint32_t)(*reinterpret_cast<uint16_t *>(&y)) << 16);
 }
 
+// MLP gate activation, mlp.rs:21-31: act 0 = silu(gate) (cpu/mod.rs:87-89), act 1 = gelu_tanh(gate) (use_gelu_mlp: candle's
+// `gelu` is the tanh approximation); the activation is rounded to D before the multiplication by `up` (the caller rounds
+// the product): two roundings, as the reference's separate ops produce.
+template <typename T> __device__ __forceinline__ float gate_act(float g, int act) {
+  if (act) return rnd<T>(0.5f * g * (1.0f + tanhf(0.7978845608028654f * g * (1.0f + 0.044715f * g * g))));
+  return rnd<T>(g / (1.0f + expf(-g)));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

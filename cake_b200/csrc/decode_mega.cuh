@@ -75,6 +75,8 @@ struct MkArgs {
   // MK_STEP_RING steps x 2 launches (tag 0: the layer launch, tag 1: rank 0's head-only launch when sharded) x 4 u64
   unsigned long long *step_trace;
   int trace_tag;
+  int act;     // mlp.rs:25-26: 0 silu, 1 gelu_tanh
+  int window;  // cache.rs:173-205 sliding window (0 = full context): attention covers the last `window` positions
 };
 constexpr int MK_STEP_RING = 2048;
 __device__ __forceinline__ unsigned long long mk_gtime() {
@@ -285,10 +287,13 @@ __device__ __forceinline__ MkAttnItem mk_attn_item(const MkArgs &a, int pos) {
 
 template <typename T>
 __device__ __forceinline__ void mk_produce_attn(MkRing &rg, const MkArgs &a, const MkLayer &L, int pos, uint64_t pol) {
+  // sliding window: the visible rows start at ws = pos + 1 - window; everything below works on row indices relative to ws
+  const int ws = (a.window > 0 && pos + 1 > a.window) ? pos + 1 - a.window : 0;
+  pos -= ws;
   const MkAttnItem it = mk_attn_item<T>(a, pos);
   const int HD = a.hd;
-  const T *kc = reinterpret_cast<const T *>(L.kc) + (size_t)it.kvh * a.cap * HD;
-  const T *vc = reinterpret_cast<const T *>(L.vc) + (size_t)it.kvh * a.cap * HD;
+  const T *kc = reinterpret_cast<const T *>(L.kc) + ((size_t)it.kvh * a.cap + ws) * HD;
+  const T *vc = reinterpret_cast<const T *>(L.vc) + ((size_t)it.kvh * a.cap + ws) * HD;
   for (int t0 = it.s0; t0 < it.s1; t0 += it.tile) {
     const int t1 = min(it.s1, t0 + it.tile);
     const int nold = min(t1, pos) - t0;  // rows already in the cache (the appended row is handled by the consumers)
@@ -364,6 +369,7 @@ __device__ __forceinline__ void mk_stage_x(T *xs, const void *x, const void *nor
 struct MkEpi {
   const void *bias, *residual;
   void *out;
+  int act;  // EPI_SWIGLU: 0 silu, 1 gelu_tanh
   // argmax
   float *part_val;
   int *part_idx;
@@ -508,7 +514,7 @@ __device__ __forceinline__ void mk_consume_gemv(MkRing &rg, const MkGeom &g, con
       const int row = row_of(2 * p);
       if (row >= N) continue;
       const float gte = row_sum(2 * p), up = row_sum(2 * p + 1);
-      const float sl = rnd<T>(gte / (1.0f + expf(-gte)));
+      const float sl = gate_act<T>(gte, e.act);
       out[row / 2] = DT<T>::from_f(sl * up);
     }
   } else {
@@ -625,6 +631,9 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
   constexpr int RPWI = 32 / LPR;         // rows per warp per iteration
   constexpr int NW = MK_CW;
   static_assert(HD == 16 || HD == 64 || HD == 128, "head_dim");
+  // sliding window (cache.rs:173-205): rows below ws = pos + 1 - window are invisible; indices below are relative to ws
+  const int ws = (a.window > 0 && pos + 1 > a.window) ? pos + 1 - a.window : 0;
+  pos -= ws;
   const MkAttnItem it = mk_attn_item<T>(a, pos);
   float *q_s = reinterpret_cast<float *>(scr);             // [G][HD]
   float *sc = q_s + ATTN_MAX_G * 256;                      // [ATTN_TILE][G]  (position-major: one vector per position)
@@ -636,8 +645,8 @@ __device__ __forceinline__ void mk_consume_attn(MkRing &rg, const MkArgs &a, con
 
   const T *qkv = reinterpret_cast<const T *>(a.qkv);
   const float *cosr = rope_cs, *sinr = rope_cs + 128;  // this step's cos/sin row, staged once per launch
-  T *kc = reinterpret_cast<T *>(L.kc) + (size_t)it.kvh * a.cap * HD;
-  T *vc = reinterpret_cast<T *>(L.vc) + (size_t)it.kvh * a.cap * HD;
+  T *kc = reinterpret_cast<T *>(L.kc) + ((size_t)it.kvh * a.cap + ws) * HD;
+  T *vc = reinterpret_cast<T *>(L.vc) + ((size_t)it.kvh * a.cap + ws) * HD;
   const int kvh = it.kvh, split = it.split, s0 = it.s0, s1 = it.s1, TILE = it.tile;
   const bool owner = (pos >= s0 && pos < s1);
 
@@ -996,6 +1005,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) decode_mega_kernel(const MkArgs
     mk_stage_x<T>(xs, a.xb, L.ln2, a.hidden, a.eps, scratch, ct, warp, lane);
     e = MkEpi{};
     e.out = a.mm;
+    e.act = a.act;
     mk_consume_gemv<T, EPI_SWIGLU>(rg, a.g_gu, xs, partial, loc_row, scratch, e, ct, warp, lane);
     if (a.trace && l == 1 && ct == 0) {
       unsigned long long t;

@@ -34,6 +34,7 @@ struct TcParams {
   const void *residual;  // [M,N] D (TCE_RESIDUAL)
   void *C;               // [M,N] D  ([M,N/2] for TCE_SWIGLU)
   int M, N, K;
+  int act;  // TCE_SWIGLU: 0 silu, 1 gelu_tanh
 };
 
 // Tile rasterisation: groups of TC_GM m-tiles (16 x 128 rows = 16 MB of A at K=4096) are walked n-major, so the A
@@ -204,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
               for (int h = 0; h < 2; h++) {
                 const float g = rnd<T>(__uint_as_float(r[4 * j + 2 * h])), u = rnd<T>(__uint_as_float(r[4 * j + 2 * h + 1]));
-                const float sl = rnd<T>(g / (1.0f + expf(-g)));
+                const float sl = gate_act<T>(g, p.act);
                 v[h] = sl * u;
               }
               o[j] = pack2<T>(v[0], v[1]);

@@ -37,6 +37,7 @@ struct GemvArgs {
   void *out;             // [N] D  ([N/2] for EPI_SWIGLU)
   float eps;
   int N, K;
+  int act;  // EPI_SWIGLU: 0 silu, 1 gelu_tanh
   // stage geometry (host-planned, see plan_gemv): a stage holds RS row segments of KC columns; the 8
   // consumer warps form (8/WPR) row slots x WPR column slices; a warp covers RS/(8/WPR) rows per stage.
   int KC, RS, WPR;
@@ -244,7 +245,7 @@ __global__ void __launch_bounds__(GEMV_THREADS, 1) gemv_kernel(const GemvArgs a)
   } else if (EPI == EPI_SWIGLU) {
     for (int p = ct; p < nrows / 2; p += CT) {
       float gte = row_sum(2 * p), up = row_sum(2 * p + 1);
-      float sl = rnd<T>(gte / (1.0f + expf(-gte)));  // silu ->D (cpu/mod.rs:87-89)
+      float sl = gate_act<T>(gte, a.act);  // activation ->D (cpu/mod.rs:87-89 / mlp.rs:25-26)
       out[r0 / 2 + p] = DT<T>::from_f(sl * up);       // * up ->D
     }
   } else {  // EPI_ARGMAX: logits in D + greedy token, first maximum wins (text_model.rs:104-105)

@@ -78,12 +78,12 @@ __global__ void __launch_bounds__(256) gemm_v0_kernel(const T *__restrict__ A, c
 
 // ---- silu(gate)*up on the row-interleaved gate_up output: gu[m][2i]=gate_i, gu[m][2i+1]=up_i -------
 template <typename T>
-__global__ void swiglu_rows_kernel(const T *__restrict__ gu, T *__restrict__ out, size_t total /* M*I */) {
+__global__ void swiglu_rows_kernel(const T *__restrict__ gu, T *__restrict__ out, size_t total /* M*I */, int act) {
   pdl_launch_dependents();
   pdl_wait();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const float g = DT<T>::to_f(gu[2 * i]), u = DT<T>::to_f(gu[2 * i + 1]);
-    const float s = rnd<T>(g / (1.0f + expf(-g)));
+    const float s = gate_act<T>(g, act);
     out[i] = DT<T>::from_f(s * u);
   }
 }
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(128) attn_prefill_v0_kernel(const T *__restric
 // ---- embedding gather (backends/mod.rs:513-528) ---------------------------------------------------
 template <typename T>
 __global__ void embed_kernel(const T *__restrict__ E, const uint32_t *__restrict__ ids, T *__restrict__ x, int n_tok,
-                             int H, int vocab) {
+                             int H, int vocab, float scale /* text_model.rs:274-276 embed_scale; 0 = none */) {
   pdl_launch_dependents();
   pdl_wait();
   const int t = blockIdx.x;
@@ -212,7 +212,19 @@ __global__ void embed_kernel(const T *__restrict__ E, const uint32_t *__restrict
   if (id >= (uint32_t)vocab) id = 0;
   const uint4 *src = reinterpret_cast<const uint4 *>(E + (size_t)id * H);
   uint4 *dst = reinterpret_cast<uint4 *>(x + (size_t)t * H);
-  for (int i = threadIdx.x; i < H * (int)sizeof(T) / 16; i += blockDim.x) dst[i] = src[i];
+  if (scale == 0.f) {
+    for (int i = threadIdx.x; i < H * (int)sizeof(T) / 16; i += blockDim.x) dst[i] = src[i];
+  } else {  // `x * scale` in D: the scalar is rounded to D first (candle affine on a half tensor), one rounding of the product
+    const float sc = rnd<T>(scale);
+    for (int i = threadIdx.x; i < H * (int)sizeof(T) / 16; i += blockDim.x) {
+      float f[8];
+      unpack8<T>(src[i], f);
+      uint4 o;
+      o.x = pack2<T>(f[0] * sc, f[1] * sc); o.y = pack2<T>(f[2] * sc, f[3] * sc);
+      o.z = pack2<T>(f[4] * sc, f[5] * sc); o.w = pack2<T>(f[6] * sc, f[7] * sc);
+      dst[i] = o;
+    }
+  }
 }
 
 // ---- decode-loop bookkeeping ----------------------------------------------------------------------

@@ -202,9 +202,7 @@ struct Config {
     c.qkv_bias = ar->bias;
     if (ar->window) {
       const int w = (int)j.number("sliding_window", 0);  // null / absent -> 0
-      if (w > 0 && w < c.max_seq)  // cache.rs:173-205 trims K/V to the window; the cache here is append-only
-        throw Error("sliding_window=" + std::to_string(w) + " < max_seq=" + std::to_string(c.max_seq) +
-                    ": the windowed KV trim is not built; cap --max-seq at the window");
+      c.sliding_window = (w > 0 && w < c.max_seq) ? w : 0;  // cache.rs:173-205: limit = min(window, max_seq_len)
     }
     c.dtype = dtype;
     c.rope_factor = 1.f; c.rope_low = 1.f; c.rope_high = 4.f;

@@ -40,10 +40,10 @@ int main(int argc, char **argv) {
       Config k = Config::from_path(dir + "/config.json", dtype, max_seq);
       const auto &c = k.c;
       printf("arch=%s hidden=%d inter=%d heads=%d kv_heads=%d head_dim=%d layers=%d vocab=%d max_seq=%d rms_eps=%g "
-             "rope_theta=%g qkv_bias=%d qk_norm=%d tie=%d rope_llama3=%d n_eos=%zu partial_rotary=%g fused=%d\n",
+             "rope_theta=%g qkv_bias=%d qk_norm=%d tie=%d rope_llama3=%d n_eos=%zu partial_rotary=%g fused=%d sliding_window=%d\n",
              k.arch.c_str(), c.hidden, c.inter, c.n_heads, c.n_kv_heads, c.head_dim, c.n_layers, c.vocab, c.max_seq,
              (double)c.rms_eps, (double)c.rope_theta, c.qkv_bias, c.qk_norm, c.tie_embeddings, c.rope_llama3, k.eos.size(),
-             (double)c.partial_rotary, (int)(k.fused_qkv_proj && k.fused_gate_up_proj));
+             (double)c.partial_rotary, (int)(k.fused_qkv_proj && k.fused_gate_up_proj), c.sliding_window);
       return 0;
     }
     Context ctx(dir, 0, dtype, max_seq);

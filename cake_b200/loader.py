@@ -201,6 +201,14 @@ BLOCK_TENSORS = ("self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_att
                  "self_attn.q_norm.weight", "self_attn.k_norm.weight")
 
 
+def rms_norm_weight(t: torch.Tensor, cfg: Config) -> torch.Tensor:
+    """config.rs:155-173 load_rms_norm_weight: with ``residual_rms_norm`` the checkpoint stores deltas and the forward
+    weight is (1 + w), added in f32 and cast back to the model dtype AT LOAD TIME — the kernels never see the flag."""
+    if not cfg.residual_rms_norm:
+        return t
+    return (t.to(torch.float32) + 1.0).to(t.dtype)
+
+
 def block_tensors(vb, cfg: Config, name: str) -> Dict[str, Optional[torch.Tensor]]:
     """The tensors `Transformer::load` reads for layer ``name`` (transformer.rs:79-101, attention.rs:76-149,
     mlp.rs:34-59), by the short names of BLOCK_TENSORS, each checked against the shape the layer declares (candle's
@@ -234,15 +242,15 @@ def block_tensors(vb, cfg: Config, name: str) -> Dict[str, Optional[torch.Tensor
         out["mlp.gate_proj.weight"] = get("mlp.gate_proj.weight", (I, H))
         out["mlp.up_proj.weight"] = get("mlp.up_proj.weight", (I, H))
     out["mlp.down_proj.weight"] = get("mlp.down_proj.weight", (H, I))
-    out["input_layernorm.weight"] = get("input_layernorm.weight", (H,))
-    out["post_attention_layernorm.weight"] = get("post_attention_layernorm.weight", (H,))
+    out["input_layernorm.weight"] = rms_norm_weight(get("input_layernorm.weight", (H,)), cfg)
+    out["post_attention_layernorm.weight"] = rms_norm_weight(get("post_attention_layernorm.weight", (H,)), cfg)
     if cfg.use_qkv_bias:  # attention.rs:96-107 (never together with a fused qkv_proj)
         out["self_attn.q_proj.bias"] = get("self_attn.q_proj.bias", (sq,))
         out["self_attn.k_proj.bias"] = get("self_attn.k_proj.bias", (skv,))
         out["self_attn.v_proj.bias"] = get("self_attn.v_proj.bias", (skv,))
     if cfg.use_qk_norm:   # attention.rs:120-129
-        out["self_attn.q_norm.weight"] = get("self_attn.q_norm.weight", (hd,))
-        out["self_attn.k_norm.weight"] = get("self_attn.k_norm.weight", (hd,))
+        out["self_attn.q_norm.weight"] = rms_norm_weight(get("self_attn.q_norm.weight", (hd,)), cfg)
+        out["self_attn.k_norm.weight"] = rms_norm_weight(get("self_attn.k_norm.weight", (hd,)), cfg)
     return out
 
 

@@ -38,12 +38,13 @@ class Cache:
         self.ctx, self.batch = ctx, batch
         self.max_seq = max_seq or ctx.max_seq
         self.h = c_void_p()
-        check(lib().cake_b200_cache_create(ctx.h, batch, self.max_seq, byref(self.h)))
+        self._lib = lib()  # a handle is only ever given back to the library that made it
+        check(self._lib.cake_b200_cache_create(ctx.h, batch, self.max_seq, byref(self.h)))
         ctx._children.append(weakref.ref(self))
 
     def close(self):
         if self.h:
-            lib().cake_b200_cache_free(self.h)
+            self._lib.cake_b200_cache_free(self.h)
             self.h = None
 
     def clear(self) -> None:  # cache.rs:247-253
@@ -170,11 +171,12 @@ class B200Transformer(Forwarder):
 
     def __init__(self, name: str, handle: c_void_p, ctx: Context):
         self.name, self.h = name, handle
+        self._lib = lib()
         ctx._children.append(weakref.ref(self))
 
     def close(self):
         if self.h:
-            lib().cake_b200_block_free(self.h)
+            self._lib.cake_b200_block_free(self.h)
             self.h = None
 
     @classmethod
@@ -269,7 +271,8 @@ class TextModelBase:
             return t.to(ctx.torch_dtype).contiguous()
 
         emb = get(f"{p}.embed_tokens.weight", (cfg.vocab_size, cfg.hidden_size))
-        lnf = get(f"{p}.norm.weight", (cfg.hidden_size,))
+        from .loader import rms_norm_weight
+        lnf = rms_norm_weight(get(f"{p}.norm.weight", (cfg.hidden_size,)), cfg)   # text_model.rs:186-192
         head = None if cfg.tie_word_embeddings else get("lm_head.weight", (cfg.vocab_size, cfg.hidden_size))
         check(lib().cake_b200_head_load(ctx.h, ptr(emb), ptr(lnf), ptr(head)))
         blocks: List[Forwarder] = []

@@ -66,6 +66,13 @@ typedef struct cake_b200_config {
   float rope_factor, rope_low, rope_high;
   int rope_orig_max;
   int dtype; /* CAKE_B200_BF16 | CAKE_B200_F16 */
+  int sliding_window; /* config.rs:121 + cache.rs:173-205: attention sees the last `sliding_window` positions (0 = full
+                         context).  The cache stays append-only in place; a call at index_pos P with s tokens attends from
+                         position max(0, P + s - window) when P > 0 and over everything when P == 0 — exactly what the
+                         reference's "cat, then keep the last `window`" leaves visible (first call stores everything,
+                         test_cache.rs:99-124). */
+  int use_gelu_mlp;   /* mlp.rs:25-26: gelu_tanh(gate) * up instead of silu(gate) * up */
+  float embed_scale;  /* text_model.rs:274-276: x = embedding * scale (0 = none) */
 } cake_b200_config;
 
 const char *cake_b200_last_error(void); /* thread-local; valid until the next call on this thread */

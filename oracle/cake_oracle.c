@@ -53,6 +53,9 @@ typedef struct ora_config {
   float rope_factor, rope_low, rope_high;
   int rope_orig_max;
   int dtype;     /* ORA_* */
+  int sliding_window; /* cache.rs:173-205 (0 = none) */
+  int use_gelu_mlp;   /* mlp.rs:25-26 */
+  float embed_scale;  /* text_model.rs:274-276 (0 = none) */
   int silu_mode; /* 0: silu in f32 then round (cpu/mod.rs:87-89 via candle_nn::ops::silu)
                     1: per-op D arithmetic x/(1+exp(-x))*y (cuda ops.cu:105-109) — tolerance probe */
 } ora_config;
@@ -262,6 +265,13 @@ float ora_silu_mul(float g, float u, int dt, int mode) {
   float q = rnd(g / d, dt);
   return rnd(q * u, dt);
 }
+/* mlp.rs:25-26 use_gelu_mlp: `backend.gelu(gate) * up`; candle's `gelu` is the tanh approximation
+ * 0.5 x (1 + tanh(sqrt(2/pi) x (1 + 0.044715 x^2))).  Evaluated in f32 and rounded to D, then the product rounded to D
+ * (assumption: candle's half-precision gelu may round per op; unverifiable here, same status as the rms_norm note). */
+float ora_gelu_mul(float g, float u, int dt) {
+  const float a = rnd(0.5f * g * (1.0f + tanhf(0.7978845608028654f * g * (1.0f + 0.044715f * g * g))), dt);
+  return rnd(a * u, dt);
+}
 
 /* ---------------------------------------------------------------- model / cache */
 ora_model *ora_model_create(const ora_config *c) {
@@ -384,6 +394,14 @@ int ora_block_forward(const ora_model *m, int layer, ora_cache *kc, const float 
    * mask j-(T-S) > i when S>1 (:314-341); softmax max-subtracted, *1/sum (backends/mod.rs:407-433);
    * att @ v; to_dtype(in_dtype) (:346). */
   const float scale = (float)(1.0 / sqrt((double)hd));
+  /* cache.rs:173-205 process_kv_windowed: when a cache entry already exists, cat(cache, new) is cut to its last
+   * limit = min(window, max_seq_len) rows; the FIRST call stores (and attends over) everything (test_cache.rs:99-124).
+   * The rows stay in place here; ws is the first row that survives the cut. */
+  int ws = 0;
+  if (c->sliding_window > 0 && P0 > 0) {
+    const int limit = c->sliding_window < c->max_seq ? c->sliding_window : c->max_seq;
+    if (T > limit) ws = T - limit;
+  }
 #pragma omp parallel for collapse(2) schedule(static)
   for (int t = 0; t < S; t++)
     for (int j = 0; j < nh; j++) {
@@ -392,7 +410,8 @@ int ora_block_forward(const ora_model *m, int layer, ora_cache *kc, const float 
       const float *kh = kk + (size_t)(j / g) * kc->cap * hd;
       const float *vh = vv + (size_t)(j / g) * kc->cap * hd;
       float mx = -INFINITY;
-      for (int p = 0; p < T; p++) {
+      for (int p = 0; p < ws; p++) att[p] = 0.f;
+      for (int p = ws; p < T; p++) {
         float s = 0.f;
         for (int d = 0; d < hd; d++) s += qv[d] * kh[(size_t)p * hd + d];
         s *= scale;
@@ -401,7 +420,7 @@ int ora_block_forward(const ora_model *m, int layer, ora_cache *kc, const float 
         if (s > mx) mx = s;
       }
       float sum = 0.f;
-      for (int p = 0; p < T; p++) {
+      for (int p = ws; p < T; p++) {
         float e = expf(att[p] - mx);
         att[p] = e;
         sum += e;
@@ -409,7 +428,7 @@ int ora_block_forward(const ora_model *m, int layer, ora_cache *kc, const float 
       float inv = 1.0f / sum;
       float *yo = y + (size_t)t * sq + (size_t)j * hd;
       for (int d = 0; d < hd; d++) yo[d] = 0.f;
-      for (int p = 0; p < T; p++) {
+      for (int p = ws; p < T; p++) {
         float a = att[p] * inv;
         for (int d = 0; d < hd; d++) yo[d] += a * vh[(size_t)p * hd + d];
       }
@@ -425,7 +444,8 @@ int ora_block_forward(const ora_model *m, int layer, ora_cache *kc, const float 
   ora_linear(h1, S, H, L->up, I, NULL, gu + I, 2 * I, dt);
   for (int t = 0; t < S; t++)
     for (int i = 0; i < I; i++)
-      mm[(size_t)t * I + i] = ora_silu_mul(gu[(size_t)t * 2 * I + i], gu[(size_t)t * 2 * I + I + i], dt, c->silu_mode);
+      mm[(size_t)t * I + i] = c->use_gelu_mlp ? ora_gelu_mul(gu[(size_t)t * 2 * I + i], gu[(size_t)t * 2 * I + I + i], dt)
+                                              : ora_silu_mul(gu[(size_t)t * 2 * I + i], gu[(size_t)t * 2 * I + I + i], dt, c->silu_mode);
   ora_linear(mm, S, I, L->down, H, NULL, out, H, dt);
   /* transformer.rs:131 mlp residual */
   for (size_t i = 0; i < (size_t)S * H; i++) out[i] = rnd(out[i] + x1[i], dt);
@@ -440,6 +460,12 @@ void ora_embed(const ora_model *m, const uint32_t *ids, int S, float *x) {
   int H = m->cfg.hidden;
   for (int t = 0; t < S; t++)
     for (int i = 0; i < H; i++) x[(size_t)t * H + i] = wld(m->embed, (size_t)ids[t] * H + i, m->cfg.dtype);
+  /* text_model.rs:274-276 `x * scale as f64`: candle's scalar multiply is affine(mul, 0) in the tensor's dtype — the
+   * scalar is converted to D, the product rounded once (assumption about candle internals, stated in the header) */
+  if (m->cfg.embed_scale != 0.f) {
+    const float sc = rnd(m->cfg.embed_scale, m->cfg.dtype);
+    for (size_t i = 0; i < (size_t)S * H; i++) x[i] = rnd(x[i] * sc, m->cfg.dtype);
+  }
 }
 /* text_model.rs:336-352: ln_f, last position, lm_head -> logits (V) in D */
 void ora_logits(const ora_model *m, const float *x, int S, float *logits) {

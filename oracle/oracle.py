@@ -86,6 +86,8 @@ def lib():
         L.ora_causal_mask.argtypes = [ci, vp]
         L.ora_silu_mul.restype = cf
         L.ora_silu_mul.argtypes = [cf, cf, ci, ci]
+        L.ora_gelu_mul.restype = cf
+        L.ora_gelu_mul.argtypes = [cf, cf, ci]
         L.ora_round.restype = cf
         L.ora_round.argtypes = [cf, ci]
         L.ora_num_threads.restype = ci
@@ -151,6 +153,10 @@ def causal_mask(seq: int) -> np.ndarray:
 
 def silu_mul(g: float, u: float, dtype: str, mode: int = 0) -> float:
     return lib().ora_silu_mul(g, u, DTYPES[dtype], mode)
+
+
+def gelu_mul(g: float, u: float, dtype: str) -> float:
+    return lib().ora_gelu_mul(g, u, DTYPES[dtype])
 
 
 def argmax(logits) -> int:
@@ -228,7 +234,11 @@ class OracleModel:
                 ptrs.append(_ptr(t))
             ol = OraLayer(*ptrs)
             lib().ora_model_set_layer(self.h, i, ctypes.byref(ol))
+        from cake_b200.loader import rms_norm_weight
         emb, lnf, head = W(f"{p}.embed_tokens.weight"), W(f"{p}.norm.weight"), W("lm_head.weight")
+        if lnf is not None and cfg.residual_rms_norm:
+            lnf = rms_norm_weight(lnf, cfg).contiguous()
+            self._keep.append(lnf)
         lib().ora_model_set_head(self.h, _ptr(emb), _ptr(lnf), _ptr(head))
 
     def new_cache(self, cap: Optional[int] = None) -> OracleCache:

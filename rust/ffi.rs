@@ -18,6 +18,7 @@ pub struct cake_b200_config {
     pub qkv_bias: c_int, pub qk_norm: c_int, pub tie_embeddings: c_int,
     pub rope_llama3: c_int, pub rope_factor: f32, pub rope_low: f32, pub rope_high: f32, pub rope_orig_max: c_int,
     pub dtype: c_int, // 0 = bf16, 1 = f16
+    pub sliding_window: c_int, pub use_gelu_mlp: c_int, pub embed_scale: f32,
 }
 
 #[link(name = "cake_b200")]

@@ -92,7 +92,7 @@ ORACLE = r'''
 
 /* oracle/cake_oracle.c API (test infrastructure) */
 typedef struct ora_config { int hidden, inter, n_heads, n_kv_heads, head_dim, n_layers, vocab, max_seq; float rms_eps, rope_theta, partial_rotary;
-  int qkv_bias, qk_norm, tie_embeddings; int rope_llama3; float rope_factor, rope_low, rope_high; int rope_orig_max; int dtype; int silu_mode; } ora_config;
+  int qkv_bias, qk_norm, tie_embeddings; int rope_llama3; float rope_factor, rope_low, rope_high; int rope_orig_max; int dtype; int sliding_window, use_gelu_mlp; float embed_scale; int silu_mode; } ora_config;
 typedef struct ora_layer { const void *q, *k, *v, *o, *gate, *up, *down, *ln1, *ln2, *q_bias, *k_bias, *v_bias, *q_norm, *k_norm; } ora_layer;
 typedef struct ora_model ora_model;
 typedef struct ora_cache ora_cache;
@@ -133,6 +133,8 @@ static void to_f32(const cake_b200_ctx *c, const void *src, float *dst, size_t n
 static void from_f32(const cake_b200_ctx *c, const float *src, void *dst, size_t n) { uint16_t *p = (uint16_t *)dst;
   for (size_t i = 0; i < n; i++) { float r = ora_round(src[i], c->cfg.dtype); if (c->cfg.dtype == CAKE_B200_BF16) { uint32_t u; memcpy(&u, &r, 4); p[i] = (uint16_t)(u >> 16); } else p[i] = f2h(r); } }
 
+static const void *own_copy(const void *p, size_t n) { void *q = malloc(n); memcpy(q, p, n); return q; }  /* leaked: test processes are short-lived */
+
 int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cake_b200_ctx **out) {
   if (!cfg || !out) return fail(CAKE_B200_EINVAL, "null argument");
   cake_b200_ctx *c = (cake_b200_ctx *)calloc(1, sizeof *c);
@@ -149,6 +151,7 @@ int cake_b200_dev_alloc(cake_b200_ctx *c, size_t bytes, void **out) { if (!c || 
 int cake_b200_dev_free(cake_b200_ctx *c, void *p) { (void)c; free(p); return 0; }
 int cake_b200_head_load(cake_b200_ctx *c, const void *embed, const void *ln_f, const void *lm_head) {
   if (!c || !embed || !ln_f) return fail(CAKE_B200_EINVAL, "null argument");
+  ln_f = own_copy(ln_f, (size_t)c->cfg.hidden * 2);   /* norm vectors may be load-time temporaries (residual_rms_norm): the real library copies everything */
   ora_model_set_head(c->m, embed, ln_f, lm_head ? lm_head : embed);
   return 0;
 }
@@ -157,6 +160,10 @@ int cake_b200_block_load(cake_b200_ctx *c, int layer, const void *q, const void 
                          const void *vb, const void *qn, const void *kn, cake_b200_block **out) {
   if (!c || !q || !k || !v || !o || !gate || !up || !down || !ln1 || !ln2 || !out) return fail(CAKE_B200_EINVAL, "null weight pointer");
   if (layer < 0 || layer >= c->cfg.n_layers) return fail(CAKE_B200_EINVAL, "layer out of range");
+  ln1 = own_copy(ln1, (size_t)c->cfg.hidden * 2);
+  ln2 = own_copy(ln2, (size_t)c->cfg.hidden * 2);
+  if (qn) qn = own_copy(qn, (size_t)c->cfg.head_dim * 2);
+  if (kn) kn = own_copy(kn, (size_t)c->cfg.head_dim * 2);
   ora_layer l = {q, k, v, o, gate, up, down, ln1, ln2, qb, kb, vb, qn, kn};
   ora_model_set_layer(c->m, layer, &l);
   cake_b200_block *b = (cake_b200_block *)malloc(sizeof *b);
@@ -215,6 +222,8 @@ int cake_b200_forward_batch(cake_b200_ctx *c, cake_b200_block *const *blocks, co
   if (!c || !blocks || !idx || !kc || !x || !y || n < 1) return fail(CAKE_B200_EINVAL, "null/empty argument");
   if (batch != kc->batch) { snprintf(g_err, sizeof g_err, "batch %d != cache batch %d", batch, kc->batch); return CAKE_B200_EINVAL; }
   if (seq < 1 || pos < 0) return fail(CAKE_B200_ESTATE, "bad position");
+  if (c->cfg.sliding_window > 0 && pos > 0 && seq > c->cfg.sliding_window)
+    return fail(CAKE_B200_EINVAL, "a chunk on a non-empty cache exceeds the sliding window");
   const size_t ne = (size_t)seq * c->cfg.hidden;
   float *f = (float *)malloc(ne * 4);
   int rc = 0;

@@ -31,6 +31,12 @@ CASES = {
     # Falcon3 checkpoints are Llama blocks with an explicit head_dim (falcon3/config.rs:53-90); HF runs them as Llama
     "falcon3_tiny": ("FalconForCausalLM", dict(head_dim=24, rope_theta=500000.0, num_key_value_heads=1)),
     # Phi-3/4: pre-fused qkv_proj / gate_up_proj tensors, rotary on the first half of each head only (phi4/config.rs:63-100)
+    # an ACTIVE sliding window (mistral/config.rs + cache.rs:173-205): HF masks per query (last 4 keys); cake trims the
+    # cache per call — identical once the prompt is no longer than the window and the rest is decoded token by token,
+    # which is how tests/test_oracle_golden.py replays this fixture
+    "mistral_window": ("MistralForCausalLM", dict(head_dim=32, rope_theta=1000000.0, sliding_window=4)),
+    # use_gelu_mlp (mlp.rs:25-26; Gemma-style gelu_tanh gate) through HF's Llama with hidden_act=gelu_pytorch_tanh
+    "llama_gelu_tiny": ("LlamaForCausalLM", dict(use_gelu_mlp=True)),
     "phi3_tiny": ("Phi3ForCausalLM", dict(partial_rotary_factor=0.5, rope_theta=1000000.0, fused_qkv_proj=True,
                                           fused_gate_up_proj=True)),
 }
@@ -47,12 +53,14 @@ def hf_logits(arch, cfg, sd, ids):
                               Qwen2Config, Qwen2ForCausalLM, Qwen3Config, Qwen3ForCausalLM)
     d = cfg.to_hf(arch)
     d.pop("architectures")
+    window = d.pop("sliding_window", None)
     if arch in ("LlamaForCausalLM", "FalconForCausalLM"):
-        m = LlamaForCausalLM(LlamaConfig(**d, attention_bias=False, mlp_bias=False))
+        m = LlamaForCausalLM(LlamaConfig(**d, attention_bias=False, mlp_bias=False,
+                                         hidden_act="gelu_pytorch_tanh" if cfg.use_gelu_mlp else "silu"))
     elif arch == "Qwen2ForCausalLM":
         m = Qwen2ForCausalLM(Qwen2Config(**d, use_sliding_window=False))
     elif arch == "MistralForCausalLM":
-        m = MistralForCausalLM(MistralConfig(**d, sliding_window=None))
+        m = MistralForCausalLM(MistralConfig(**d, sliding_window=window, attn_implementation="eager"))
     elif arch == "Phi3ForCausalLM":
         m = Phi3ForCausalLM(Phi3Config(**d, pad_token_id=0, original_max_position_embeddings=d["max_position_embeddings"]))
     else:

@@ -83,20 +83,21 @@ def test_other_block_types_are_refused_by_name(tmp_path, arch):
     assert r.returncode == 1 and "outside the block-forward path" in r.stderr
 
 
-def test_active_sliding_window_is_refused_until_the_trim_exists(tmp_path):
+def test_active_sliding_window_reaches_the_library(tmp_path):
+    """mistral/config.rs: sliding_window is carried into the generalized config; cache.rs:173-205 caps the visible KV at
+    min(window, max_seq_len) — a window that can never bite is passed as 0 (full context)."""
     d = {**BASE, "architectures": ["MistralForCausalLM"], "sliding_window": 4096, "max_position_embeddings": 32768}
     c = Config.from_hf(d)
     assert c.sliding_window == 4096
-    with pytest.raises(ValueError, match="sliding_window=4096"):
-        CConfig.from_config(c, "bf16")
-    assert CConfig.from_config(c, "bf16", max_seq=4096).max_seq == 4096  # inside the window nothing is ever trimmed
+    assert CConfig.from_config(c, "bf16").sliding_window == 4096
+    assert CConfig.from_config(c, "bf16", max_seq=4096).sliding_window == 0
     build_host()
     with open(tmp_path / "config.json", "w") as f:
         json.dump(d, f)
     r = subprocess.run([RUN, str(tmp_path), "--show-config"], capture_output=True, text=True)
-    assert r.returncode == 1 and "sliding_window=4096" in r.stderr
+    assert r.returncode == 0 and "sliding_window=4096" in r.stdout
     r = subprocess.run([RUN, str(tmp_path), "--show-config", "--max-seq", "4096"], capture_output=True, text=True)
-    assert r.returncode == 0 and "max_seq=4096" in r.stdout
+    assert r.returncode == 0 and "max_seq=4096" in r.stdout and "sliding_window=0" in r.stdout
 
 
 @pytest.mark.parametrize("drop", ["hidden_size", "intermediate_size", "vocab_size", "num_hidden_layers", "num_attention_heads",

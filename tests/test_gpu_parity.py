@@ -38,6 +38,9 @@ def _llama31_scaling():
 
 
 CONFIGS = {
+    # an active sliding window (cache.rs:173-205; bites from the second decode step on), the GELU MLP
+    "medium_window": lambda: medium_config(sliding_window=5),
+    "medium_gelu": lambda: medium_config(use_gelu_mlp=True),
     "medium_rope_llama3": lambda: medium_config(rope_scaling=_llama31_scaling(), rope_theta=10000.0),
     "ref_tiny": lambda: reference_test_config(),                       # helpers.rs:8-44 (hd=16, GQA 4:2)
     "ref_tiny_qknorm": lambda: reference_test_config(use_qk_norm=True),  # test_blocks.rs:920-933
@@ -321,3 +324,51 @@ def test_megakernel_equals_per_op_kernels(monkeypatch):
     assert max_ulp_err(to_np(res["0"][1]), to_np(res["1"][1]), "bf16") <= 2.0
     assert max_ulp_err(to_np(res["0"][2]), to_np(res["1"][2]), "bf16") <= 2.0
     assert res["0"][3] == res["1"][3]
+
+
+def test_sliding_window_chunked_prefill_and_long_decode_match_oracle():
+    """cache.rs:173-205 through every kernel path: first call (6 tokens, stored and attended in full although the window
+    is 5), a second multi-token chunk on the non-empty cache (all its queries see the same surviving old rows), then
+    decode steps far past the window (several flash-decoding splits over the visible rows only)."""
+    from cake_b200.model import B200Transformer
+    dtype = "bf16"
+    cfg = medium_config(sliding_window=5)
+    sd = checkpoint(cfg, dtype, seed=12)
+    om, ctx = O.OracleModel(cfg, sd, dtype), _ctx(cfg, sd, dtype)
+    oc = om.new_cache()
+    blk = B200Transformer.load(cfg.layer_name(0), ctx)
+    x = rand_x((1, 40, cfg.hidden_size), dtype, seed=13)
+    pos = 0
+    for n in (6, 3, 1, 1, 2, 1) + (1,) * 26:
+        y_ref = om.block_forward(0, x[0, pos:pos + n].float().numpy(), pos, oc)
+        y = blk.forward(ctx.to_device(x[:, pos:pos + n]), pos, 0, ctx)
+        ctx.sync()
+        e = max_ulp_err(to_np(y[0]), y_ref, dtype)
+        assert e <= BLOCK_TOL_ULP, f"{n} token(s) @ {pos}: {e} ulp"
+        pos += n
+    # a chunk longer than the window on a non-empty cache is an error, not a silent mis-trim
+    with pytest.raises(Exception, match="sliding window"):
+        blk.forward(ctx.to_device(x[:, :7]), pos, 0, ctx)
+    ctx.close()
+
+
+def test_embed_scale_residual_norm_and_gelu_through_the_model():
+    """text_model.rs:274-276 embed_scale, config.rs:155-173 residual RMS-norm weights ((1 + w) at load) and the GELU MLP
+    through TextModelBase: host-stepped logits and the decode graph against the oracle."""
+    from cake_b200.model import Context, TextModelBase
+    cfg = medium_config(use_gelu_mlp=True, embed_scale=22.627416997969522, residual_rms_norm=True, use_qk_norm=True, num_hidden_layers=2)
+    sd = checkpoint(cfg, "bf16", seed=77, peaked=True)
+    for k in list(sd):   # residual checkpoints store norm weights as deltas around 0
+        if k.endswith("norm.weight") or k.endswith("layernorm.weight"):
+            sd[k] = (sd[k].float() - 1.0).to(sd[k].dtype)
+    om = O.OracleModel(cfg, sd, "bf16", max_seq=64)
+    prompt = [3, 700, 41, 9, 256]
+    ref_toks, ref_logits = om.generate(prompt, 8)
+    ctx = Context(cfg, sd, "bf16", device=0, max_seq=64)
+    m = TextModelBase.load(ctx)
+    m.prepare_prompt(prompt)
+    t0 = m.next_token(0)
+    assert max_ulp_err(to_np(m.last_logits), ref_logits[0], "bf16") <= LOGIT_TOL_ULP and t0.id == ref_toks[0]
+    m.decode_build()
+    assert [t0.id] + m.decode_greedy(t0.id, 7) == list(ref_toks)
+    ctx.close()
