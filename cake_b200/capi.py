@@ -67,6 +67,7 @@ class CSampling(ctypes.Structure):
 SYMBOLS += [
     ("cake_b200_sample", _I, [_VP, _VP, POINTER(CSampling), c_float, POINTER(c_uint32), _I, c_uint64, POINTER(c_float), POINTER(c_uint32)]),
     ("cake_b200_decode_set_sampling", _I, [_VP, POINTER(CSampling)]),
+    ("cake_b200_load_stats", _I, [_VP, POINTER(ctypes.c_double), POINTER(ctypes.c_double)]),
 ]
 
 

@@ -11,7 +11,10 @@
 #include <string.h>
 
 #include <atomic>
+#include <algorithm>
+#include <chrono>
 #include <mutex>
+#include <thread>
 #include <set>
 #include <string>
 #include <vector>
@@ -49,6 +52,8 @@ static int fail(int code, const char *fmt, ...) {
     if (rc_ != CAKE_B200_OK) return rc_; \
   } while (0)
 
+struct cake_b200_ctx;
+static int wait_loads(cake_b200_ctx *c);
 extern "C" const char *cake_b200_last_error(void) { return g_err; }
 extern "C" const char *cake_b200_version(void) { return "cake_b200 0.1 (sm_100a)"; }
 
@@ -111,6 +116,14 @@ struct cake_b200_ctx {
   int *part_idx = nullptr, *d_step = nullptr;
   unsigned *attn_counters = nullptr, *argmax_counter = nullptr;
   uint32_t *d_token = nullptr, *token_ring = nullptr, *d_ids = nullptr, *d_pen = nullptr;
+  // weight upload pipe: mmapped safetensors -> two pinned staging buffers (filled by a few host
+  // threads) -> cudaMemcpy(2D)Async on a copy stream straight into the fused device layouts
+  cudaStream_t load_stream = nullptr;
+  void *stage[2] = {nullptr, nullptr};
+  cudaEvent_t stage_free[2] = {nullptr, nullptr}, load_done = nullptr;
+  int stage_cur = 0;
+  bool load_pending = false;
+  double load_bytes = 0, load_seconds = 0;
   float *samp_p = nullptr, *samp_noise = nullptr;  // sampler scratch: probabilities (vocab) / supplied uniforms
   cake_b200_sampling sampling{};                   // sampler of the decode graph (kind 0 = greedy)
   size_t d_ids_cap = 0, d_pen_cap = 0;
@@ -438,6 +451,12 @@ extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
   for (void *b : bufs)
     if (b) cudaFree(b);
   if (c->lm_head && c->lm_head != c->embed) cudaFree(c->lm_head);
+  for (int i = 0; i < 2; i++) {
+    if (c->stage[i]) cudaFreeHost(c->stage[i]);
+    if (c->stage_free[i]) cudaEventDestroy(c->stage_free[i]);
+  }
+  if (c->load_done) cudaEventDestroy(c->load_done);
+  if (c->load_stream) { cudaStreamSynchronize(c->load_stream); cudaStreamDestroy(c->load_stream); }
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->h_pin_x) cudaFreeHost(c->h_pin_x);
   if (c->mk_tab_host) cudaFreeHost(c->mk_tab_host);
@@ -447,6 +466,8 @@ extern "C" void cake_b200_ctx_destroy(cake_b200_ctx *c) {
 extern "C" int cake_b200_sync(cake_b200_ctx *c) {
   if (!c) return fail(CAKE_B200_EINVAL, "null argument");
   CU(cudaSetDevice(c->device));
+  RC(wait_loads(c));
+  if (c->load_stream) CU(cudaStreamSynchronize(c->load_stream));
   CU(cudaStreamSynchronize(c->stream));
   return CAKE_B200_OK;
 }
@@ -471,11 +492,94 @@ extern "C" int cake_b200_dev_free(cake_b200_ctx *c, void *p) {
   return CAKE_B200_OK;
 }
 
-// ------------------------------------------------------------------------------------------ blocks
-static int upload(void **dst, const void *src, size_t bytes) {
-  CU(cudaMalloc(dst, bytes + 16));
-  CU(cudaMemcpy(*dst, src, bytes, cudaMemcpyDefault));
+// ------------------------------------------------------------------------------------------ weight upload pipe
+constexpr size_t STAGE_BYTES = (size_t)64 << 20;
+constexpr int STAGE_THREADS = 6;
+static int pipe_init(cake_b200_ctx *c) {
+  if (c->load_stream) return CAKE_B200_OK;
+  CU(cudaStreamCreateWithFlags(&c->load_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CU(cudaMallocHost(&c->stage[i], STAGE_BYTES));
+    CU(cudaEventCreateWithFlags(&c->stage_free[i], cudaEventDisableTiming));
+  }
+  CU(cudaEventCreateWithFlags(&c->load_done, cudaEventDisableTiming));
   return CAKE_B200_OK;
+}
+// host rows [r0, r1) of width bytes (source pitch spitch) -> packed staging buffer, split over a few threads: one thread
+// tops out at ~6 GB/s out of the page cache, far below what the PCIe link takes
+static void stage_rows(char *dst, const char *src, size_t spitch, size_t width, size_t rows) {
+  const size_t total = rows * width;
+  int nt = total >= ((size_t)4 << 20) ? STAGE_THREADS : 1;
+  if (nt == 1) {
+    for (size_t r = 0; r < rows; r++) memcpy(dst + r * width, src + r * spitch, width);
+    return;
+  }
+  std::vector<std::thread> th;
+  if (spitch == width) {  // contiguous: split by bytes
+    for (int t = 0; t < nt; t++) {
+      const size_t a = total * t / nt, b = total * (t + 1) / nt;
+      th.emplace_back([=]() { memcpy(dst + a, src + a, b - a); });
+    }
+  } else {
+    for (int t = 0; t < nt; t++) {
+      const size_t a = rows * t / nt, b = rows * (t + 1) / nt;
+      th.emplace_back([=]() { for (size_t r = a; r < b; r++) memcpy(dst + r * width, src + r * spitch, width); });
+    }
+  }
+  for (auto &x : th) x.join();
+}
+// dst[r * dpitch .. + width) = src[r * spitch .. + width) for r < rows (rows == 1: a plain copy).  Device sources
+// (synthetic checkpoints generated on the GPU) are copied device-to-device on the same stream.
+static int pipe_copy(cake_b200_ctx *c, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) {
+  RC(pipe_init(c));
+  cudaPointerAttributes at{};
+  const bool dev_src = (cudaPointerGetAttributes(&at, src) == cudaSuccess) && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged);
+  (void)cudaGetLastError();
+  if (dev_src) {
+    // written by someone else's stream (torch): copy on the legacy default stream, which orders after that work, and
+    // wait — the caller may free the source as soon as we return
+    CU(cudaMemcpy2D(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToDevice));
+    CU(cudaStreamSynchronize(0));
+    return CAKE_B200_OK;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  if (rows == 1 && width > STAGE_BYTES) {  // a long contiguous tensor: treat it as rows of 1 MB
+    const size_t rw = (size_t)1 << 20, full = width / rw;
+    if (full) RC(pipe_copy(c, dst, rw, src, rw, rw, full));
+    if (width % rw) RC(pipe_copy(c, (char *)dst + full * rw, width % rw, (const char *)src + full * rw, width % rw, width % rw, 1));
+    return CAKE_B200_OK;
+  }
+  const size_t rows_per = std::max<size_t>(1, STAGE_BYTES / width);
+  for (size_t r0 = 0; r0 < rows; r0 += rows_per) {
+    const size_t nr = std::min(rows_per, rows - r0);
+    const int b = c->stage_cur;
+    CU(cudaEventSynchronize(c->stage_free[b]));  // the DMA that last read this buffer has finished
+    stage_rows((char *)c->stage[b], (const char *)src + r0 * spitch, spitch, width, nr);
+    CU(cudaMemcpy2DAsync((char *)dst + r0 * dpitch, dpitch, c->stage[b], width, width, nr, cudaMemcpyHostToDevice, c->load_stream));
+    CU(cudaEventRecord(c->stage_free[b], c->load_stream));
+    c->stage_cur ^= 1;
+  }
+  c->load_bytes += (double)width * rows;
+  c->load_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return CAKE_B200_OK;
+}
+static int pipe_mark(cake_b200_ctx *c) {  // compute must not start before the uploads issued so far have landed
+  CU(cudaEventRecord(c->load_done, c->load_stream));
+  c->load_pending = true;
+  return CAKE_B200_OK;
+}
+static int wait_loads(cake_b200_ctx *c) {
+  if (c->load_pending) {
+    CU(cudaStreamWaitEvent(c->stream, c->load_done, 0));
+    c->load_pending = false;
+  }
+  return CAKE_B200_OK;
+}
+
+// ------------------------------------------------------------------------------------------ blocks
+static int upload(cake_b200_ctx *c, void **dst, const void *src, size_t bytes) {
+  CU(cudaMalloc(dst, bytes + 16));
+  return pipe_copy(c, *dst, bytes, src, bytes, bytes, 1);
 }
 
 extern "C" void cake_b200_block_free(cake_b200_block *b);
@@ -493,29 +597,29 @@ extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void 
   const int rc = [&]() -> int {  // on any failure (e.g. out of memory half way through a shard) nothing is leaked
   // attention.rs:109-113: Wqkv = cat([q,k,v], 0)
   CU(cudaMalloc(&b->wqkv, (sq + 2 * skv) * H * es + 16));
-  CU(cudaMemcpy(b->wqkv, q, sq * H * es, cudaMemcpyDefault));
-  CU(cudaMemcpy((char *)b->wqkv + sq * H * es, k, skv * H * es, cudaMemcpyDefault));
-  CU(cudaMemcpy((char *)b->wqkv + (sq + skv) * H * es, v, skv * H * es, cudaMemcpyDefault));
-  RC(upload(&b->wo, o, H * sq * es));
+  RC(pipe_copy(c, b->wqkv, sq * H * es, q, sq * H * es, sq * H * es, 1));
+  RC(pipe_copy(c, (char *)b->wqkv + sq * H * es, skv * H * es, k, skv * H * es, skv * H * es, 1));
+  RC(pipe_copy(c, (char *)b->wqkv + (sq + skv) * H * es, skv * H * es, v, skv * H * es, skv * H * es, 1));
+  RC(upload(c, &b->wo, o, H * sq * es));
   // mlp.rs:43-45 fuses gate|up by cat; here the fused matrix is ROW-INTERLEAVED (row 2i = gate_i,
   // row 2i+1 = up_i) so that silu(gate_i)*up_i is local to one warp's epilogue.  Numerically identical.
   CU(cudaMalloc(&b->wgu, 2 * I * H * es + 16));
-  CU(cudaMemcpy2D(b->wgu, 2 * H * es, gate, H * es, H * es, I, cudaMemcpyDefault));
-  CU(cudaMemcpy2D((char *)b->wgu + H * es, 2 * H * es, up, H * es, H * es, I, cudaMemcpyDefault));
-  RC(upload(&b->wd, down, H * I * es));
-  RC(upload(&b->ln1, ln1, H * es));
-  RC(upload(&b->ln2, ln2, H * es));
+  RC(pipe_copy(c, b->wgu, 2 * H * es, gate, H * es, H * es, I));               // the row interleave is done by the DMA engine
+  RC(pipe_copy(c, (char *)b->wgu + H * es, 2 * H * es, up, H * es, H * es, I));
+  RC(upload(c, &b->wd, down, H * I * es));
+  RC(upload(c, &b->ln1, ln1, H * es));
+  RC(upload(c, &b->ln2, ln2, H * es));
   if (c->cfg.qkv_bias) {
     CU(cudaMalloc(&b->bqkv, (sq + 2 * skv) * es + 16));
-    CU(cudaMemcpy(b->bqkv, q_bias, sq * es, cudaMemcpyDefault));
-    CU(cudaMemcpy((char *)b->bqkv + sq * es, k_bias, skv * es, cudaMemcpyDefault));
-    CU(cudaMemcpy((char *)b->bqkv + (sq + skv) * es, v_bias, skv * es, cudaMemcpyDefault));
+    RC(pipe_copy(c, b->bqkv, sq * es, q_bias, sq * es, sq * es, 1));
+    RC(pipe_copy(c, (char *)b->bqkv + sq * es, skv * es, k_bias, skv * es, skv * es, 1));
+    RC(pipe_copy(c, (char *)b->bqkv + (sq + skv) * es, skv * es, v_bias, skv * es, skv * es, 1));
   }
   if (c->cfg.qk_norm) {
-    RC(upload(&b->qn, q_norm, hd * es));
-    RC(upload(&b->kn, k_norm, hd * es));
+    RC(upload(c, &b->qn, q_norm, hd * es));
+    RC(upload(c, &b->kn, k_norm, hd * es));
   }
-  return CAKE_B200_OK;
+  return pipe_mark(c);
   }();
   if (rc != CAKE_B200_OK) {
     cake_b200_block_free(b);
@@ -1007,6 +1111,7 @@ extern "C" int cake_b200_forward_batch(cake_b200_ctx *c, cake_b200_block *const 
   if (seq < 1 || index_pos < 0 || index_pos + seq > kc->cap)
     return fail(CAKE_B200_ESTATE, "index_pos %d + seq %d exceeds cache capacity %d", index_pos, seq, kc->cap);
   CU(cudaSetDevice(c->device));
+  RC(wait_loads(c));
   for (int i = 0; i < n_blocks; i++) {
     RC(cache_ensure(kc, block_idx[i]));
     if (kc->len[block_idx[i]] != index_pos)
@@ -1063,16 +1168,17 @@ extern "C" int cake_b200_head_load(cake_b200_ctx *c, const void *embed, const vo
   if (!lm_head && !c->cfg.tie_embeddings) return fail(CAKE_B200_EINVAL, "lm_head is NULL but tie_embeddings is 0");
   CU(cudaSetDevice(c->device));
   const size_t es = c->es, H = c->cfg.hidden, V = c->cfg.vocab;
-  RC(upload(&c->embed, embed, V * H * es));
-  RC(upload(&c->ln_f, ln_f, H * es));
-  if (lm_head) RC(upload(&c->lm_head, lm_head, V * H * es));
+  RC(upload(c, &c->embed, embed, V * H * es));
+  RC(upload(c, &c->ln_f, ln_f, H * es));
+  if (lm_head) RC(upload(c, &c->lm_head, lm_head, V * H * es));
   else c->lm_head = c->embed;  // text_model.rs:164-167
-  return CAKE_B200_OK;
+  return pipe_mark(c);
 }
 
 extern "C" int cake_b200_embed(cake_b200_ctx *c, const uint32_t *ids_host, int batch, int seq, void *x_dev) {
   if (!c || !ids_host || !x_dev || !c->embed) return fail(CAKE_B200_EINVAL, "null argument or head not loaded");
   CU(cudaSetDevice(c->device));
+  RC(wait_loads(c));
   if (batch < 1 || seq < 1) return fail(CAKE_B200_EINVAL, "embed: batch and seq must be >= 1");
   const size_t n = (size_t)batch * seq;
   for (size_t i = 0; i < n; i++)  // index_select on an out-of-range id is an error in the reference (backends/mod.rs:513-528)
@@ -1099,6 +1205,7 @@ extern "C" int cake_b200_logits(cake_b200_ctx *c, const void *x_dev, int batch, 
   if (!c || !x_dev || !c->lm_head) return fail(CAKE_B200_EINVAL, "null argument or head not loaded");
   if (batch > 64) return fail(CAKE_B200_EINVAL, "batch > 64");
   CU(cudaSetDevice(c->device));
+  RC(wait_loads(c));
   const size_t H = c->cfg.hidden, V = c->cfg.vocab, es = c->es;
   for (int b = 0; b < batch; b++) {
     const char *row = (const char *)x_dev + ((size_t)b * seq + (seq - 1)) * H * es;  // text_model.rs:342-346
@@ -1288,6 +1395,7 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
   if (world > 1 && !c->comm) return fail(CAKE_B200_ESTATE, "world > 1 needs cake_b200_comm_init first");
   if (rank == 0 && !c->lm_head) return fail(CAKE_B200_ESTATE, "rank 0 needs cake_b200_head_load first");
   CU(cudaSetDevice(c->device));
+  RC(wait_loads(c));
   for (int i = 0; i < n_blocks; i++) RC(cache_ensure(kc, block_idx[i]));
   if (c->gexec) { cudaGraphExecDestroy(c->gexec); c->gexec = nullptr; }
   if (c->graph) { cudaGraphDestroy(c->graph); c->graph = nullptr; }
@@ -1395,6 +1503,7 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
 extern "C" int cake_b200_decode_begin(cake_b200_ctx *c, uint32_t first_token, int index_pos) {
   if (!c || !c->gexec) return fail(CAKE_B200_ESTATE, "decode_build has not been called");
   CU(cudaSetDevice(c->device));
+  RC(wait_loads(c));
   cake_b200_cache *kc = c->g_cache;
   for (int l : c->g_block_idx)
     if (kc->len[l] != index_pos)
@@ -1464,6 +1573,7 @@ extern "C" int cake_b200_bench_kernel(cake_b200_ctx *c, cake_b200_block *const *
   if (!c || !blocks || !kc || !ms_per_launch || n_blocks < 1 || reps < 1 || which < 0 || which > 4)
     return fail(CAKE_B200_EINVAL, "bad bench_kernel arguments");
   CU(cudaSetDevice(c->device));
+  RC(wait_loads(c));
   for (int i = 0; i < n_blocks; i++) RC(cache_ensure(kc, block_idx[i]));
   const int len = kc->len[block_idx[0]];
   if (which == 4 && len < 1) return fail(CAKE_B200_ESTATE, "attention bench needs a non-empty cache");
@@ -1496,6 +1606,17 @@ extern "C" int cake_b200_bench_kernel(cake_b200_ctx *c, cake_b200_block *const *
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   *ms_per_launch = ms / (float)(reps * n_blocks);
+  return CAKE_B200_OK;
+}
+
+extern "C" int cake_b200_load_stats(cake_b200_ctx *c, double *bytes, double *seconds) {
+  if (!c || !bytes || !seconds) return fail(CAKE_B200_EINVAL, "null argument");
+  CU(cudaSetDevice(c->device));
+  if (c->load_stream) {  // include the tail of the last DMA in the wall time of the caller, not in `seconds` (host staging time)
+    CU(cudaStreamSynchronize(c->load_stream));
+  }
+  *bytes = c->load_bytes;
+  *seconds = c->load_seconds;
   return CAKE_B200_OK;
 }
 

@@ -197,6 +197,13 @@ int cake_b200_decode_set_sampling(cake_b200_ctx *, const cake_b200_sampling *);
 int cake_b200_bench_kernel(cake_b200_ctx *, cake_b200_block *const *blocks, const int *block_idx, int n_blocks,
                            cake_b200_cache *, int which, int reps, float *ms_per_launch);
 
+/* Weight upload statistics of this ctx (utils/mod.rs:255-384 is the reference's loader): block_load / head_load stage host
+ * tensors through two pinned 64 MB buffers (filled by a few host threads) and copy them with cudaMemcpy(2D)Async on a
+ * copy stream straight into the fused qkv / row-interleaved gate_up layouts; compute entry points wait for the uploads
+ * issued so far.  bytes = host bytes uploaded, seconds = time spent staging + enqueueing them.  Synchronises the copy
+ * stream. */
+int cake_b200_load_stats(cake_b200_ctx *, double *bytes, double *seconds);
+
 /* Per-step timeline of this rank's decode kernels for the last `n_steps` steps since cake_b200_decode_begin
  * (n_steps <= 2048): 8 u64 per step = {entry, input acquired, exit, 0} of the layer launch followed by the same for
  * rank 0's head-only launch when sharded (zeros otherwise); %globaltimer nanoseconds of CTA 0.  "input acquired"

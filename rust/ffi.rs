@@ -78,6 +78,7 @@ extern "C" {
     pub fn cake_b200_sample(ctx: *mut cake_b200_ctx, logits_dev: *mut c_void, sampling: *const cake_b200_sampling, repeat_penalty: f32,
         ctx_tokens_host: *const u32, n_tokens: c_int, step: u64, noise_host: *const f32, token_host: *mut u32) -> c_int;
     pub fn cake_b200_decode_set_sampling(ctx: *mut cake_b200_ctx, sampling: *const cake_b200_sampling) -> c_int;
+    pub fn cake_b200_load_stats(ctx: *mut cake_b200_ctx, bytes: *mut f64, seconds: *mut f64) -> c_int;
 }
 
 /// `cake_b200_sampling` (include/cake_b200.h): the Sampling enum of candle_transformers::generation flattened.
