@@ -293,9 +293,11 @@ template <typename T> static int set_smem_attrs_T() {
 #undef SETC
   CU(cudaFuncSetAttribute(attn_prefill_mma_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * FA_BN * 128 * 2));
   CU(cudaFuncSetAttribute(attn_prefill_mma_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * FA_BN * 64 * 2));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, TCE_PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, TCE_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, TCE_SWIGLU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+#define SETT(EPI)                                                                                                                  \
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, EPI, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));      \
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, EPI, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
+  SETT(TCE_PLAIN) SETT(TCE_RESIDUAL) SETT(TCE_SWIGLU)
+#undef SETT
   return CAKE_B200_OK;
 }
 
@@ -1002,13 +1004,19 @@ static bool tc_gemm_ok(int M, int N, int K) { return M >= 1 && N % TC_BN == 0 &&
 // C = epi(A[M,K] W[N,K]^T) on the tensor cores (gemm_tc.cuh)
 template <typename T, int EPI>
 static int gemm_tc_T(cake_b200_ctx *c, const void *A, const void *W, const void *bias, const void *res, void *C, int M, int N, int K) {
+  // 128 x 256 tiles when N allows and there are enough tiles to fill the chip; CAKE_B200_TC_BN=128 forces the small tile (A/B aid)
+  static const int force_bn = []() { const char *e = getenv("CAKE_B200_TC_BN"); return e ? atoi(e) : 0; }();
+  const int tiles_m = (M + TC_BM - 1) / TC_BM;
+  const bool big = force_bn ? force_bn == 256 && N % 256 == 0 : (N % 256 == 0 && tiles_m * (N / 256) >= c->sm_count);
+  const int bn = big ? 256 : 128;
   CUtensorMap ma, mb;
   RC(make_tmap(&ma, A, (uint64_t)M, (uint64_t)K, c->cfg.dtype, TC_BM));
-  RC(make_tmap(&mb, W, (uint64_t)N, (uint64_t)K, c->cfg.dtype, TC_BN));
+  RC(make_tmap(&mb, W, (uint64_t)N, (uint64_t)K, c->cfg.dtype, (uint32_t)bn));
   TcParams p{bias, res, C, M, N, K, c->cfg.use_gelu_mlp ? 1 : 0};
-  const int tiles = ((M + TC_BM - 1) / TC_BM) * (N / TC_BN);
+  const int tiles = tiles_m * (N / bn);
   dim3 grid(tiles < c->sm_count ? tiles : c->sm_count), block(TC_THREADS);
-  return launch_pdl(c, gemm_tc_kernel<T, EPI>, grid, block, (size_t)TC_SMEM_BYTES, ma, mb, p);
+  if (big) return launch_pdl(c, gemm_tc_kernel<T, EPI, 256>, grid, block, (size_t)TcCfg<256>::SMEM_BYTES, ma, mb, p);
+  return launch_pdl(c, gemm_tc_kernel<T, EPI, 128>, grid, block, (size_t)TcCfg<128>::SMEM_BYTES, ma, mb, p);
 }
 
 // ------------------------------------------------------------------------------------------ prefill path (any batch / seq)

@@ -24,9 +24,17 @@
 
 namespace cake {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64, TC_STAGES = 6, TC_THREADS = 256;
-constexpr int TC_STAGE_BYTES = (TC_BM + TC_BN) * TC_BK * 2;  // 32 KB
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+// Tile: 128 x BN with BN in {128, 256}.  A 128x128 tile needs 32 KB of operands per 2.1 MFLOP k-block = 64 flop/B, i.e.
+// ~240 GB/s per SM at the tensor peak — more than one SM pulls out of L2, which is what capped round 1 at ~55 % tensor-pipe
+// activity.  128x256 (all 512 TMEM columns: two 128x256 fp32 accumulators) moves 48 KB per 4.2 MFLOP = 87 flop/B.
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 256;
+constexpr int TC_BN = 128;                     // granularity the host checks N against (BN = 256 when N % 256 == 0)
+template <int BN> struct TcCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGE_BYTES = (TC_BM + BN) * TC_BK * 2;  // 32 KB | 48 KB
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+constexpr int TC_SMEM_BYTES = TcCfg<256>::SMEM_BYTES > TcCfg<128>::SMEM_BYTES ? TcCfg<256>::SMEM_BYTES : TcCfg<128>::SMEM_BYTES;
 enum { TCE_PLAIN = 0, TCE_RESIDUAL = 1, TCE_SWIGLU = 2 };
 
 struct TcParams {
@@ -41,12 +49,12 @@ struct TcParams {
 // group stays in the 126 MB L2 while each W tile streams once per group.  With plain m-fastest order a 1 GB A
 // (bs=32 x 4k) is re-read for every W tile column: measured 815 TFLOP/s, HBM-bound (profiles/README.md).
 constexpr int TC_GM = 16;
-__device__ __forceinline__ void tc_tile(int t, int tiles_m, int tiles_n, int &m0, int &n0) {
+__device__ __forceinline__ void tc_tile(int t, int tiles_m, int tiles_n, int bn, int &m0, int &n0) {
   const int per_group = TC_GM * tiles_n;
   const int mg = t / per_group, r = t % per_group;
   const int gm = min(TC_GM, tiles_m - mg * TC_GM);
   m0 = (mg * TC_GM + r % gm) * TC_BM;
-  n0 = (r / gm) * TC_BN;
+  n0 = (r / gm) * bn;
 }
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -91,36 +99,36 @@ __device__ __forceinline__ uint64_t tc_smem_desc(const void *tile) {
   return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 // instruction descriptor, kind::f16: D = f32, A/B = bf16 (1) or f16 (0), both K-major, N >> 3, M >> 4
-template <typename T> __device__ __forceinline__ uint32_t tc_idesc();
-template <> __device__ __forceinline__ uint32_t tc_idesc<__nv_bfloat16>() {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+template <typename T> __device__ __forceinline__ uint32_t tc_idesc(int bn);
+template <> __device__ __forceinline__ uint32_t tc_idesc<__nv_bfloat16>(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
-template <> __device__ __forceinline__ uint32_t tc_idesc<__half>() {
-  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+template <> __device__ __forceinline__ uint32_t tc_idesc<__half>(int bn) {
+  return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-template <typename T, int EPI>
+template <typename T, int EPI, int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   extern __shared__ unsigned char smem_raw_tc[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~(uintptr_t)1023);
-  uint64_t *full = reinterpret_cast<uint64_t *>(smem + TC_STAGES * TC_STAGE_BYTES);
-  uint64_t *empty = full + TC_STAGES;
-  uint64_t *acc_full = empty + TC_STAGES;   // [2]
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + TcCfg<BN>::STAGES * TcCfg<BN>::STAGE_BYTES);
+  uint64_t *empty = full + TcCfg<BN>::STAGES;
+  uint64_t *acc_full = empty + TcCfg<BN>::STAGES;   // [2]
   uint64_t *acc_empty = acc_full + 2;       // [2]
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = p.N / TC_BN, n_tiles = tiles_m * tiles_n;
+  const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = p.N / BN, n_tiles = tiles_m * tiles_n;
   const int kblocks = p.K / TC_BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TC_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < TcCfg<BN>::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
     mbar_fence_init();
   }
-  if (warp == 2) {  // TMEM: 256 columns = two 128x128 fp32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_ptr)) : "memory");
+  if (warp == 2) {  // TMEM: 2 x BN columns = two 128 x BN fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -139,21 +147,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t ph = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         int m0, n0;
-        tc_tile(t, tiles_m, tiles_n, m0, n0);
+        tc_tile(t, tiles_m, tiles_n, BN, m0, n0);
         for (int kb = 0; kb < kblocks; kb++) {
           mbar_wait(&empty[s], ph ^ 1u);
-          unsigned char *st = smem + (size_t)s * TC_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
+          unsigned char *st = smem + (size_t)s * TcCfg<BN>::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], TcCfg<BN>::STAGE_BYTES);
           tma_load_2d(st, &map_a, kb * TC_BK, m0, &full[s]);
           tma_load_2d(st + TC_BM * TC_BK * 2, &map_b, kb * TC_BK, n0, &full[s]);
-          if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+          if (++s == TcCfg<BN>::STAGES) { s = 0; ph ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =======================================================
     if (lane == 0) {
-      const uint32_t idesc = tc_idesc<T>();
+      const uint32_t idesc = tc_idesc<T>(BN);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
@@ -162,17 +170,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const uint32_t aph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&acc_empty[a], aph ^ 1u);  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t tmem_c = tmem_base + (uint32_t)(a * TC_BN);
+        const uint32_t tmem_c = tmem_base + (uint32_t)(a * BN);
         for (int kb = 0; kb < kblocks; kb++) {
           mbar_wait(&full[s], ph);
           tc_fence_after();
-          const unsigned char *st = smem + (size_t)s * TC_STAGE_BYTES;
+          const unsigned char *st = smem + (size_t)s * TcCfg<BN>::STAGE_BYTES;
           const uint64_t da = tc_smem_desc(st), db = tc_smem_desc(st + TC_BM * TC_BK * 2);
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; k++)  // +32 bytes (2 x 16 B units) per K=16 slab inside the swizzle atom
             tc_mma_f16(tmem_c, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
           tc_commit(&empty[s]);  // arrives when the MMAs above have read the stage
-          if (++s == TC_STAGES) { s = 0; ph ^= 1u; }
+          if (++s == TcCfg<BN>::STAGES) { s = 0; ph ^= 1u; }
         }
         tc_commit(&acc_full[a]);  // accumulator complete
       }
@@ -188,14 +196,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int a = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       int m0, n0;
-      tc_tile(t, tiles_m, tiles_n, m0, n0);
+      tc_tile(t, tiles_m, tiles_n, BN, m0, n0);
       const int row = m0 + wq * 32 + lane;
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[32];
-        tc_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * TC_BN + c0), r);
+        tc_ld32(tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(a * BN + c0), r);
         if (row < p.M) {
           if (EPI == TCE_SWIGLU) {
             uint32_t o[8];
@@ -243,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");
   }
 }
 

@@ -49,24 +49,27 @@ def test_llama3_8b_block_matches_oracle_prefill_and_decode():
 
 def test_llama3_8b_decode_equals_prefill_at_depth():
     """Size-independent property: the hidden state of position t computed by token-by-token decode (megakernel,
-    flash-decoding over 600+ cached rows, several K/V tiles per split) equals the one computed by a one-shot
+    flash-decoding over 1200+ cached rows, several K/V tiles per split) equals the one computed by a one-shot
     causal prefill (tcgen05 GEMM + flash prefill) — two disjoint kernel paths, same arithmetic."""
     from cake_b200.model import B200Transformer
-    cfg = llama3_8b(max_seq=1024)
+    cfg = llama3_8b(max_seq=1536)
     cfg.num_hidden_layers = 2
     sd = {}
     for i in range(2):
         sd.update(make_layer(cfg, i, "bf16", seed=5))
-    ctx = _ctx(cfg, sd, 1024)
+    ctx = _ctx(cfg, sd, 1536)
     blks = [B200Transformer.load(cfg.layer_name(i), ctx) for i in range(2)]
     batch = lambda pos: [(b.layer_name(), pos, i) for i, b in enumerate(blks)]
-    x = ctx.to_device(rand_x((1, 640, cfg.hidden_size), "bf16", seed=9))
-    full = blks[0].forward_batch(x, batch(0), ctx, blocks=blks)         # one-shot prefill of 640
+    # 1280 rows = 10 m-tiles: every projection has >= 148 tiles of 128 x 256, so all three epilogues of the large-tile
+    # tcgen05 GEMM (plain, +residual, silu*mul) are on this path; 632 rows (5 m-tiles) keep qkv / o / down on 128 x 128
+    x = ctx.to_device(rand_x((1, 1280, cfg.hidden_size), "bf16", seed=9))
+    full = blks[0].forward_batch(x, batch(0), ctx, blocks=blks)         # one-shot prefill of 1280
     ctx.sync()
     full = full.cpu()
     ctx.cache.clear()
-    blks[0].forward_batch(x[:, :632], batch(0), ctx, blocks=blks)       # prefill 632, then decode 8
-    for t in range(632, 640):
+    blks[0].forward_batch(x[:, :632], batch(0), ctx, blocks=blks)       # prefill 632 ...
+    blks[0].forward_batch(x[:, 632:1272], batch(632), ctx, blocks=blks)  # ... a second chunk on the non-empty cache, then decode 8
+    for t in range(1272, 1280):
         y = blks[0].forward_batch(x[:, t:t + 1], batch(t), ctx, blocks=blks)
         ctx.sync()
         e = max_ulp_err(to_np(y[0, 0]), to_np(full[0, t]), "bf16")
