@@ -108,9 +108,10 @@ class Config:
         rope = None
         if rs:
             rope = RopeScaling(
-                factor=float(rs.get("factor", 1.0)),
-                low_freq_factor=float(rs.get("low_freq_factor", 1.0)),
-                high_freq_factor=float(rs.get("high_freq_factor", 4.0)),
+                # serde defaults of the reference's RopeScaling: every missing number is 0.0 (config.rs)
+                factor=float(rs.get("factor", 0.0)),
+                low_freq_factor=float(rs.get("low_freq_factor", 0.0)),
+                high_freq_factor=float(rs.get("high_freq_factor", 0.0)),
                 original_max_position_embeddings=int(rs.get("original_max_position_embeddings", 0)),
                 rope_type=rs.get("rope_type"),
             )

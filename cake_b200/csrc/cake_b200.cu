@@ -347,6 +347,8 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
   if (!cfg || !out) return fail(CAKE_B200_EINVAL, "null argument");
   if (cfg->dtype != CAKE_B200_BF16 && cfg->dtype != CAKE_B200_F16)
     return fail(CAKE_B200_EINVAL, "dtype %d unsupported (bf16=0, f16=1)", cfg->dtype);
+  if (cfg->hidden < 1 || cfg->inter < 1 || cfg->n_heads < 1 || cfg->n_kv_heads < 1 || cfg->n_layers < 1 || cfg->vocab < 1 || cfg->max_seq < 1)
+    return fail(CAKE_B200_EINVAL, "config dimensions must be positive");
   if (cfg->n_heads % cfg->n_kv_heads != 0 || cfg->n_heads / cfg->n_kv_heads > ATTN_MAX_G)
     return fail(CAKE_B200_EINVAL, "n_heads/n_kv_heads must be an integer <= %d", ATTN_MAX_G);
   if (cfg->head_dim != 16 && cfg->head_dim != 32 && cfg->head_dim != 64 && cfg->head_dim != 128 && cfg->head_dim != 256)
@@ -1116,7 +1118,7 @@ extern "C" int cake_b200_forward_batch(cake_b200_ctx *c, cake_b200_block *const 
                                        int seq, int index_pos) {
   if (!c || !blocks || !block_idx || !kc || !x_dev || !y_dev || n_blocks < 1) return fail(CAKE_B200_EINVAL, "null/empty argument");
   if (batch != kc->batch) return fail(CAKE_B200_EINVAL, "batch %d != cache batch %d", batch, kc->batch);
-  if (seq < 1 || index_pos < 0 || index_pos + seq > kc->cap)
+  if (seq < 1 || index_pos < 0 || (long long)index_pos + (long long)seq > (long long)kc->cap)
     return fail(CAKE_B200_ESTATE, "index_pos %d + seq %d exceeds cache capacity %d", index_pos, seq, kc->cap);
   CU(cudaSetDevice(c->device));
   RC(wait_loads(c));
@@ -1157,7 +1159,11 @@ static int io_reserve(cake_b200_ctx *c, size_t bytes) {
 extern "C" int cake_b200_forward_batch_host(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *block_idx,
                                             int n_blocks, cake_b200_cache *kc, const void *x_host, void *y_host,
                                             int batch, int seq, int index_pos) {
-  if (!c || !x_host || !y_host) return fail(CAKE_B200_EINVAL, "null argument");
+  if (!c || !x_host || !y_host || !kc) return fail(CAKE_B200_EINVAL, "null argument");
+  // validated BEFORE any size is derived from them: the dims may come off the wire (cake_worker)
+  if (batch < 1 || seq < 1 || batch != kc->batch) return fail(CAKE_B200_EINVAL, "batch %d (cache batch %d) / seq %d out of range", batch, kc->batch, seq);
+  if (index_pos < 0 || (long long)index_pos + (long long)seq > (long long)kc->cap)
+    return fail(CAKE_B200_ESTATE, "index_pos %d + seq %d exceeds cache capacity %d", index_pos, seq, kc->cap);
   CU(cudaSetDevice(c->device));
   const size_t bytes = (size_t)batch * seq * c->cfg.hidden * c->es;
   RC(io_reserve(c, bytes));

@@ -212,9 +212,9 @@ struct Config {
         const int orig = (int)rs->number("original_max_position_embeddings", 0);
         if (t && t->str == "llama3" && orig > 0) {  // cache.rs:49-80
           c.rope_llama3 = 1;
-          c.rope_factor = (float)rs->number("factor", 1.0);
-          c.rope_low = (float)rs->number("low_freq_factor", 1.0);
-          c.rope_high = (float)rs->number("high_freq_factor", 4.0);
+          c.rope_factor = (float)rs->number("factor", 0.0);            // serde defaults of the reference's RopeScaling
+          c.rope_low = (float)rs->number("low_freq_factor", 0.0);
+          c.rope_high = (float)rs->number("high_freq_factor", 0.0);
           c.rope_orig_max = orig;
         }
       }

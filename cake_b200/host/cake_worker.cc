@@ -148,6 +148,13 @@ struct B200Backend : cw::Backend {
       auto where = [&](size_t i) { return "forward pass failed for layer " + std::get<0>(ops[i]) + " (block_idx=" + std::to_string(std::get<2>(ops[i])) + "): "; };
       if (x.dtype != want) throw Error(where(0) + "activation dtype tag " + std::to_string((int)x.dtype) + " is not the model dtype " + ctx.dtype_name);
       if (x.shape.size() != 3 || x.shape[2] != (uint64_t)ctx.config.c.hidden) throw Error(where(0) + "unexpected activation shape");
+      // u64 fields from an untrusted master are narrowed to int below: bound them first (a [0, 2^32+5, H] shape has numel 0
+      // and passes RawTensor::validate)
+      const uint64_t lim = (uint64_t)ctx.config.c.max_seq;
+      if (x.shape[0] < 1 || x.shape[0] > 1024 || x.shape[1] < 1 || x.shape[1] > lim) throw Error(where(0) + "activation batch / sequence out of range");
+      for (size_t k = 0; k < ops.size(); k++)
+        if (std::get<1>(ops[k]) > lim || std::get<2>(ops[k]) > (uint64_t)ctx.config.c.n_layers)
+          throw Error(where(k) + "index_pos / block_idx out of range");
       cw::RawTensor cur = x, next = x;
       std::lock_guard<std::mutex> g(be.mu);
       size_t i = 0;
