@@ -218,6 +218,29 @@ static int launch_pdl(cake_b200_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 
   return CAKE_B200_OK;
 }
 
+// the same with a thread-block cluster of `cluster` CTAs along x (TMA multicast between the CTAs of a pair)
+template <typename... KArgs, typename... Args>
+static int launch_cluster_pdl(cake_b200_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, unsigned cluster, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = cluster;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  CU(cudaLaunchKernelEx(&cfg, kern, KArgs(args)...));
+  if (c->capturing) c->g_kernels++;
+  else c->launches++;
+  return CAKE_B200_OK;
+}
+
 // ------------------------------------------------------------------------------------------ GEMV plan + launch
 struct GemvPlan {
   int KC, RS, WPR, RPW, n_stages, max_rows, grid;
@@ -295,7 +318,8 @@ template <typename T> static int set_smem_attrs_T() {
   CU(cudaFuncSetAttribute(attn_prefill_mma_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * FA_BN * 64 * 2));
 #define SETT(EPI)                                                                                                                  \
   CU(cudaFuncSetAttribute(gemm_tc_kernel<T, EPI, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));      \
-  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, EPI, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, EPI, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));      \
+  CU(cudaFuncSetAttribute(gemm_tc_kernel<T, EPI, 256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));
   SETT(TCE_PLAIN) SETT(TCE_RESIDUAL) SETT(TCE_SWIGLU)
 #undef SETT
   return CAKE_B200_OK;
@@ -1011,12 +1035,19 @@ static int gemm_tc_T(cake_b200_ctx *c, const void *A, const void *W, const void 
   const int tiles_m = (M + TC_BM - 1) / TC_BM;
   const bool big = force_bn ? force_bn == 256 && N % 256 == 0 : (N % 256 == 0 && tiles_m * (N / 256) >= c->sm_count);
   const int bn = big ? 256 : 128;
+  // pairs of CTAs sharing the W tile by TMA multicast (gemm_tc.cuh MC): needs an even number of 128-row tiles
+  static const int no_mc = []() { const char *e = getenv("CAKE_B200_TC_MC"); return (e && e[0] == '0') ? 1 : 0; }();
+  const bool mc = big && !no_mc && M % 256 == 0 && (tiles_m / 2) * (N / 256) >= c->sm_count / 2;
   CUtensorMap ma, mb;
   RC(make_tmap(&ma, A, (uint64_t)M, (uint64_t)K, c->cfg.dtype, TC_BM));
-  RC(make_tmap(&mb, W, (uint64_t)N, (uint64_t)K, c->cfg.dtype, (uint32_t)bn));
+  RC(make_tmap(&mb, W, (uint64_t)N, (uint64_t)K, c->cfg.dtype, mc ? 128u : (uint32_t)bn));
   TcParams p{bias, res, C, M, N, K, c->cfg.use_gelu_mlp ? 1 : 0};
   const int tiles = tiles_m * (N / bn);
   dim3 grid(tiles < c->sm_count ? tiles : c->sm_count), block(TC_THREADS);
+  if (mc) {
+    dim3 g2((unsigned)(c->sm_count & ~1));
+    return launch_cluster_pdl(c, gemm_tc_kernel<T, EPI, 256, true>, g2, block, (size_t)TcCfg<256>::SMEM_BYTES, 2u, ma, mb, p);
+  }
   if (big) return launch_pdl(c, gemm_tc_kernel<T, EPI, 256>, grid, block, (size_t)TcCfg<256>::SMEM_BYTES, ma, mb, p);
   return launch_pdl(c, gemm_tc_kernel<T, EPI, 128>, grid, block, (size_t)TcCfg<128>::SMEM_BYTES, ma, mb, p);
 }

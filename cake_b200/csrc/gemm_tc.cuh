@@ -65,6 +65,27 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same load delivered to the same shared-memory offset of every CTA in cta_mask (and signalling each one's mbarrier)
+__device__ __forceinline__ void tma_load_2d_mc(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t *bar, uint16_t cta_mask) {  // arrive on the barrier at this offset in every CTA of the mask
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
@@ -107,9 +128,16 @@ template <> __device__ __forceinline__ uint32_t tc_idesc<__half>(int bn) {
   return (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-template <typename T, int EPI, int BN>
+// MC (BN == 256 only, launched as clusters of 2 CTAs, M % 256 == 0): the two CTAs of a cluster work on vertically adjacent
+// 128-row tiles of the SAME 256-column panel and share its W tile — each loads one 128-row half of it and multicasts the
+// half into both CTAs' shared memory, so a CTA pulls 16 KB (A) + 16 KB (its W half) instead of 48 KB per k-block out of L2:
+// the operand traffic of a 2-CTA MMA without giving up the independent cta_group::1 accumulators.  A stage may be refilled
+// only when BOTH CTAs have consumed it (the peer's multicast lands in our buffer): every MMA commit arrives on the empty
+// barrier of both CTAs (count 2).
+template <typename T, int EPI, int BN, bool MC = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  static_assert(!MC || BN == 256, "multicast variant is built for 128 x 256 tiles");
   extern __shared__ unsigned char smem_raw_tc[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(smem_raw_tc) + 1023) & ~(uintptr_t)1023);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + TcCfg<BN>::STAGES * TcCfg<BN>::STAGE_BYTES);
@@ -119,11 +147,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = p.N / BN, n_tiles = tiles_m * tiles_n;
+  const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = p.N / BN;
   const int kblocks = p.K / TC_BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < TcCfg<BN>::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < TcCfg<BN>::STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], MC ? 2 : 1); }
     for (int a = 0; a < 2; a++) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], 128); }
     mbar_fence_init();
   }
@@ -134,9 +162,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (MC) cluster_sync_all();  // the peer's barriers exist before anything is multicast to it
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
+  // work distribution: non-MC: one tile per CTA and round; MC: one (256-row, 256-column) unit per cluster and round
+  const uint32_t crank = MC ? cluster_rank() : 0u;
+  const int first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, stride = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int units_m = MC ? tiles_m / 2 : tiles_m, n_units = units_m * tiles_n;
+  auto unit_tile = [&](int u, int &m0, int &n0) {
+    tc_tile(u, units_m, tiles_n, BN, m0, n0);   // m0 in units of TC_BM rows of the unit grid
+    if (MC) m0 = m0 * 2 + (int)crank * TC_BM;
+  };
 
   if (warp == 0) {
     // ===================== TMA producer ==================================================================
@@ -145,15 +182,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
       int s = 0;
       uint32_t ph = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      for (int t = first; t < n_units; t += stride) {
         int m0, n0;
-        tc_tile(t, tiles_m, tiles_n, BN, m0, n0);
+        unit_tile(t, m0, n0);
         for (int kb = 0; kb < kblocks; kb++) {
           mbar_wait(&empty[s], ph ^ 1u);
           unsigned char *st = smem + (size_t)s * TcCfg<BN>::STAGE_BYTES;
           mbar_arrive_expect_tx(&full[s], TcCfg<BN>::STAGE_BYTES);
           tma_load_2d(st, &map_a, kb * TC_BK, m0, &full[s]);
-          tma_load_2d(st + TC_BM * TC_BK * 2, &map_b, kb * TC_BK, n0, &full[s]);
+          if (MC)  // map_b has a 128-row box here: our half of the W tile, delivered to both CTAs
+            tma_load_2d_mc(st + TC_BM * TC_BK * 2 + crank * (128 * TC_BK * 2), &map_b, kb * TC_BK, n0 + (int)crank * 128, &full[s], (uint16_t)3);
+          else
+            tma_load_2d(st + TC_BM * TC_BK * 2, &map_b, kb * TC_BK, n0, &full[s]);
           if (++s == TcCfg<BN>::STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -165,7 +205,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+      for (int t = first; t < n_units; t += stride, it++) {
         const int a = it & 1;
         const uint32_t aph = (uint32_t)(it >> 1) & 1u;
         mbar_wait(&acc_empty[a], aph ^ 1u);  // the epilogue has drained this accumulator
@@ -179,7 +219,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; k++)  // +32 bytes (2 x 16 B units) per K=16 slab inside the swizzle atom
             tc_mma_f16(tmem_c, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-          tc_commit(&empty[s]);  // arrives when the MMAs above have read the stage
+          if (MC) tc_commit_mc(&empty[s], (uint16_t)3);  // ... in BOTH CTAs: the peer multicasts into this stage too
+          else tc_commit(&empty[s]);  // arrives when the MMAs above have read the stage
           if (++s == TcCfg<BN>::STAGES) { s = 0; ph ^= 1u; }
         }
         tc_commit(&acc_full[a]);  // accumulator complete
@@ -192,11 +233,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const T *res = reinterpret_cast<const T *>(p.residual);
     T *C = reinterpret_cast<T *>(p.C);
     int it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+    for (int t = first; t < n_units; t += stride, it++) {
       const int a = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       int m0, n0;
-      tc_tile(t, tiles_m, tiles_n, BN, m0, n0);
+      unit_tile(t, m0, n0);
       const int row = m0 + wq * 32 + lane;
       mbar_wait(&acc_full[a], aph);
       tc_fence_after();
@@ -249,6 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // nobody leaves while the peer may still signal our barriers
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BN) : "memory");

@@ -186,3 +186,34 @@ def test_llama3_8b_decode_at_2500_context_multi_tile_attention():
         e = max_ulp_err(to_np(y[0]), y_ref, "bf16")
         assert e <= 3.0, f"decode @{L0 + i}: {e} ulp"
     ctx.close()
+
+
+def test_llama3_8b_block_batch_gt_1_matches_oracle_per_sequence():
+    """BASELINE configs[4] is bs=32: the Forwarder's (b, s, H) contract with b > 1 at the Llama-3-8B layer widths — a
+    (2, 144, H) prefill (tcgen05 GEMMs over 288 rows, flash attention per sequence) and two (2, 1, H) steps — every
+    sequence against its own oracle run."""
+    from cake_b200.model import B200Transformer, Cache
+    cfg = llama3_8b(max_seq=256)
+    cfg.num_hidden_layers = 1
+    sd = make_layer(cfg, 0, "bf16", seed=41)
+    ctx = _ctx(cfg, sd, 256)
+    B, S = 2, 144
+    ctx.cache = Cache(ctx, batch=B, max_seq=256)
+    blk = B200Transformer.load(cfg.layer_name(0), ctx)
+    om = O.OracleModel(cfg, sd, "bf16", max_seq=256)
+    caches = [om.new_cache(256) for _ in range(B)]
+    x = rand_x((B, S + 2, cfg.hidden_size), "bf16", seed=12)
+    y = blk.forward(ctx.to_device(x[:, :S].contiguous()), 0, 0, ctx)
+    ctx.sync()
+    for b in range(B):
+        ref = om.block_forward(0, x[b, :S].float().numpy(), 0, caches[b])
+        e = max_ulp_err(to_np(y[b]), ref, "bf16")
+        assert e <= 3.0 and mean_ulp_err(to_np(y[b]), ref, "bf16") <= 0.25, f"prefill seq {b}: {e} ulp"
+    for t in (S, S + 1):
+        y = blk.forward(ctx.to_device(x[:, t:t + 1].contiguous()), t, 0, ctx)
+        ctx.sync()
+        for b in range(B):
+            ref = om.block_forward(0, x[b, t:t + 1].float().numpy(), t, caches[b])
+            e = max_ulp_err(to_np(y[b]), ref, "bf16")
+            assert e <= 3.0, f"step @{t} seq {b}: {e} ulp"
+    ctx.close()
