@@ -51,8 +51,11 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // (stride HD*2 bytes, a multiple of 128) land in 8 different bank groups
 template <int HD> __device__ __forceinline__ uint32_t fa_off(int r, int c) { return (uint32_t)(r * HD * 2 + ((c ^ (r & 7)) << 4)); }
 
+// Occupancy (ncu r02: 189 registers + 80 KB -> 2 CTAs = 2 warps per sub-partition, HMMA pipe 50 % active, issue-bound on
+// dependent MMA chains): the Q tile is only needed until its fragments sit in registers, so it is staged in the second V
+// buffer (64 KB per CTA instead of 80), and the register budget is capped for 3 CTAs per SM.
 template <typename T, int HD>
-__global__ void __launch_bounds__(FA_THREADS)
+__global__ void __launch_bounds__(FA_THREADS, (HD == 128) ? 3 : 4)
 attn_prefill_mma_kernel(const T *__restrict__ qkv, const T *__restrict__ kcache, const T *__restrict__ vcache, T *__restrict__ y,
                         int S, int n_heads, int n_kv, int cap, int pos0, float scale) {
   constexpr int CH = HD / 8;        // 16-byte chunks per row
@@ -61,9 +64,9 @@ attn_prefill_mma_kernel(const T *__restrict__ qkv, const T *__restrict__ kcache,
   constexpr int DT = HD / 8;        // 8-dim n-tiles of the output
   constexpr int TILE_B = FA_BN * HD * 2;
   extern __shared__ __align__(128) unsigned char fa_smem[];
-  unsigned char *q_s = fa_smem;                   // [64][HD]
-  unsigned char *k_s = q_s + FA_BM * HD * 2;      // [2][64][HD]
+  unsigned char *k_s = fa_smem;                   // [2][64][HD]
   unsigned char *v_s = k_s + 2 * TILE_B;          // [2][64][HD]
+  unsigned char *q_s = v_s + TILE_B;              // [64][HD]: aliases V buffer 1, which is first filled after the Q fragments are read
   pdl_launch_dependents();
   pdl_wait();
 
@@ -104,17 +107,19 @@ attn_prefill_mma_kernel(const T *__restrict__ qkv, const T *__restrict__ kcache,
   const int qpos0 = pos0 + m0 + warp * 16 + g;  // absolute position of this thread's first row (second: +8)
   const int mi = lane >> 3, lr = lane & 7;
 
+  // Q fragments first (they live in V buffer 1), then the pipeline may overwrite that buffer
+  cp_async_wait<0>();
+  __syncthreads();
+#pragma unroll
+  for (int ks = 0; ks < KS; ks++)
+    ldsm_x4(qf[ks], smem_u32(q_s) + fa_off<HD>(warp * 16 + (mi & 1) * 8 + lr, ks * 2 + (mi >> 1)));
+  __syncthreads();
   for (int j = 0; j < n_tiles; j++) {
     const int buf = j & 1;
     if (j + 1 < n_tiles) load_kv(j + 1, buf ^ 1);
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    if (j == 0) {
-#pragma unroll
-      for (int ks = 0; ks < KS; ks++)
-        ldsm_x4(qf[ks], smem_u32(q_s) + fa_off<HD>(warp * 16 + (mi & 1) * 8 + lr, ks * 2 + (mi >> 1)));
-    }
     // ---- S = Q K^T (16 x 64 per warp), fp32 ------------------------------------------------------------
     float s[NT][4];
 #pragma unroll

@@ -22,6 +22,7 @@
 #include "../../include/cake_b200.h"
 #include "attn_decode.cuh"
 #include "attn_prefill.cuh"
+#include "attn_prefill_tc.cuh"
 #include "common.cuh"
 #include "decode_mega.cuh"
 #include "gemm_tc.cuh"
@@ -314,8 +315,10 @@ template <typename T> static int set_smem_attrs_T() {
   CU(cudaFuncSetAttribute(decode_mega_kernel<T, HD, G>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   MK_FOR_ALL(SETC)
 #undef SETC
-  CU(cudaFuncSetAttribute(attn_prefill_mma_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * FA_BN * 128 * 2));
-  CU(cudaFuncSetAttribute(attn_prefill_mma_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * FA_BN * 64 * 2));
+  CU(cudaFuncSetAttribute(attn_prefill_mma_kernel<T, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * FA_BN * 128 * 2));
+  CU(cudaFuncSetAttribute(attn_prefill_mma_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * FA_BN * 64 * 2));
+  CU(cudaFuncSetAttribute(attn_prefill_tc_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, FT_SMEM_BYTES));
+  CU(cudaFuncSetAttribute(attn_prefill_tc_kernel<T>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 #define SETT(EPI)                                                                                                                  \
   CU(cudaFuncSetAttribute(gemm_tc_kernel<T, EPI, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES));      \
   CU(cudaFuncSetAttribute(gemm_tc_kernel<T, EPI, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES));      \
@@ -1025,6 +1028,23 @@ static int make_tmap(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t K,
   return CAKE_B200_OK;
 }
 
+// [slabs][rows][cols] tensor of D with a slab stride of slab_rows rows -> 3-D map, (64 x box_rows x 1) box, 128-byte swizzle.
+// `rows` is the VISIBLE extent: the TMA unit zero-fills rows past it (query rows >= S, keys >= the attended length), so a
+// tile never carries a neighbouring slab's rows or uninitialised cache memory into an MMA.
+static int make_tmap3(CUtensorMap *m, const void *ptr, uint64_t cols, uint64_t row_stride_elems, uint64_t rows, uint64_t slab_rows,
+                      uint64_t slabs, int dtype, uint32_t box_rows) {
+  RC(tmap_init());
+  const cuuint64_t gdim[3] = {cols, rows, slabs};
+  const cuuint64_t gstride[2] = {row_stride_elems * 2, slab_rows * row_stride_elems * 2};
+  const cuuint32_t box[3] = {64u, box_rows, 1u};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult r = g_encode_tiled(m, dtype == CAKE_B200_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                                    const_cast<void *>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CAKE_B200_ECUDA, "cuTensorMapEncodeTiled(3d: cols=%llu rows=%llu slabs=%llu) -> CUresult %d", (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)slabs, (int)r);
+  return CAKE_B200_OK;
+}
+
 static bool tc_gemm_ok(int M, int N, int K) { return M >= 1 && N % TC_BN == 0 && K % TC_BK == 0; }
 
 // C = epi(A[M,K] W[N,K]^T) on the tensor cores (gemm_tc.cuh)
@@ -1114,11 +1134,25 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
       if (use_tc && (hd == 64 || hd == 128)) {  // tensor-core flash attention (attn_prefill.cuh)
         dim3 grid((S + FA_BM - 1) / FA_BM, f.n_heads, B), block(FA_THREADS);
         const float sc = (float)(1.0 / sqrt((double)hd));
-        if (hd == 128)
-          RC(launch_pdl(c, attn_prefill_mma_kernel<T, 128>, grid, block, (size_t)5 * FA_BN * 128 * 2, (const T *)c->pf_qkv,
+        // head_dim 128: tcgen05 flash attention (attn_prefill_tc.cuh); CAKE_B200_FA=mma keeps the mma.sync kernel (A/B aid)
+        static const bool fa_mma = []() { const char *e = getenv("CAKE_B200_FA"); return e && !strcmp(e, "mma"); }();
+        static const float fa_tau = []() { const char *e = getenv("CAKE_B200_FA_TAU"); return e ? (float)atof(e) : 5.545f; }();
+        if (hd == 128 && !fa_mma) {
+          CUtensorMap mq, mk, mv;
+          const uint64_t nqkv_cols = (uint64_t)(f.n_heads + 2 * f.n_kv_heads) * hd;
+          RC(make_tmap3(&mq, c->pf_qkv, nqkv_cols, nqkv_cols, (uint64_t)S, (uint64_t)S, (uint64_t)B, f.dtype, FT_BM));
+          RC(make_tmap3(&mk, (const T *)kc->k[l] + wsoff, (uint64_t)hd, (uint64_t)hd, (uint64_t)(apos0 + S), (uint64_t)kc->cap,
+                        (uint64_t)B * f.n_kv_heads, f.dtype, FT_BN));
+          RC(make_tmap3(&mv, (const T *)kc->v[l] + wsoff, (uint64_t)hd, (uint64_t)hd, (uint64_t)(apos0 + S), (uint64_t)kc->cap,
+                        (uint64_t)B * f.n_kv_heads, f.dtype, FT_BN));
+          dim3 gt((S + FT_BM - 1) / FT_BM, f.n_heads, B);
+          RC(launch_pdl(c, attn_prefill_tc_kernel<T>, gt, dim3(FT_THREADS), (size_t)FT_SMEM_BYTES, mq, mk, mv, (T *)c->pf_y, S, f.n_heads,
+                        f.n_kv_heads, apos0, sc, fa_tau));
+        } else if (hd == 128)
+          RC(launch_pdl(c, attn_prefill_mma_kernel<T, 128>, grid, block, (size_t)4 * FA_BN * 128 * 2, (const T *)c->pf_qkv,
                         (const T *)kc->k[l] + wsoff, (const T *)kc->v[l] + wsoff, (T *)c->pf_y, S, f.n_heads, f.n_kv_heads, kc->cap, apos0, sc));
         else
-          RC(launch_pdl(c, attn_prefill_mma_kernel<T, 64>, grid, block, (size_t)5 * FA_BN * 64 * 2, (const T *)c->pf_qkv,
+          RC(launch_pdl(c, attn_prefill_mma_kernel<T, 64>, grid, block, (size_t)4 * FA_BN * 64 * 2, (const T *)c->pf_qkv,
                         (const T *)kc->k[l] + wsoff, (const T *)kc->v[l] + wsoff, (T *)c->pf_y, S, f.n_heads, f.n_kv_heads, kc->cap, apos0, sc));
       } else {
         const long items = (long)M * f.n_heads;
