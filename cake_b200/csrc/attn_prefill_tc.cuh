@@ -10,13 +10,15 @@
 // One CTA = one 128-query tile of one head; two CTAs per SM (2 x 256 TMEM columns, 2 x 97 KB shared memory), so one CTA's
 // softmax overlaps the other's MMAs.  192 threads:
 //   warps 0-3  softmax: thread = query row (TMEM lane).  tcgen05.ld of the 128 x 64 S tile, scale + mask + running max /
-//              sum entirely in-thread (no shuffles), P_hi / P_lo written to shared memory in the K-major 128-byte-swizzled
-//              layout the MMA's A operand expects, lazy rescale of O in TMEM (only when the row max grew by more than tau,
-//              P stays <= e^tau; the final O / l is the same quotient), epilogue O / l -> D -> global
-//   warp 4     TMA producer: Q tile once, then one 64-key K tile and V tile per step (3-D maps: keys past the visible
-//              length and query rows past S are zero-filled by the TMA unit, nothing uninitialised reaches an MMA)
-//   warp 5     TMEM allocator + MMA issuer (one thread): S = Q K^T (8 x M128 N64 K16), O += P_hi V + P_lo V
-//              (8 x M128 N128 K16, V consumed straight from its [key][hd] cache layout as an MN-major B operand)
+//              sum entirely in-thread (no shuffles), P_hi / P_lo packed to D and stored with tcgen05.st over the S tile they
+//              came from (the MMA takes its A operand from TMEM), lazy rescale of O in TMEM (only when the row max grew by
+//              more than tau, P stays <= e^tau; the final O / l is the same quotient), epilogue O / l -> D -> global
+//   warp 4     TMA producer: Q tile once, then 64-key K and V tiles through two-stage rings (3-D maps: keys past the
+//              visible length and query rows past S are zero-filled by the TMA unit, nothing uninitialised reaches an MMA)
+//   warp 5     TMEM allocator + MMA issuer (one thread): S = Q K^T (8 x M128 N64 K16, operands from shared memory) into one
+//              of two S buffers — S of tile j+1 is issued BEFORE P V of tile j, so the softmax of j+1 runs under it —
+//              and O += P_hi V + P_lo V (8 x M128 N128 K16, P from TMEM, V consumed straight from its [key][hd] cache
+//              layout as an MN-major B operand)
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -25,9 +27,8 @@ namespace cake {
 constexpr int FT_BM = 128, FT_BN = 64, FT_HD = 128, FT_THREADS = 192;
 constexpr int FT_Q_BYTES = FT_BM * FT_HD * 2;   // 32 KB: two 128-row x 64-dim boxes
 constexpr int FT_KV_BYTES = FT_BN * FT_HD * 2;  // 16 KB: two 64-key x 64-dim boxes
-constexpr int FT_P_BYTES = FT_BM * FT_BN * 2;   // 16 KB each for P_hi and P_lo
-constexpr int FT_SMEM_BYTES = FT_Q_BYTES + 2 * FT_KV_BYTES + 2 * FT_P_BYTES + 1024 /*align*/ + 128 /*barriers*/;
-constexpr int FT_TMEM_COLS = 256;               // S: columns 0..63, O: columns 128..255
+constexpr int FT_SMEM_BYTES = FT_Q_BYTES + 4 * FT_KV_BYTES + 1024 /*align*/ + 128 /*barriers*/;  // Q + 2 K stages + 2 V stages
+constexpr int FT_TMEM_COLS = 256;               // S/P buffers: columns 0..63 and 64..127 (P_hi | P_lo packed over S), O: 128..255
 
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int c0, int c1, int c2, uint64_t *bar) {
   asm volatile(
@@ -48,7 +49,20 @@ __device__ __forceinline__ void tc_st32(uint32_t taddr, const uint32_t (&r)[32])
       : "memory");
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] x B[smem]: the A operand (M = lane, K packed two D values per 32-bit column) comes from tensor memory
+__device__ __forceinline__ void tc_mma_f16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ float ft_ex2(float x) {  // MUFU.EX2: 2^x, 2^-inf = 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // MN-major B operand (V: rows = keys = K dimension, 64 contiguous head dims = one 128-byte swizzle row):
 // LBO = distance between the two 64-dim halves, SBO = 1024 B between groups of 8 keys
@@ -61,17 +75,16 @@ template <typename T>
 __global__ void __launch_bounds__(FT_THREADS, 2)
 attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                        const __grid_constant__ CUtensorMap map_v, T *__restrict__ y, int S, int n_heads, int n_kv, int pos0,
-                       float scale, float tau) {
+                       float scale_log2, float tau_log2) {
   extern __shared__ unsigned char ft_smem_raw[];
   unsigned char *smem = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~(uintptr_t)1023);
   unsigned char *q_s = smem;
-  unsigned char *k_s = q_s + FT_Q_BYTES;
-  unsigned char *v_s = k_s + FT_KV_BYTES;
-  unsigned char *p_s = v_s + FT_KV_BYTES;  // P_hi, then P_lo
-  uint64_t *bars = reinterpret_cast<uint64_t *>(p_s + 2 * FT_P_BYTES);
-  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 2, *v_full = bars + 3, *v_empty = bars + 4, *s_full = bars + 5,
-           *p_full = bars + 6, *o_full = bars + 7;
-  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 8);
+  unsigned char *k_s = q_s + FT_Q_BYTES;       // [2] stages
+  unsigned char *v_s = k_s + 2 * FT_KV_BYTES;  // [2] stages
+  uint64_t *bars = reinterpret_cast<uint64_t *>(v_s + 2 * FT_KV_BYTES);
+  uint64_t *q_full = bars, *k_full = bars + 1, *k_empty = bars + 3, *v_full = bars + 5, *v_empty = bars + 7, *s_full = bars + 9,
+           *p_full = bars + 11, *o_full = bars + 12;
+  uint32_t *tmem_ptr = reinterpret_cast<uint32_t *>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int mt = gridDim.x - 1 - blockIdx.x;  // heavy (late) query tiles first
@@ -81,7 +94,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   const int n_tiles = (kv_end + FT_BN - 1) / FT_BN;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 8; i++) mbar_init(&bars[i], i == 6 ? 128u : 1u);
+    for (int i = 0; i < 13; i++) mbar_init(&bars[i], i == 11 ? 128u : 1u);
     mbar_fence_init();
   }
   if (warp == 5) {
@@ -94,7 +107,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
   pdl_launch_dependents();
   pdl_wait();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 128u;
+  const uint32_t tmem_o = tmem_base + 128u;  // S/P buffer i at columns 64 i
 
   if (warp == 4) {
     // ===================== TMA producer ====================================================================
@@ -107,46 +120,57 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       tma_load_3d(q_s + FT_Q_BYTES / 2, &map_q, h * FT_HD + 64, m0, b, q_full);
       const int slab = b * n_kv + kvh;
       for (int j = 0; j < n_tiles; j++) {
-        if (j > 0) mbar_wait(k_empty, (uint32_t)(j - 1) & 1u);
-        mbar_arrive_expect_tx(k_full, FT_KV_BYTES);
-        tma_load_3d(k_s, &map_k, 0, j * FT_BN, slab, k_full);
-        tma_load_3d(k_s + FT_KV_BYTES / 2, &map_k, 64, j * FT_BN, slab, k_full);
-        if (j > 0) mbar_wait(v_empty, (uint32_t)(j - 1) & 1u);
-        mbar_arrive_expect_tx(v_full, FT_KV_BYTES);
-        tma_load_3d(v_s, &map_v, 0, j * FT_BN, slab, v_full);
-        tma_load_3d(v_s + FT_KV_BYTES / 2, &map_v, 64, j * FT_BN, slab, v_full);
+        const int st = j & 1;
+        const uint32_t eph = (uint32_t)((j >> 1) - 1) & 1u;  // the stage's previous use (tile j-2) has been consumed
+        unsigned char *kd = k_s + st * FT_KV_BYTES, *vd = v_s + st * FT_KV_BYTES;
+        if (j >= 2) mbar_wait(&k_empty[st], eph);
+        mbar_arrive_expect_tx(&k_full[st], FT_KV_BYTES);
+        tma_load_3d(kd, &map_k, 0, j * FT_BN, slab, &k_full[st]);
+        tma_load_3d(kd + FT_KV_BYTES / 2, &map_k, 64, j * FT_BN, slab, &k_full[st]);
+        if (j >= 2) mbar_wait(&v_empty[st], eph);
+        mbar_arrive_expect_tx(&v_full[st], FT_KV_BYTES);
+        tma_load_3d(vd, &map_v, 0, j * FT_BN, slab, &v_full[st]);
+        tma_load_3d(vd + FT_KV_BYTES / 2, &map_v, 64, j * FT_BN, slab, &v_full[st]);
       }
     }
   } else if (warp == 5) {
     // ===================== MMA issuer (one thread) =========================================================
     if (lane == 0) {
       const uint32_t idesc_s = tc_idesc<T>(FT_BN);                   // M128 N64, A and B K-major
-      const uint32_t idesc_o = tc_idesc<T>(FT_HD) | (1u << 16);      // M128 N128, B (V) MN-major
-      mbar_wait(q_full, 0);
-      for (int j = 0; j < n_tiles; j++) {
-        const uint32_t ph = (uint32_t)j & 1u;
-        mbar_wait(k_full, ph);
+      const uint32_t idesc_o = tc_idesc<T>(FT_HD) | (1u << 16);      // M128 N128, A from TMEM, B (V) MN-major
+      auto issue_s = [&](int j) {  // S_j = Q K_j^T into S buffer j&1
+        const int st = j & 1;
+        mbar_wait(&k_full[st], (uint32_t)(j >> 1) & 1u);
         tc_fence_after();
+        const unsigned char *kt = k_s + st * FT_KV_BYTES;
 #pragma unroll
         for (int k = 0; k < FT_HD / 16; k++) {  // head dims 16k..16k+15: box k/4, 32-byte slab k%4 inside the swizzle row
           const uint64_t da = tc_smem_desc(q_s + (k >> 2) * (FT_Q_BYTES / 2)) + (uint64_t)((k & 3) * 2);
-          const uint64_t db = tc_smem_desc(k_s + (k >> 2) * (FT_KV_BYTES / 2)) + (uint64_t)((k & 3) * 2);
-          tc_mma_f16(tmem_s, da, db, idesc_s, k ? 1u : 0u);
+          const uint64_t db = tc_smem_desc(kt + (k >> 2) * (FT_KV_BYTES / 2)) + (uint64_t)((k & 3) * 2);
+          tc_mma_f16(tmem_base + (uint32_t)(st * 64), da, db, idesc_s, k ? 1u : 0u);
         }
-        tc_commit(k_empty);
-        tc_commit(s_full);
-        mbar_wait(p_full, ph);  // P_j in shared memory, S consumed, O rescaled
-        mbar_wait(v_full, ph);
+        tc_commit(&k_empty[st]);
+        tc_commit(&s_full[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < n_tiles; j++) {
+        const int st = j & 1;
+        // S of the next tile first: its buffer held P of tile j-1, whose P V is already queued ahead of it in the pipe
+        if (j + 1 < n_tiles) issue_s(j + 1);
+        mbar_wait(p_full, (uint32_t)j & 1u);  // P_j in TMEM (over S_j), O rescaled
+        mbar_wait(&v_full[st], (uint32_t)(j >> 1) & 1u);
         tc_fence_after();
+        const unsigned char *vt = v_s + st * FT_KV_BYTES;
 #pragma unroll
         for (int half = 0; half < 2; half++)
 #pragma unroll
-          for (int ks = 0; ks < FT_BN / 16; ks++) {  // keys 16ks..16ks+15
-            const uint64_t da = tc_smem_desc(p_s + half * FT_P_BYTES) + (uint64_t)(ks * 2);
-            const uint64_t db = ft_desc_mn(v_s + ks * 2048, FT_KV_BYTES / 2);
-            tc_mma_f16(tmem_o, da, db, idesc_o, (j | half | ks) ? 1u : 0u);
+          for (int ks = 0; ks < FT_BN / 16; ks++) {  // keys 16ks..16ks+15 = 8 packed columns of P_hi (0..31) or P_lo (32..63)
+            const uint32_t ta = tmem_base + (uint32_t)(st * 64 + half * 32 + ks * 8);
+            const uint64_t db = ft_desc_mn(vt + ks * 2048, FT_KV_BYTES / 2);
+            tc_mma_f16_ts(tmem_o, ta, db, idesc_o, (j | half | ks) ? 1u : 0u);
           }
-        tc_commit(v_empty);
+        tc_commit(&v_empty[st]);
         tc_commit(o_full);
       }
     }
@@ -155,57 +179,55 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
     const int row = warp * 32 + lane;
     const int qp = pos0 + m0 + row;  // absolute position of this row's query
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    unsigned char *prow_hi = p_s + row * 128, *prow_lo = p_s + FT_P_BYTES + row * 128;
+    float m_run = -INFINITY, l_run = 0.f;  // m_run: reference max of the raw scores (unscaled)
     for (int j = 0; j < n_tiles; j++) {
-      mbar_wait(s_full, (uint32_t)j & 1u);
+      const uint32_t tmem_sp = tmem_base + lane_addr + (uint32_t)((j & 1) * 64);
+      mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1u);
       tc_fence_after();
       float sv[FT_BN];
       {
         uint32_t r[32];
-        tc_ld32(tmem_s + lane_addr, r);
+        tc_ld32(tmem_sp, r);
 #pragma unroll
         for (int i = 0; i < 32; i++) sv[i] = __uint_as_float(r[i]);
-        tc_ld32(tmem_s + lane_addr + 32u, r);
+        tc_ld32(tmem_sp + 32u, r);
 #pragma unroll
         for (int i = 0; i < 32; i++) sv[32 + i] = __uint_as_float(r[i]);
       }
-      // scale, causal mask (attention.rs:314-341) — only tiles reaching past the first row's position need the compare
+      // causal mask (attention.rs:314-341) — only tiles reaching past the first row's position need the compare
       float mx = -INFINITY;
       if (j * FT_BN + FT_BN - 1 > pos0 + m0) {
 #pragma unroll
         for (int i = 0; i < FT_BN; i++) {
-          const float v = (j * FT_BN + i <= qp) ? sv[i] * scale : -INFINITY;
-          sv[i] = v;
-          mx = fmaxf(mx, v);
+          if (j * FT_BN + i > qp) sv[i] = -INFINITY;
+          mx = fmaxf(mx, sv[i]);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < FT_BN; i++) {
-          sv[i] *= scale;
-          mx = fmaxf(mx, sv[i]);
-        }
+        for (int i = 0; i < FT_BN; i++) mx = fmaxf(mx, sv[i]);
       }
       // running max with lazy update: keep the old reference while the new max exceeds it by at most tau
       float fac = 1.f;
       bool resc = false;
       if (j == 0) {
         m_run = mx;
-      } else if (mx - m_run > tau) {
-        fac = __expf(m_run - mx);
+      } else if ((mx - m_run) * scale_log2 > tau_log2) {
+        fac = ft_ex2((m_run - mx) * scale_log2);
         m_run = mx;
         resc = true;
       }
+      // p = exp((s - m) / sqrt(hd)) = 2^(s c - m c), c = log2(e) / sqrt(hd): one FFMA + one MUFU.EX2 per score; 2^-inf = 0 masks
+      const float mc = m_run * scale_log2;
       float rs = 0.f;
 #pragma unroll
       for (int i = 0; i < FT_BN; i++) {
-        const float p = __expf(sv[i] - m_run);  // MUFU ex2-based exp, exp(-inf) = 0 for masked keys
+        const float p = ft_ex2(fmaf(sv[i], scale_log2, -mc));
         sv[i] = p;
         rs += p;
       }
       l_run = l_run * fac + rs;
       if (j > 0) {
-        mbar_wait(o_full, (uint32_t)(j - 1) & 1u);  // P V of the previous tile is complete: P buffers free, O stable
+        mbar_wait(o_full, (uint32_t)(j - 1) & 1u);  // P V of the previous tile is complete: O stable
         tc_fence_after();
         if (__any_sync(0xffffffffu, resc)) {
 #pragma unroll 1
@@ -216,25 +238,22 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
             for (int i = 0; i < 32; i++) r[i] = __float_as_uint(__uint_as_float(r[i]) * fac);
             tc_st32(tmem_o + lane_addr + (uint32_t)c0, r);
           }
-          tc_wait_st();
         }
       }
-      // P = P_hi + P_lo, both in D, into the swizzled K-major A tiles (row = 128 bytes = 64 keys)
+      // P = P_hi + P_lo, both in D, packed two keys per column over the S tile: columns 0..31 P_hi, 32..63 P_lo
+      {
+        uint32_t hi[32], lo[32];
 #pragma unroll
-      for (int c = 0; c < FT_BN / 8; c++) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const float p0 = sv[c * 8 + 2 * q], p1 = sv[c * 8 + 2 * q + 1];
+        for (int i = 0; i < 32; i++) {
+          const float p0 = sv[2 * i], p1 = sv[2 * i + 1];
           const float h0 = rnd<T>(p0), h1 = rnd<T>(p1);
-          hi[q] = pack2<T>(h0, h1);
-          lo[q] = pack2<T>(p0 - h0, p1 - h1);
+          hi[i] = pack2<T>(h0, h1);
+          lo[i] = pack2<T>(p0 - h0, p1 - h1);
         }
-        const int off = (c ^ (row & 7)) << 4;
-        *reinterpret_cast<uint4 *>(prow_hi + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4 *>(prow_lo + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        tc_st32(tmem_sp, hi);
+        tc_st32(tmem_sp + 32u, lo);
       }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+      tc_wait_st();
       tc_fence_before();
       mbar_arrive(p_full);
     }

@@ -1147,7 +1147,7 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
                         (uint64_t)B * f.n_kv_heads, f.dtype, FT_BN));
           dim3 gt((S + FT_BM - 1) / FT_BM, f.n_heads, B);
           RC(launch_pdl(c, attn_prefill_tc_kernel<T>, gt, dim3(FT_THREADS), (size_t)FT_SMEM_BYTES, mq, mk, mv, (T *)c->pf_y, S, f.n_heads,
-                        f.n_kv_heads, apos0, sc, fa_tau));
+                        f.n_kv_heads, apos0, sc * 1.4426950408889634f, fa_tau * 1.4426950408889634f));
         } else if (hd == 128)
           RC(launch_pdl(c, attn_prefill_mma_kernel<T, 128>, grid, block, (size_t)4 * FA_BN * 128 * 2, (const T *)c->pf_qkv,
                         (const T *)kc->k[l] + wsoff, (const T *)kc->v[l] + wsoff, (T *)c->pf_y, S, f.n_heads, f.n_kv_heads, kc->cap, apos0, sc));
