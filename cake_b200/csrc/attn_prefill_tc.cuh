@@ -246,9 +246,9 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
 #pragma unroll
         for (int i = 0; i < 32; i++) {
           const float p0 = sv[2 * i], p1 = sv[2 * i + 1];
-          const float h0 = rnd<T>(p0), h1 = rnd<T>(p1);
-          hi[i] = pack2<T>(h0, h1);
-          lo[i] = pack2<T>(p0 - h0, p1 - h1);
+          hi[i] = pack2x<T>(p0, p1);
+          const float2 hf = DT<T>::unpack2(hi[i]);
+          lo[i] = pack2x<T>(p0 - hf.x, p1 - hf.y);
         }
         tc_st32(tmem_sp, hi);
         tc_st32(tmem_sp + 32u, lo);
@@ -270,7 +270,7 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_c
       if (t < S) {
         uint32_t o[16];
 #pragma unroll
-        for (int i = 0; i < 16; i++) o[i] = pack2<T>(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
+        for (int i = 0; i < 16; i++) o[i] = pack2x<T>(__uint_as_float(r[2 * i]) * inv, __uint_as_float(r[2 * i + 1]) * inv);
         uint4 *d4 = reinterpret_cast<uint4 *>(dst + c0);
 #pragma unroll
         for (int i = 0; i < 4; i++) d4[i] = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);

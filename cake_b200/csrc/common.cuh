@@ -37,6 +37,18 @@ template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b
   return (uint32_t)(*reinterpret_cast<uint16_t *>(&x)) | ((uint32_t)(*reinterpret_cast<uint16_t *>(&y)) << 16);
 }
 
+// the same two roundings in ONE packed conversion (cvt.rn.{bf16x2|f16x2}.f32 = F2FP on the ALU pipe; the scalar F2F goes
+// through the quarter-rate XU pipe, which is what bound the tcgen05 attention's softmax: ncu r02, XU 81 % busy)
+template <typename T> __device__ __forceinline__ uint32_t pack2x(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2x<__nv_bfloat16>(float a, float b) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t *>(&v);
+}
+template <> __device__ __forceinline__ uint32_t pack2x<__half>(float a, float b) {
+  const __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t *>(&v);
+}
+
 // MLP gate activation, mlp.rs:21-31: act 0 = silu(gate) (cpu/mod.rs:87-89), act 1 = gelu_tanh(gate) (use_gelu_mlp: candle's
 // `gelu` is the tanh approximation); the activation is rounded to D before the multiplication by `up` (the caller rounds
 // the product): two roundings, as the reference's separate ops produce.
