@@ -1091,6 +1091,18 @@ static int pf_reserve(cake_b200_ctx *c, size_t rows) {
   return CAKE_B200_OK;
 }
 
+// RMSNorm over M rows of n: warp-per-row vector kernel for n = 256 * {4, 8, 16, 32} and 16-byte aligned rows, else the generic one
+template <typename T>
+static int rmsnorm_rows_T(cake_b200_ctx *c, const void *x, const void *w, void *out, int M, int n, float eps) {
+  const bool al = (((uintptr_t)x | (uintptr_t)w | (uintptr_t)out) & 15) == 0;
+  const dim3 g((unsigned)((M + 7) / 8)), blk(256);
+  if (al && n == 1024) return launch_pdl(c, rmsnorm_rows_vec_kernel<T, 4>, g, blk, 0, (const T *)x, (const T *)w, (T *)out, M, eps);
+  if (al && n == 2048) return launch_pdl(c, rmsnorm_rows_vec_kernel<T, 8>, g, blk, 0, (const T *)x, (const T *)w, (T *)out, M, eps);
+  if (al && n == 4096) return launch_pdl(c, rmsnorm_rows_vec_kernel<T, 16>, g, blk, 0, (const T *)x, (const T *)w, (T *)out, M, eps);
+  if (al && n == 8192) return launch_pdl(c, rmsnorm_rows_vec_kernel<T, 32>, g, blk, 0, (const T *)x, (const T *)w, (T *)out, M, eps);
+  return launch_pdl(c, rmsnorm_rows_kernel<T>, dim3(M), dim3(256), 0, (const T *)x, (const T *)w, (T *)out, n, eps);
+}
+
 template <typename T>
 static int gemm_T(cake_b200_ctx *c, const void *A, const void *W, const void *bias, const void *res, void *C, int M,
                   int N, int K) {
@@ -1122,11 +1134,16 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
     for (int i = 0; i < n; i++) {
       const cake_b200_block *b = blocks[i];
       const int l = block_idx[i];
-      RC(launch_pdl(c, rmsnorm_rows_kernel<T>, dim3(M), dim3(256), 0, (const T *)cur, (const T *)b->ln1, (T *)c->pf_h, H, f.rms_eps));
+      RC(rmsnorm_rows_T<T>(c, cur, b->ln1, c->pf_h, M, H, f.rms_eps));
       if (use_tc && tc_gemm_ok(M, c->nqkv, H)) RC((gemm_tc_T<T, TCE_PLAIN>(c, c->pf_h, b->wqkv, b->bqkv, nullptr, c->pf_qkv, M, c->nqkv, H)));
       else RC(gemm_T<T>(c, c->pf_h, b->wqkv, b->bqkv, nullptr, c->pf_qkv, M, c->nqkv, H));
       {
         const long items = (long)M * (f.n_heads + 2 * f.n_kv_heads);
+        if (hd == 128 && c->rot == 128 && ((uintptr_t)c->cos_t & 3) == 0)  // full rotary on 128-wide heads: token-per-warp vector kernel
+          RC(launch_pdl(c, rope_append_vec_kernel<T>, dim3((unsigned)((M + 3) / 4)), dim3(128), 0, (T *)c->pf_qkv, (T *)kc->k[l], (T *)kc->v[l],
+                        (const T *)c->cos_t, (const T *)c->sin_t, (const T *)b->qn, (const T *)b->kn, B, S, f.n_heads, f.n_kv_heads, kc->cap, pos0,
+                        f.rms_eps));
+        else
         RC(launch_pdl(c, rope_append_kernel<T>, dim3((unsigned)((items + 3) / 4)), dim3(128), (size_t)4 * hd * 4,
                       (T *)c->pf_qkv, (T *)kc->k[l], (T *)kc->v[l], (const T *)c->cos_t, (const T *)c->sin_t,
                       (const T *)b->qn, (const T *)b->kn, B, S, f.n_heads, f.n_kv_heads, hd, c->rot, kc->cap, pos0, f.rms_eps));
@@ -1160,9 +1177,9 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
                       (const T *)kc->k[l] + wsoff, (const T *)kc->v[l] + wsoff, (T *)c->pf_y, B, S, f.n_heads, f.n_kv_heads, hd, kc->cap,
                       apos0, (float)(1.0 / sqrt((double)hd))));
       }
-      if (use_tc && tc_gemm_ok(M, H, sq)) RC((gemm_tc_T<T, TCE_RESIDUAL>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq)));
+      if (use_tc && tc_gemm_ok(M, H, sq) && ((uintptr_t)cur & 15) == 0) RC((gemm_tc_T<T, TCE_RESIDUAL>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq)));
       else RC(gemm_T<T>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq));
-      RC(launch_pdl(c, rmsnorm_rows_kernel<T>, dim3(M), dim3(256), 0, (const T *)c->pf_x1, (const T *)b->ln2, (T *)c->pf_h, H, f.rms_eps));
+      RC(rmsnorm_rows_T<T>(c, c->pf_x1, b->ln2, c->pf_h, M, H, f.rms_eps));
       if (use_tc && tc_gemm_ok(M, 2 * I, H)) {
         RC((gemm_tc_T<T, TCE_SWIGLU>(c, c->pf_h, b->wgu, nullptr, nullptr, c->pf_mm, M, 2 * I, H)));
       } else {

@@ -265,6 +265,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
             uint32_t o[16];
             const size_t off = (size_t)row * p.N + n0 + c0;
+            uint32_t rr[16];  // the residual row segment as four 16-byte loads (scalar 2-byte loads made this epilogue longer
+                              // than a K=4096 main loop: ncu r02, o_proj 68 % tensor-pipe active against 88-91 % elsewhere)
+            if (EPI == TCE_RESIDUAL) {
+              const uint4 *r4 = reinterpret_cast<const uint4 *>(res + off);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const uint4 v = r4[j];
+                rr[4 * j] = v.x; rr[4 * j + 1] = v.y; rr[4 * j + 2] = v.z; rr[4 * j + 3] = v.w;
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 16; j++) {
               float v0 = rnd<T>(__uint_as_float(r[2 * j])), v1 = rnd<T>(__uint_as_float(r[2 * j + 1]));
@@ -273,8 +283,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                 v1 = rnd<T>(v1 + DT<T>::to_f(bias[n0 + c0 + 2 * j + 1]));
               }
               if (EPI == TCE_RESIDUAL) {
-                v0 += DT<T>::to_f(res[off + 2 * j]);
-                v1 += DT<T>::to_f(res[off + 2 * j + 1]);
+                const float2 rv = DT<T>::unpack2(rr[j]);
+                v0 += rv.x;
+                v1 += rv.y;
               }
               o[j] = pack2<T>(v0, v1);
             }
