@@ -577,9 +577,9 @@ def decode_leg(env: Env, model: str, K: int, W: int, n_e2e: int, parity: bool, i
     return line
 
 
-TRAFFIC_NCU = {"bytes": 15280821000 + 7653120,
+TRAFFIC_NCU = {"bytes": 15280381000 + 8281856,
                "source": "dram__bytes_read.sum + dram__bytes_write.sum of one decode_mega_kernel launch, ncu --set full at N=1 "
-                         "(profiles/mega_r01_raw.csv); cited from the committed capture, not measured in this run"}
+                         "(profiles/mega_r02_raw.csv); cited from the committed capture, not measured in this run"}
 
 
 def step_stats(traces, K: int, ms_all: float):
@@ -878,7 +878,7 @@ def prefill_leg(env: Env, reps: int = 3, batch: int = 32, seq: int = 4096) -> di
                         "peak_source": pk["src"] + " (sustained cuBLAS bf16, the kernel runs inside a seconds-long step)",
                         "algorithmic_flops_per_step": flops,
                         "flops_split": {"linears": flop_lin, "causal_attention": flop_att, "lm_head": flop_head},
-                        "kernels": "gemm_tc_kernel (tcgen05) x4 per layer + attn_prefill + rmsnorm/rope_append"}}
+                        "kernels": "per layer: gemm_tc_kernel (tcgen05, 128x256 tiles, TMA-multicast CTA pairs) x4 + attn_prefill_tc_kernel (tcgen05 flash attention) + rmsnorm_rows_vec x2 + rope_append_vec; ncu: profiles/launches_prefill_r02.csv"}}
     ctx.close()
     torch.cuda.empty_cache()
     return res

@@ -372,3 +372,34 @@ def test_embed_scale_residual_norm_and_gelu_through_the_model():
     m.decode_build()
     assert [t0.id] + m.decode_greedy(t0.id, 7) == list(ref_toks)
     ctx.close()
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+def test_tcgen05_prefill_attention_head_dim_128_shapes(dtype):
+    """attn_prefill_tc.cuh (head_dim 128 takes the tcgen05 path) against the oracle on the shapes that stress its tiling:
+    a ragged query tile (200 = 128 + 72 rows: zero-filled Q rows, unwritten keys past the visible length), batch 2 with
+    GQA 4:2, a second chunk on a non-empty cache (pos0 > 0, diagonal tiles not aligned to the 64-key tiles), and a
+    sliding window that moves the K/V base of the chunk (cache.rs:173-205)."""
+    from cake_b200.model import B200Transformer
+    for window, chunks in ((None, (200, 77, 130)), (96, (200, 50, 90))):
+        kw = dict(head_dim=128, num_attention_heads=4, num_key_value_heads=2)
+        if window:
+            kw["sliding_window"] = window
+        cfg = medium_config(**kw)
+        sd = checkpoint(cfg, dtype, seed=31)
+        om, ctx = O.OracleModel(cfg, sd, dtype), _ctx(cfg, sd, dtype)
+        from cake_b200.model import Cache
+        ctx.cache = Cache(ctx, 2, cfg.max_seq_len)
+        ocs = [om.new_cache(), om.new_cache()]
+        blk = B200Transformer.load(cfg.layer_name(0), ctx)
+        x = rand_x((2, sum(chunks), cfg.hidden_size), dtype, seed=32)
+        pos = 0
+        for n in chunks:
+            y = blk.forward(ctx.to_device(x[:, pos:pos + n]), pos, 0, ctx)
+            ctx.sync()
+            for b in range(2):
+                y_ref = om.block_forward(0, x[b, pos:pos + n].float().numpy(), pos, ocs[b])
+                e = max_ulp_err(to_np(y[b]), y_ref, dtype)
+                assert e <= BLOCK_TOL_ULP, f"window {window}, batch row {b}, {n} tokens @ {pos}: {e} ulp"
+            pos += n
+        ctx.close()
