@@ -71,6 +71,14 @@ SYMBOLS += [
 ]
 
 
+class CBlockVariant(ctypes.Structure):
+    """``cake_b200_block_variant`` (include/cake_b200.h)."""
+    _fields_ = [("sliding_window", c_int), ("use_rope", c_int), ("post_attention_norm", _VP), ("post_feedforward_norm", _VP)]
+
+
+SYMBOLS += [("cake_b200_block_set_variant", _I, [_VP, POINTER(CBlockVariant)])]
+
+
 class CakeB200Error(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"cake_b200 error {code}: {msg}")

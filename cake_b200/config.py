@@ -15,6 +15,8 @@ import json
 from dataclasses import dataclass, field, asdict
 from typing import Optional
 
+import numpy as np
+
 DTYPES = {"bf16": 0, "f16": 1, "f32": 2}
 
 
@@ -53,6 +55,31 @@ class Config:
     use_gelu_mlp: bool = False        # config.rs:133: gelu_tanh(gate) * up (mlp.rs:25-26)
     embed_scale: Optional[float] = None   # config.rs:136: embeddings scaled before the blocks (text_model.rs:274-276)
     residual_rms_norm: bool = False   # config.rs:113: norm weights stored as deltas; (1 + w) in f32 at LOAD time (config.rs:155-173)
+    pre_reshape_qk_norm: bool = False  # config.rs:116 (OLMo2): QK-norm over the whole q / k projection, before the head reshape
+    global_layers: list = field(default_factory=list)  # config.rs:126-130: per-layer schedule, True = global (full context)
+    block_kind: str = "llama"         # which block.rs the layers are: "llama" (transformer.rs), "olmo2", "gemma3", "exaone4"
+
+    def layer_variant(self, i: int, max_seq: Optional[int] = None) -> dict:
+        """Norm placement and attention mode of layer ``i``, as the reference's per-architecture block.rs sets them up:
+          llama   (common/transformer.rs:103-135)  pre-norms, the config's window, RoPE
+          olmo2   (olmo2/block.rs:62-90)           NO pre-norms, post-attention / post-feedforward norms, RoPE
+          gemma3  (gemma3/block.rs:60-135)         all four norms; global layers: full context + RoPE, local: window, NO RoPE
+          exaone4 (exaone4/block.rs:50-110)        pre-norms; global layers: full context, NO RoPE, local: window + RoPE
+        ``window``: -1 = the config's, 0 = none, > 0 = this layer's (passed as 0 when it can never bite)."""
+        def win(w):
+            return int(w) if (w and w < (max_seq or self.max_seq_len)) else 0
+        is_global = bool(self.global_layers[i]) if i < len(self.global_layers) else False
+        if self.block_kind == "olmo2":
+            return dict(pre_norms=False, post_norms=True, window=-1, no_rope=False)
+        if self.block_kind == "gemma3":
+            return dict(pre_norms=True, post_norms=True, window=0 if is_global else win(self.sliding_window), no_rope=not is_global)
+        if self.block_kind == "exaone4":
+            return dict(pre_norms=True, post_norms=False, window=0 if is_global else win(self.sliding_window), no_rope=is_global)
+        return dict(pre_norms=True, post_norms=False, window=-1, no_rope=False)
+
+    @property
+    def standard_blocks(self) -> bool:
+        return self.block_kind == "llama"
 
     @property
     def hd(self) -> int:
@@ -85,8 +112,9 @@ class Config:
         "Phi4ForCausalLM": (1000000.0, 131072, dict(_head_dim=True, _partial=True, _fused=True)),
     }
     _OTHER_BLOCKS = ("Qwen3_5ForConditionalGeneration", "Qwen3MoeForCausalLM", "Qwen3_5MoeForConditionalGeneration",
-                     "Gemma3ForCausalLM", "OLMo2ForCausalLM",
-                     "Olmo2ForCausalLM", "ExaoneForCausalLM", "LuxTTSForTextToSpeech")
+                     "LuxTTSForTextToSpeech")
+    _SIBLING_BLOCKS = {"Gemma3ForCausalLM": "gemma3", "OLMo2ForCausalLM": "olmo2", "Olmo2ForCausalLM": "olmo2",
+                       "ExaoneForCausalLM": "exaone4"}  # cake/mod.rs:99-105
 
     @staticmethod
     def detect_arch(d: dict) -> str:
@@ -103,6 +131,8 @@ class Config:
         arch = Config.detect_arch(d)
         if arch in Config._OTHER_BLOCKS:
             raise ValueError(f"architecture {arch!r} is outside the block-forward path built here")
+        if arch in Config._SIBLING_BLOCKS:
+            return Config._from_hf_sibling(d, Config._SIBLING_BLOCKS[arch])
         rope_default, max_default, flags = Config._ARCHS.get(arch, Config._ARCHS["LlamaForCausalLM"])
         rs = d.get("rope_scaling")
         rope = None
@@ -137,6 +167,42 @@ class Config:
             partial_rotary_factor=float(d.get("partial_rotary_factor") or 1.0) if flags.get("_partial") else 1.0,
             fused_qkv_proj=bool(flags.get("_fused")), fused_gate_up_proj=bool(flags.get("_fused")),
         )
+
+    @staticmethod
+    def _from_hf_sibling(d: dict, kind: str) -> "Config":
+        """models/{gemma3,olmo2,exaone4}/config.rs ``into_config``: the serde defaults and the flags each hard-wires."""
+        n = int(d["num_hidden_layers"])
+        rs = d.get("rope_scaling")
+        rope = RopeScaling(factor=float(rs.get("factor", 0.0)), low_freq_factor=float(rs.get("low_freq_factor", 0.0)),
+                           high_freq_factor=float(rs.get("high_freq_factor", 0.0)),
+                           original_max_position_embeddings=int(rs.get("original_max_position_embeddings", 0)),
+                           rope_type=rs.get("rope_type")) if rs else None
+        eos = d.get("eos_token_id")
+        eos = [] if eos is None else (list(eos) if isinstance(eos, (list, tuple)) else [eos])
+        base = dict(hidden_size=d["hidden_size"], intermediate_size=d["intermediate_size"], vocab_size=d["vocab_size"],
+                    num_hidden_layers=n, num_attention_heads=d["num_attention_heads"],
+                    num_key_value_heads=d.get("num_key_value_heads") or d["num_attention_heads"],
+                    rms_norm_eps=d["rms_norm_eps"], rope_scaling=rope, eos_token_id=eos, head_dim=d.get("head_dim"),
+                    use_qk_norm=True, block_kind=kind)
+        if kind == "olmo2":    # olmo2/config.rs:52-90
+            return Config(**base, rope_theta=float(d.get("rope_theta") or 500000.0),
+                          tie_word_embeddings=bool(d.get("tie_word_embeddings", False)),
+                          max_seq_len=int(d.get("max_position_embeddings") or 4096), pre_reshape_qk_norm=True)
+        if kind == "exaone4":  # exaone4/config.rs:62-110: every `global_layer_period`-th layer is global
+            period = int(d.get("global_layer_period") or 4)
+            return Config(**base, rope_theta=float(d.get("rope_theta") or 500000.0),
+                          tie_word_embeddings=bool(d.get("tie_word_embeddings", False)),
+                          max_seq_len=int(d.get("max_position_embeddings") or 131072),
+                          sliding_window=int(d.get("sliding_window") or 4096),
+                          global_layers=[(i + 1) % period == 0 for i in range(n)])
+        # gemma3/config.rs:76-125: explicit schedule (true = global) or every `sliding_window_pattern`-th layer
+        sched = d.get("sliding_window_attention_schedule") or []
+        pattern = int(d.get("sliding_window_pattern") or 6)
+        gl = [bool(sched[i]) if i < len(sched) else False for i in range(n)] if sched else [(i + 1) % pattern == 0 for i in range(n)]
+        return Config(**base, rope_theta=float(d.get("rope_theta") or 10000.0), tie_word_embeddings=True,
+                      max_seq_len=int(d.get("max_position_embeddings") or 131072),
+                      sliding_window=int(d.get("sliding_window") or 1024), global_layers=gl, residual_rms_norm=True,
+                      use_gelu_mlp=True, embed_scale=float(np.sqrt(np.float32(d["hidden_size"]))))
 
     @staticmethod
     def from_path(path: str) -> "Config":
@@ -179,6 +245,7 @@ class CConfig(ctypes.Structure):
         ("rope_orig_max", ctypes.c_int),
         ("dtype", ctypes.c_int),
         ("sliding_window", ctypes.c_int), ("use_gelu_mlp", ctypes.c_int), ("embed_scale", ctypes.c_float),
+        ("pre_reshape_qk_norm", ctypes.c_int),
     ]
 
     @staticmethod
@@ -196,7 +263,7 @@ class CConfig(ctypes.Structure):
             rs.factor if llama3 else 1.0, rs.low_freq_factor if llama3 else 1.0,
             rs.high_freq_factor if llama3 else 4.0, rs.original_max_position_embeddings if llama3 else 0,
             DTYPES[dtype],
-            win, int(c.use_gelu_mlp), float(c.embed_scale or 0.0),
+            win, int(c.use_gelu_mlp), float(c.embed_scale or 0.0), int(c.pre_reshape_qk_norm),
         )
 
 

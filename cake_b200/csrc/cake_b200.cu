@@ -176,6 +176,11 @@ struct cake_b200_block {
   int device = 0;  // copied so that block_free never dereferences a ctx that was destroyed first
   void *wqkv = nullptr, *wo = nullptr, *wgu = nullptr, *wd = nullptr, *ln1 = nullptr, *ln2 = nullptr;
   void *bqkv = nullptr, *qn = nullptr, *kn = nullptr;
+  // cake_b200_block_set_variant: the sibling block structures (olmo2 / gemma3 / exaone4 block.rs)
+  void *pan = nullptr, *pfn = nullptr;  // post-attention / post-feedforward RmsNorm vectors
+  int window = -1;                      // -1: the config's
+  bool use_rope = true;
+  bool variant() const { return !ln1 || !ln2 || pan || pfn || window >= 0 || !use_rope || ctx->cfg.pre_reshape_qk_norm; }
 };
 
 struct cake_b200_cache {
@@ -618,7 +623,7 @@ extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void 
                                     const void *o, const void *gate, const void *up, const void *down, const void *ln1,
                                     const void *ln2, const void *q_bias, const void *k_bias, const void *v_bias,
                                     const void *q_norm, const void *k_norm, cake_b200_block **out) {
-  if (!c || !q || !k || !v || !o || !gate || !up || !down || !ln1 || !ln2 || !out) return fail(CAKE_B200_EINVAL, "null weight pointer");
+  if (!c || !q || !k || !v || !o || !gate || !up || !down || !out) return fail(CAKE_B200_EINVAL, "null weight pointer");  // ln1 / ln2 may be NULL (OLMo2: no pre-norms)
   if (c->cfg.qkv_bias && (!q_bias || !k_bias || !v_bias)) return fail(CAKE_B200_EINVAL, "config has qkv_bias but a bias pointer is null");
   if (c->cfg.qk_norm && (!q_norm || !k_norm)) return fail(CAKE_B200_EINVAL, "config has qk_norm but a norm pointer is null");
   CU(cudaSetDevice(c->device));
@@ -638,8 +643,8 @@ extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void 
   RC(pipe_copy(c, b->wgu, 2 * H * es, gate, H * es, H * es, I));               // the row interleave is done by the DMA engine
   RC(pipe_copy(c, (char *)b->wgu + H * es, 2 * H * es, up, H * es, H * es, I));
   RC(upload(c, &b->wd, down, H * I * es));
-  RC(upload(c, &b->ln1, ln1, H * es));
-  RC(upload(c, &b->ln2, ln2, H * es));
+  if (ln1) RC(upload(c, &b->ln1, ln1, H * es));
+  if (ln2) RC(upload(c, &b->ln2, ln2, H * es));
   if (c->cfg.qkv_bias) {
     CU(cudaMalloc(&b->bqkv, (sq + 2 * skv) * es + 16));
     RC(pipe_copy(c, b->bqkv, sq * es, q_bias, sq * es, sq * es, 1));
@@ -647,8 +652,8 @@ extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void 
     RC(pipe_copy(c, (char *)b->bqkv + (sq + skv) * es, skv * es, v_bias, skv * es, skv * es, 1));
   }
   if (c->cfg.qk_norm) {
-    RC(upload(c, &b->qn, q_norm, hd * es));
-    RC(upload(c, &b->kn, k_norm, hd * es));
+    RC(upload(c, &b->qn, q_norm, (c->cfg.pre_reshape_qk_norm ? sq : hd) * es));   // attention.rs:121-122
+    RC(upload(c, &b->kn, k_norm, (c->cfg.pre_reshape_qk_norm ? skv : hd) * es));
   }
   return pipe_mark(c);
   }();
@@ -662,13 +667,31 @@ extern "C" int cake_b200_block_load(cake_b200_ctx *c, int layer_idx, const void 
 extern "C" void cake_b200_block_free(cake_b200_block *b) {
   if (!b) return;
   cudaSetDevice(b->device);
-  void *bufs[] = {b->wqkv, b->wo, b->wgu, b->wd, b->ln1, b->ln2, b->bqkv, b->qn, b->kn};
+  void *bufs[] = {b->wqkv, b->wo, b->wgu, b->wd, b->ln1, b->ln2, b->bqkv, b->qn, b->kn, b->pan, b->pfn};
   for (void *p : bufs)
     if (p) cudaFree(p);  // cudaFree synchronises with outstanding work
   (void)cudaGetLastError();
   delete b;
 }
 extern "C" int cake_b200_block_layer(const cake_b200_block *b) { return b ? b->layer : -1; }
+extern "C" int cake_b200_block_set_variant(cake_b200_block *b, const cake_b200_block_variant *v) {
+  if (!b || !v) return fail(CAKE_B200_EINVAL, "null argument");
+  if (v->sliding_window < -1) return fail(CAKE_B200_EINVAL, "sliding_window %d (use -1 for the config's, 0 for none)", v->sliding_window);
+  cake_b200_ctx *c = b->ctx;
+  CU(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)c->cfg.hidden * c->es;
+  if (v->post_attention_norm) {
+    if (b->pan) { cudaFree(b->pan); b->pan = nullptr; }
+    RC(upload(c, &b->pan, v->post_attention_norm, bytes));
+  }
+  if (v->post_feedforward_norm) {
+    if (b->pfn) { cudaFree(b->pfn); b->pfn = nullptr; }
+    RC(upload(c, &b->pfn, v->post_feedforward_norm, bytes));
+  }
+  b->window = v->sliding_window;
+  b->use_rope = v->use_rope != 0;
+  return pipe_mark(c);
+}
 
 // ------------------------------------------------------------------------------------------ cache
 extern "C" int cake_b200_cache_create(cake_b200_ctx *c, int batch, int max_seq, cake_b200_cache **out) {
@@ -1119,13 +1142,18 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
   // cache.rs:173-205: a call on a non-empty cache sees the last `window` positions of cat(cache, new) — every query of
   // the chunk the same old rows [ws, pos0) — while the first call (pos0 == 0) attends over everything it stores.  The
   // attention kernels only see row indices relative to ws (base pointers advanced by ws rows); K/V append is unaffected.
-  int ws = 0;
-  if (f.sliding_window > 0 && pos0 > 0 && pos0 + S > f.sliding_window) {
-    ws = pos0 + S - f.sliding_window;
-    if (ws > pos0) return fail(CAKE_B200_EINVAL, "a chunk of %d tokens on a non-empty cache exceeds the sliding window %d", S, f.sliding_window);
-  }
-  const size_t wsoff = (size_t)ws * hd;
-  const int apos0 = pos0 - ws;
+  // per block (attention.rs load_custom gives every layer its own window): block_window() below
+  auto block_window = [&](const cake_b200_block *b, int *ws_out) -> int {
+    const int w = b->window >= 0 ? b->window : f.sliding_window;
+    int ws = 0;
+    if (w > 0 && pos0 > 0 && pos0 + S > w) {
+      ws = pos0 + S - w;
+      if (ws > pos0) return fail(CAKE_B200_EINVAL, "a chunk of %d tokens on a non-empty cache exceeds the sliding window %d", S, w);
+    }
+    *ws_out = ws;
+    return CAKE_B200_OK;
+  };
+  for (int i = 0; i < n; i++) { int t; RC(block_window(blocks[i], &t)); }  // refuse before anything is enqueued
   const char *env_tc = getenv("CAKE_B200_NO_TC");
   const bool use_tc = !(env_tc && env_tc[0] == '1');  // CAKE_B200_NO_TC=1: CUDA-core GEMM (A/B testing aid)
   return DISPATCH_T(f.dtype, T_LAMBDA {
@@ -1134,19 +1162,32 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
     for (int i = 0; i < n; i++) {
       const cake_b200_block *b = blocks[i];
       const int l = block_idx[i];
-      RC(rmsnorm_rows_T<T>(c, cur, b->ln1, c->pf_h, M, H, f.rms_eps));
-      if (use_tc && tc_gemm_ok(M, c->nqkv, H)) RC((gemm_tc_T<T, TCE_PLAIN>(c, c->pf_h, b->wqkv, b->bqkv, nullptr, c->pf_qkv, M, c->nqkv, H)));
-      else RC(gemm_T<T>(c, c->pf_h, b->wqkv, b->bqkv, nullptr, c->pf_qkv, M, c->nqkv, H));
+      int ws = 0;
+      RC(block_window(b, &ws));
+      const size_t wsoff = (size_t)ws * hd;
+      const int apos0 = pos0 - ws;
+      // transformer.rs:112 rms_1 — or none: olmo2/block.rs:70 feeds x itself to the attention
+      const void *att_in = cur;
+      if (b->ln1) { RC(rmsnorm_rows_T<T>(c, cur, b->ln1, c->pf_h, M, H, f.rms_eps)); att_in = c->pf_h; }
+      if (use_tc && tc_gemm_ok(M, c->nqkv, H) && ((uintptr_t)att_in & 15) == 0) RC((gemm_tc_T<T, TCE_PLAIN>(c, att_in, b->wqkv, b->bqkv, nullptr, c->pf_qkv, M, c->nqkv, H)));
+      else RC(gemm_T<T>(c, att_in, b->wqkv, b->bqkv, nullptr, c->pf_qkv, M, c->nqkv, H));
+      const void *qn = b->qn, *kn = b->kn;
+      if (f.pre_reshape_qk_norm && qn && kn) {  // attention.rs:176-192: RmsNorm over the whole q and k projections, in place
+        RC(launch_pdl(c, rmsnorm_strided_kernel<T>, dim3(M), dim3(256), 0, (T *)c->pf_qkv, (const T *)qn, c->nqkv, sq, f.rms_eps));
+        RC(launch_pdl(c, rmsnorm_strided_kernel<T>, dim3(M), dim3(256), 0, (T *)c->pf_qkv + sq, (const T *)kn, c->nqkv, (int)(f.n_kv_heads * hd), f.rms_eps));
+        qn = kn = nullptr;
+      }
+      const int rope_on = b->use_rope ? 1 : 0;
       {
         const long items = (long)M * (f.n_heads + 2 * f.n_kv_heads);
         if (hd == 128 && c->rot == 128 && ((uintptr_t)c->cos_t & 3) == 0)  // full rotary on 128-wide heads: token-per-warp vector kernel
           RC(launch_pdl(c, rope_append_vec_kernel<T>, dim3((unsigned)((M + 3) / 4)), dim3(128), 0, (T *)c->pf_qkv, (T *)kc->k[l], (T *)kc->v[l],
-                        (const T *)c->cos_t, (const T *)c->sin_t, (const T *)b->qn, (const T *)b->kn, B, S, f.n_heads, f.n_kv_heads, kc->cap, pos0,
-                        f.rms_eps));
+                        (const T *)c->cos_t, (const T *)c->sin_t, (const T *)qn, (const T *)kn, B, S, f.n_heads, f.n_kv_heads, kc->cap, pos0,
+                        f.rms_eps, rope_on));
         else
         RC(launch_pdl(c, rope_append_kernel<T>, dim3((unsigned)((items + 3) / 4)), dim3(128), (size_t)4 * hd * 4,
                       (T *)c->pf_qkv, (T *)kc->k[l], (T *)kc->v[l], (const T *)c->cos_t, (const T *)c->sin_t,
-                      (const T *)b->qn, (const T *)b->kn, B, S, f.n_heads, f.n_kv_heads, hd, c->rot, kc->cap, pos0, f.rms_eps));
+                      (const T *)qn, (const T *)kn, B, S, f.n_heads, f.n_kv_heads, hd, c->rot, kc->cap, pos0, f.rms_eps, rope_on));
       }
       if (use_tc && (hd == 64 || hd == 128)) {  // tensor-core flash attention (attn_prefill.cuh)
         dim3 grid((S + FA_BM - 1) / FA_BM, f.n_heads, B), block(FA_THREADS);
@@ -1177,16 +1218,25 @@ static int enqueue_prefill_layers(cake_b200_ctx *c, cake_b200_block *const *bloc
                       (const T *)kc->k[l] + wsoff, (const T *)kc->v[l] + wsoff, (T *)c->pf_y, B, S, f.n_heads, f.n_kv_heads, hd, kc->cap,
                       apos0, (float)(1.0 / sqrt((double)hd))));
       }
-      if (use_tc && tc_gemm_ok(M, H, sq) && ((uintptr_t)cur & 15) == 0) RC((gemm_tc_T<T, TCE_RESIDUAL>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq)));
+      if (b->pan) {  // olmo2/block.rs:77-79, gemma3/block.rs:120-122: x1 = x + rms_norm(o_proj(y))  (pf_h is free again here)
+        if (use_tc && tc_gemm_ok(M, H, sq)) RC((gemm_tc_T<T, TCE_PLAIN>(c, c->pf_y, b->wo, nullptr, nullptr, c->pf_h, M, H, sq)));
+        else RC(gemm_T<T>(c, c->pf_y, b->wo, nullptr, nullptr, c->pf_h, M, H, sq));
+        RC(launch_pdl(c, rmsnorm_residual_rows_kernel<T>, dim3(M), dim3(256), 0, (const T *)c->pf_h, (const T *)b->pan, (const T *)cur, (T *)c->pf_x1, H, f.rms_eps));
+      } else if (use_tc && tc_gemm_ok(M, H, sq) && ((uintptr_t)cur & 15) == 0) RC((gemm_tc_T<T, TCE_RESIDUAL>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq)));
       else RC(gemm_T<T>(c, c->pf_y, b->wo, nullptr, cur, c->pf_x1, M, H, sq));
-      RC(rmsnorm_rows_T<T>(c, c->pf_x1, b->ln2, c->pf_h, M, H, f.rms_eps));
+      const void *mlp_in = c->pf_x1;
+      if (b->ln2) { RC(rmsnorm_rows_T<T>(c, c->pf_x1, b->ln2, c->pf_h, M, H, f.rms_eps)); mlp_in = c->pf_h; }
       if (use_tc && tc_gemm_ok(M, 2 * I, H)) {
-        RC((gemm_tc_T<T, TCE_SWIGLU>(c, c->pf_h, b->wgu, nullptr, nullptr, c->pf_mm, M, 2 * I, H)));
+        RC((gemm_tc_T<T, TCE_SWIGLU>(c, mlp_in, b->wgu, nullptr, nullptr, c->pf_mm, M, 2 * I, H)));
       } else {
-        RC(gemm_T<T>(c, c->pf_h, b->wgu, nullptr, nullptr, c->pf_gu, M, 2 * I, H));
+        RC(gemm_T<T>(c, mlp_in, b->wgu, nullptr, nullptr, c->pf_gu, M, 2 * I, H));
         RC(launch_pdl(c, swiglu_rows_kernel<T>, dim3(c->sm_count * 4), dim3(256), 0, (const T *)c->pf_gu, (T *)c->pf_mm, (size_t)M * I, f.use_gelu_mlp ? 1 : 0));
       }
-      if (use_tc && tc_gemm_ok(M, H, I)) RC((gemm_tc_T<T, TCE_RESIDUAL>(c, c->pf_mm, b->wd, nullptr, c->pf_x1, x_out, M, H, I)));
+      if (b->pfn) {  // olmo2/block.rs:84-86, gemma3/block.rs:130-132: out = x1 + rms_norm(down(...))
+        if (use_tc && tc_gemm_ok(M, H, I)) RC((gemm_tc_T<T, TCE_PLAIN>(c, c->pf_mm, b->wd, nullptr, nullptr, c->pf_h, M, H, I)));
+        else RC(gemm_T<T>(c, c->pf_mm, b->wd, nullptr, nullptr, c->pf_h, M, H, I));
+        RC(launch_pdl(c, rmsnorm_residual_rows_kernel<T>, dim3(M), dim3(256), 0, (const T *)c->pf_h, (const T *)b->pfn, (const T *)c->pf_x1, (T *)x_out, H, f.rms_eps));
+      } else if (use_tc && tc_gemm_ok(M, H, I)) RC((gemm_tc_T<T, TCE_RESIDUAL>(c, c->pf_mm, b->wd, nullptr, c->pf_x1, x_out, M, H, I)));
       else RC(gemm_T<T>(c, c->pf_mm, b->wd, nullptr, c->pf_x1, x_out, M, H, I));
       cur = x_out;
     }
@@ -1210,7 +1260,9 @@ extern "C" int cake_b200_forward_batch(cake_b200_ctx *c, cake_b200_block *const 
       return fail(CAKE_B200_ESTATE, "block %d: index_pos %d != cache length %d (clear the cache or feed positions in order)",
                   block_idx[i], index_pos, kc->len[block_idx[i]]);
   }
-  if (batch == 1 && seq == 1) {
+  bool variant = false;  // sibling block structures step through the batched path (cake_b200_block_set_variant)
+  for (int i = 0; i < n_blocks; i++) variant = variant || blocks[i]->variant();
+  if (batch == 1 && seq == 1 && !variant) {
     set_int_kernel<<<1, 1, 0, c->stream>>>(kc->d_pos, index_pos);
     c->launches++;
     if (c->use_mega && mega_supported(c)) RC(enqueue_mega_layers(c, blocks, block_idx, n_blocks, kc, x_dev, y_dev));
@@ -1490,6 +1542,10 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
   if (kc->batch != 1) return fail(CAKE_B200_EINVAL, "decode graph is batch 1 (cake run/serve never batch, text_model.rs:418-420)");
   if (world > 1 && !c->comm) return fail(CAKE_B200_ESTATE, "world > 1 needs cake_b200_comm_init first");
   if (rank == 0 && !c->lm_head) return fail(CAKE_B200_ESTATE, "rank 0 needs cake_b200_head_load first");
+  for (int i = 0; i < n_blocks; i++)
+    if (blocks[i]->variant())
+      return fail(CAKE_B200_EINVAL, "block %d is a sibling block structure (cake_b200_block_set_variant / pre-reshape QK-norm): "
+                  "the decode graph covers the standard block only; step it with cake_b200_forward_batch", block_idx[i]);
   CU(cudaSetDevice(c->device));
   RC(wait_loads(c));
   for (int i = 0; i < n_blocks; i++) RC(cache_ensure(kc, block_idx[i]));

@@ -32,6 +32,55 @@ __global__ void __launch_bounds__(256) rmsnorm_rows_kernel(const T *__restrict__
     orow[i] = DT<T>::from_f(DT<T>::to_f(xr[i]) * inv * DT<T>::to_f(w[i]));
 }
 
+// ---- the sibling block structures (olmo2 / gemma3 block.rs) -----------------------------------------------------------
+// out = res + rms_norm(x) * w: the post-attention / post-feedforward norm followed by the residual add (olmo2/block.rs:77-90,
+// gemma3/block.rs:120-133); two roundings to D, as the reference's rms_norm and `+` produce.  One CTA per row.
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_residual_rows_kernel(const T *__restrict__ x, const T *__restrict__ w,
+                                                                    const T *__restrict__ res, T *__restrict__ out, int n, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8];
+  const T *xr = x + (size_t)blockIdx.x * n;
+  const T *rr = res + (size_t)blockIdx.x * n;
+  T *orow = out + (size_t)blockIdx.x * n;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = DT<T>::to_f(xr[i]);
+    ss += v * v;
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); i++) tot += red[i];
+  const float inv = 1.0f / sqrtf(tot / (float)n + eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    orow[i] = DT<T>::from_f(rnd<T>(DT<T>::to_f(xr[i]) * inv * DT<T>::to_f(w[i])) + DT<T>::to_f(rr[i]));
+}
+
+// In-place RmsNorm of an n-wide segment of every row of a wider matrix (row stride `stride` elements): the OLMo2 QK-norm over
+// the whole q (or k) projection inside the fused qkv buffer, attention.rs:176-192.  One CTA per row.
+template <typename T>
+__global__ void __launch_bounds__(256) rmsnorm_strided_kernel(T *__restrict__ x, const T *__restrict__ w, int stride, int n, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
+  __shared__ float red[8];
+  T *xr = x + (size_t)blockIdx.x * stride;
+  float ss = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = DT<T>::to_f(xr[i]);
+    ss += v * v;
+  }
+  ss = warp_sum(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); i++) tot += red[i];
+  const float inv = 1.0f / sqrtf(tot / (float)n + eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xr[i] = DT<T>::from_f(DT<T>::to_f(xr[i]) * inv * DT<T>::to_f(w[i]));
+}
+
 // The same operator at HBM speed for the row lengths the served models have (n = 256 NV): one WARP per row, the row
 // read once with NV 16-byte loads per lane (all in flight together) and kept in registers between the sum of squares
 // and the scaling; 8 rows per CTA.  The one-CTA-per-row kernel above (2-byte accesses, row read twice) ran at 1.85 TB/s
@@ -138,7 +187,7 @@ __global__ void __launch_bounds__(128) rope_append_kernel(T *__restrict__ qkv, T
                                                           T *__restrict__ vcache, const T *__restrict__ cos_t,
                                                           const T *__restrict__ sin_t, const T *__restrict__ q_norm,
                                                           const T *__restrict__ k_norm, int B, int S, int n_heads,
-                                                          int n_kv, int hd, int rot, int cap, int pos0, float eps) {
+                                                          int n_kv, int hd, int rot, int cap, int pos0, float eps, int rope_on) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float sm[];  // 4 warps * hd
@@ -172,7 +221,7 @@ __global__ void __launch_bounds__(128) rope_append_kernel(T *__restrict__ qkv, T
   }
   const int half = rot / 2;
   const T *cr = cos_t + (size_t)pos * half, *sr = sin_t + (size_t)pos * half;
-  for (int i = lane; i < half; i += 32) {
+  for (int i = lane; i < half && rope_on; i += 32) {  // rope_on == 0: this layer does not rotate (attention.rs:242-253)
     const float c = DT<T>::to_f(cr[i]), s = DT<T>::to_f(sr[i]);
     const float x1 = buf[i], x2 = buf[i + half];
     buf[i] = rnd<T>(rnd<T>(x1 * c) - rnd<T>(x2 * s));
@@ -193,7 +242,7 @@ template <typename T>
 __global__ void __launch_bounds__(128) rope_append_vec_kernel(T *__restrict__ qkv, T *__restrict__ kcache, T *__restrict__ vcache,
                                                               const T *__restrict__ cos_t, const T *__restrict__ sin_t,
                                                               const T *__restrict__ q_norm, const T *__restrict__ k_norm, int B,
-                                                              int S, int n_heads, int n_kv, int cap, int pos0, float eps) {
+                                                              int S, int n_heads, int n_kv, int cap, int pos0, float eps, int rope_on) {
   pdl_launch_dependents();
   pdl_wait();
   constexpr int HD = 128, HC = 4;
@@ -203,8 +252,9 @@ __global__ void __launch_bounds__(128) rope_append_vec_kernel(T *__restrict__ qk
   const int t = (int)(tok % S), b = (int)(tok / S);
   const int nh_all = n_heads + 2 * n_kv, pos = pos0 + t;
   uint32_t *row = reinterpret_cast<uint32_t *>(qkv + (size_t)tok * nh_all * HD);  // 64 words per head
-  const float2 c = DT<T>::unpack2(reinterpret_cast<const uint32_t *>(cos_t + (size_t)pos * (HD / 2))[lane]);
-  const float2 sn = DT<T>::unpack2(reinterpret_cast<const uint32_t *>(sin_t + (size_t)pos * (HD / 2))[lane]);
+  float2 c = DT<T>::unpack2(reinterpret_cast<const uint32_t *>(cos_t + (size_t)pos * (HD / 2))[lane]);
+  float2 sn = DT<T>::unpack2(reinterpret_cast<const uint32_t *>(sin_t + (size_t)pos * (HD / 2))[lane]);
+  if (!rope_on) { c = make_float2(1.f, 1.f); sn = make_float2(0.f, 0.f); }  // no rotation on this layer: x*1 - y*0 = x exactly
   float2 qw0 = {1.f, 1.f}, qw1 = {1.f, 1.f}, kw0 = {1.f, 1.f}, kw1 = {1.f, 1.f};
   if (q_norm) { qw0 = DT<T>::unpack2(reinterpret_cast<const uint32_t *>(q_norm)[lane]); qw1 = DT<T>::unpack2(reinterpret_cast<const uint32_t *>(q_norm)[32 + lane]); }
   if (k_norm) { kw0 = DT<T>::unpack2(reinterpret_cast<const uint32_t *>(k_norm)[lane]); kw1 = DT<T>::unpack2(reinterpret_cast<const uint32_t *>(k_norm)[32 + lane]); }

@@ -201,6 +201,10 @@ BLOCK_TENSORS = ("self_attn.q_proj.weight", "self_attn.k_proj.weight", "self_att
                  "self_attn.q_norm.weight", "self_attn.k_norm.weight")
 
 
+# the two extra RmsNorm vectors of the sandwich-norm blocks (olmo2/block.rs:49-52, gemma3/block.rs:84-91), by logical role
+EXTRA_TENSORS = ("post_attn_norm", "post_ffn_norm")
+
+
 def rms_norm_weight(t: torch.Tensor, cfg: Config) -> torch.Tensor:
     """config.rs:155-173 load_rms_norm_weight: with ``residual_rms_norm`` the checkpoint stores deltas and the forward
     weight is (1 + w), added in f32 and cast back to the model dtype AT LOAD TIME — the kernels never see the flag."""
@@ -242,15 +246,32 @@ def block_tensors(vb, cfg: Config, name: str) -> Dict[str, Optional[torch.Tensor
         out["mlp.gate_proj.weight"] = get("mlp.gate_proj.weight", (I, H))
         out["mlp.up_proj.weight"] = get("mlp.up_proj.weight", (I, H))
     out["mlp.down_proj.weight"] = get("mlp.down_proj.weight", (H, I))
-    out["input_layernorm.weight"] = rms_norm_weight(get("input_layernorm.weight", (H,)), cfg)
-    out["post_attention_layernorm.weight"] = rms_norm_weight(get("post_attention_layernorm.weight", (H,)), cfg)
+    # Norm vectors by ROLE.  out["input_layernorm.weight"] is the pre-attention norm and out["post_attention_layernorm.weight"]
+    # the pre-MLP norm (the Llama naming, transformer.rs:84-90); the sibling blocks name theirs differently:
+    #   gemma3 (block.rs:84-91): input_layernorm | post_attention_layernorm = POST-attention | pre_feedforward_layernorm = pre-MLP
+    #                            | post_feedforward_layernorm
+    #   olmo2  (block.rs:49-52): no pre-norms; post_attention_layernorm and post_feedforward_layernorm are post-norms
+    kind = getattr(cfg, "block_kind", "llama")
+    out.update({k: None for k in EXTRA_TENSORS})
+    norm = lambda short: rms_norm_weight(get(short, (H,)), cfg)
+    if kind == "olmo2":
+        out["post_attn_norm"], out["post_ffn_norm"] = norm("post_attention_layernorm.weight"), norm("post_feedforward_layernorm.weight")
+    elif kind == "gemma3":
+        out["input_layernorm.weight"] = norm("input_layernorm.weight")
+        out["post_attn_norm"] = norm("post_attention_layernorm.weight")
+        out["post_attention_layernorm.weight"] = norm("pre_feedforward_layernorm.weight")
+        out["post_ffn_norm"] = norm("post_feedforward_layernorm.weight")
+    else:
+        out["input_layernorm.weight"] = norm("input_layernorm.weight")
+        out["post_attention_layernorm.weight"] = norm("post_attention_layernorm.weight")
     if cfg.use_qkv_bias:  # attention.rs:96-107 (never together with a fused qkv_proj)
         out["self_attn.q_proj.bias"] = get("self_attn.q_proj.bias", (sq,))
         out["self_attn.k_proj.bias"] = get("self_attn.k_proj.bias", (skv,))
         out["self_attn.v_proj.bias"] = get("self_attn.v_proj.bias", (skv,))
     if cfg.use_qk_norm:   # attention.rs:120-129
-        out["self_attn.q_norm.weight"] = rms_norm_weight(get("self_attn.q_norm.weight", (hd,)), cfg)
-        out["self_attn.k_norm.weight"] = rms_norm_weight(get("self_attn.k_norm.weight", (hd,)), cfg)
+        pre = getattr(cfg, "pre_reshape_qk_norm", False)  # attention.rs:121-122: norm dim = size_q / size_kv (OLMo2) or head_dim
+        out["self_attn.q_norm.weight"] = rms_norm_weight(get("self_attn.q_norm.weight", (sq if pre else hd,)), cfg)
+        out["self_attn.k_norm.weight"] = rms_norm_weight(get("self_attn.k_norm.weight", (skv if pre else hd,)), cfg)
     return out
 
 

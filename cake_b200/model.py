@@ -193,7 +193,20 @@ class B200Transformer(Forwarder):
             keep.append(t)
         h = c_void_p()
         check(lib().cake_b200_block_load(ctx.h, _layer_index(name), *[ptr(t) for t in keep], byref(h)))
-        return cls(name, h, ctx)
+        blk = cls(name, h, ctx)
+        # the sibling block structures (models/{olmo2,gemma3,exaone4}/block.rs): post-norms and the per-layer attention mode
+        var = ctx.config.layer_variant(_layer_index(name), getattr(ctx, "max_seq", None))
+        if var["post_norms"] or var["window"] >= 0 or var["no_rope"]:
+            from .capi import CBlockVariant
+            extra = []
+            for k in ("post_attn_norm", "post_ffn_norm"):
+                t = views.get(k)
+                if t is not None:
+                    t = t.to(ctx.torch_dtype).contiguous()
+                extra.append(t)
+            cv = CBlockVariant(var["window"], 0 if var["no_rope"] else 1, ptr(extra[0]), ptr(extra[1]))
+            check(lib().cake_b200_block_set_variant(h, byref(cv)))
+        return blk
 
     def forward(self, x, index_pos, block_idx, ctx):
         return self.forward_batch(x, [(self.name, index_pos, block_idx)], ctx, blocks=[self])

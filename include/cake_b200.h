@@ -73,6 +73,8 @@ typedef struct cake_b200_config {
                          test_cache.rs:99-124). */
   int use_gelu_mlp;   /* mlp.rs:25-26: gelu_tanh(gate) * up instead of silu(gate) * up */
   float embed_scale;  /* text_model.rs:274-276: x = embedding * scale (0 = none) */
+  int pre_reshape_qk_norm; /* config.rs:116, attention.rs:176-192 (OLMo2): QK-norm over the whole q / k projection (weights
+                              [n_heads*head_dim] / [n_kv_heads*head_dim]) before the head reshape, instead of per head */
 } cake_b200_config;
 
 const char *cake_b200_last_error(void); /* thread-local; valid until the next call on this thread */
@@ -99,6 +101,25 @@ int cake_b200_block_load(cake_b200_ctx *, int layer_idx, const void *q, const vo
                          const void *k_norm, cake_b200_block **out);
 void cake_b200_block_free(cake_b200_block *);
 int cake_b200_block_layer(const cake_b200_block *); /* global layer index given at load */
+
+/* The sibling block structures — models/olmo2/block.rs:62-90, models/gemma3/block.rs:60-135, models/exaone4/block.rs:50-110 —
+ * are the same attention and MLP with a different norm placement and a per-layer attention mode
+ * (CausalSelfAttention::load_custom(vb, cfg, use_qk_norm, sliding_window, use_rope), attention.rs:76-149):
+ *   - cake_b200_block_load accepts ln1 == NULL and/or ln2 == NULL: no pre-attention / pre-MLP norm (OLMo2);
+ *   - post_attention_norm / post_feedforward_norm, when non-NULL ([hidden], D, host or device): RmsNorm of the attention /
+ *     MLP output BEFORE the residual add (OLMo2, Gemma3);
+ *   - sliding_window: -1 = the config's, 0 = none (a global layer), > 0 = this layer's window (cache.rs:173-205);
+ *   - use_rope: 0 = q and k are not rotated on this layer (EXAONE4 global layers, Gemma3 local layers; attention.rs:242-253).
+ * Part of loading: call it right after cake_b200_block_load, before the block is used.  A block with any of these set
+ * runs its single-token steps through the batched path as well (cake_b200_forward_batch works for every shape);
+ * cake_b200_decode_build refuses such blocks with CAKE_B200_EINVAL — hosts step them with cake_b200_forward_batch. */
+typedef struct cake_b200_block_variant {
+  int sliding_window;
+  int use_rope;
+  const void *post_attention_norm;
+  const void *post_feedforward_norm;
+} cake_b200_block_variant;
+int cake_b200_block_set_variant(cake_b200_block *, const cake_b200_block_variant *);
 
 /* ---- cache ------------------------------------------------------------------------------------ */
 int cake_b200_cache_create(cake_b200_ctx *, int batch, int max_seq, cake_b200_cache **out);

@@ -56,6 +56,7 @@ typedef struct ora_config {
   int sliding_window; /* cache.rs:173-205 (0 = none) */
   int use_gelu_mlp;   /* mlp.rs:25-26 */
   float embed_scale;  /* text_model.rs:274-276 (0 = none) */
+  int pre_reshape_qk_norm; /* attention.rs:176-192 (OLMo2): QK-norm over the whole q / k projection, before the head reshape */
   int silu_mode; /* 0: silu in f32 then round (cpu/mod.rs:87-89 via candle_nn::ops::silu)
                     1: per-op D arithmetic x/(1+exp(-x))*y (cuda ops.cu:105-109) — tolerance probe */
 } ora_config;
@@ -64,6 +65,11 @@ typedef struct ora_layer {
   const void *q, *k, *v, *o, *gate, *up, *down, *ln1, *ln2;
   const void *q_bias, *k_bias, *v_bias; /* nullable */
   const void *q_norm, *k_norm;          /* nullable */
+  /* the sibling block structures (models/{olmo2,gemma3,exaone4}/block.rs): ln1 / ln2 may be NULL (OLMo2 has no input
+   * norms); post_attn / post_ffn, when set, are RmsNorms applied to the attention / MLP output BEFORE the residual add */
+  const void *post_attn, *post_ffn;     /* nullable */
+  int window;   /* this layer's sliding window (attention.rs load_custom): -1 = the config's, 0 = none (global layer) */
+  int no_rope;  /* 1: this layer does not rotate q / k (attention.rs:242-253; exaone4 global, gemma3 local layers) */
 } ora_layer;
 
 typedef struct ora_model {
@@ -365,19 +371,25 @@ int ora_block_forward(const ora_model *m, int layer, ora_cache *kc, const float 
   float *gu = (float *)malloc(sizeof(float) * (size_t)S * 2 * I);
   float *mm = (float *)malloc(sizeof(float) * (size_t)S * I);
 
-  /* transformer.rs:112 rms_1 */
-  ora_rms_norm(x, S, H, L->ln1, c->rms_eps, h1, dt);
+  /* transformer.rs:112 rms_1 (olmo2/block.rs:70-76: no input norm, the attention reads x itself) */
+  if (L->ln1) ora_rms_norm(x, S, H, L->ln1, c->rms_eps, h1, dt);
+  else memcpy(h1, x, sizeof(float) * (size_t)S * H);
   /* attention.rs:162-174 fused qkv linear == three row-stacked linears (cat dim 0, :109-113) */
   ora_linear(h1, S, H, L->q, sq, L->q_bias, q, sq, dt);
   ora_linear(h1, S, H, L->k, skv, L->k_bias, kn, skv, dt);
   ora_linear(h1, S, H, L->v, skv, L->v_bias, vn, skv, dt);
+  /* attention.rs:176-192 OLMo2: QK-norm over the full projection (norm dim = size_q / size_kv), before the reshape */
+  if (c->qk_norm && c->pre_reshape_qk_norm && L->q_norm && L->k_norm) {
+    ora_rms_norm(q, S, sq, L->q_norm, c->rms_eps, q, dt);
+    ora_rms_norm(kn, S, skv, L->k_norm, c->rms_eps, kn, dt);
+  }
   /* attention.rs:202-215 per-head QK-norm over head_dim (Qwen3) */
-  if (c->qk_norm && L->q_norm && L->k_norm) {
+  if (c->qk_norm && !c->pre_reshape_qk_norm && L->q_norm && L->k_norm) {
     ora_rms_norm(q, S * nh, hd, L->q_norm, c->rms_eps, q, dt);
     ora_rms_norm(kn, S * nkv, hd, L->k_norm, c->rms_eps, kn, dt);
   }
   /* attention.rs:242-253 RoPE at absolute positions index_pos + t; v is not rotated */
-  for (int t = 0; t < S; t++) {
+  for (int t = 0; t < S && !L->no_rope; t++) {
     ora_rope(q + (size_t)t * sq, nh, hd, m->rot, m->cos_t, m->sin_t, index_pos + t, dt);
     ora_rope(kn + (size_t)t * skv, nkv, hd, m->rot, m->cos_t, m->sin_t, index_pos + t, dt);
   }
@@ -398,8 +410,9 @@ int ora_block_forward(const ora_model *m, int layer, ora_cache *kc, const float 
    * limit = min(window, max_seq_len) rows; the FIRST call stores (and attends over) everything (test_cache.rs:99-124).
    * The rows stay in place here; ws is the first row that survives the cut. */
   int ws = 0;
-  if (c->sliding_window > 0 && P0 > 0) {
-    const int limit = c->sliding_window < c->max_seq ? c->sliding_window : c->max_seq;
+  const int window = L->window >= 0 ? L->window : c->sliding_window;  /* per-layer override: load_custom(…, sliding_window, …) */
+  if (window > 0 && P0 > 0) {
+    const int limit = window < c->max_seq ? window : c->max_seq;
     if (T > limit) ws = T - limit;
   }
 #pragma omp parallel for collapse(2) schedule(static)
@@ -437,9 +450,12 @@ int ora_block_forward(const ora_model *m, int layer, ora_cache *kc, const float 
     }
   /* attention.rs:354 o_proj; transformer.rs:123 residual (D add) */
   ora_linear(y, S, sq, L->o, H, NULL, x1, H, dt);
+  /* olmo2/block.rs:77-79, gemma3/block.rs:120-122: post-attention RmsNorm of the attention output, then the residual */
+  if (L->post_attn) ora_rms_norm(x1, S, H, L->post_attn, c->rms_eps, x1, dt);
   for (size_t i = 0; i < (size_t)S * H; i++) x1[i] = rnd(x1[i] + x[i], dt);
   /* transformer.rs:129 rms_2; mlp.rs:22-30 */
-  ora_rms_norm(x1, S, H, L->ln2, c->rms_eps, h1, dt);
+  if (L->ln2) ora_rms_norm(x1, S, H, L->ln2, c->rms_eps, h1, dt);
+  else memcpy(h1, x1, sizeof(float) * (size_t)S * H);
   ora_linear(h1, S, H, L->gate, I, NULL, gu, 2 * I, dt);
   ora_linear(h1, S, H, L->up, I, NULL, gu + I, 2 * I, dt);
   for (int t = 0; t < S; t++)
@@ -447,6 +463,7 @@ int ora_block_forward(const ora_model *m, int layer, ora_cache *kc, const float 
       mm[(size_t)t * I + i] = c->use_gelu_mlp ? ora_gelu_mul(gu[(size_t)t * 2 * I + i], gu[(size_t)t * 2 * I + I + i], dt)
                                               : ora_silu_mul(gu[(size_t)t * 2 * I + i], gu[(size_t)t * 2 * I + I + i], dt, c->silu_mode);
   ora_linear(mm, S, I, L->down, H, NULL, out, H, dt);
+  if (L->post_ffn) ora_rms_norm(out, S, H, L->post_ffn, c->rms_eps, out, dt);  /* olmo2/block.rs:84-86, gemma3/block.rs:130-132 */
   /* transformer.rs:131 mlp residual */
   for (size_t i = 0; i < (size_t)S * H; i++) out[i] = rnd(out[i] + x1[i], dt);
 

@@ -26,7 +26,8 @@ class OraConfig(ctypes.Structure):
 class OraLayer(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in
                 ("q", "k", "v", "o", "gate", "up", "down", "ln1", "ln2",
-                 "q_bias", "k_bias", "v_bias", "q_norm", "k_norm")]
+                 "q_bias", "k_bias", "v_bias", "q_norm", "k_norm", "post_attn", "post_ffn")] + \
+               [("window", ctypes.c_int), ("no_rope", ctypes.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -222,17 +223,18 @@ class OracleModel:
             self._keep.append(t)
             return t
 
-        from cake_b200.loader import BLOCK_TENSORS, block_tensors  # same tensor naming / fused-checkpoint rules as the loader
+        from cake_b200.loader import BLOCK_TENSORS, EXTRA_TENSORS, block_tensors  # same tensor naming / fused-checkpoint rules as the loader
         for i in (layers if layers is not None else range(cfg.num_hidden_layers)):
             views = block_tensors(weights, cfg, cfg.layer_name(i))
+            var = cfg.layer_variant(i, self.ccfg.max_seq)
             ptrs = []
-            for short in BLOCK_TENSORS:
+            for short in BLOCK_TENSORS + EXTRA_TENSORS:
                 t = views[short]
                 if t is not None:
                     t = t.detach().cpu().contiguous()
                     self._keep.append(t)
                 ptrs.append(_ptr(t))
-            ol = OraLayer(*ptrs)
+            ol = OraLayer(*ptrs, var["window"], int(var["no_rope"]))
             lib().ora_model_set_layer(self.h, i, ctypes.byref(ol))
         from cake_b200.loader import rms_norm_weight
         emb, lnf, head = W(f"{p}.embed_tokens.weight"), W(f"{p}.norm.weight"), W("lm_head.weight")

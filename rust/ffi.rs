@@ -19,6 +19,7 @@ pub struct cake_b200_config {
     pub rope_llama3: c_int, pub rope_factor: f32, pub rope_low: f32, pub rope_high: f32, pub rope_orig_max: c_int,
     pub dtype: c_int, // 0 = bf16, 1 = f16
     pub sliding_window: c_int, pub use_gelu_mlp: c_int, pub embed_scale: f32,
+    pub pre_reshape_qk_norm: c_int, // config.rs:116 (OLMo2)
 }
 
 #[link(name = "cake_b200")]
@@ -79,6 +80,18 @@ extern "C" {
         ctx_tokens_host: *const u32, n_tokens: c_int, step: u64, noise_host: *const f32, token_host: *mut u32) -> c_int;
     pub fn cake_b200_decode_set_sampling(ctx: *mut cake_b200_ctx, sampling: *const cake_b200_sampling) -> c_int;
     pub fn cake_b200_load_stats(ctx: *mut cake_b200_ctx, bytes: *mut f64, seconds: *mut f64) -> c_int;
+    pub fn cake_b200_block_set_variant(block: *mut cake_b200_block, variant: *const cake_b200_block_variant) -> c_int;
+}
+
+/// `cake_b200_block_variant` (include/cake_b200.h): norm placement and per-layer attention mode of the OLMo2 / Gemma3 /
+/// EXAONE4 blocks (models/{olmo2,gemma3,exaone4}/block.rs).
+#[repr(C)]
+#[derive(Clone, Copy, Debug)]
+pub struct cake_b200_block_variant {
+    pub sliding_window: c_int, // -1 = the config's, 0 = none, > 0 = this layer's
+    pub use_rope: c_int,
+    pub post_attention_norm: *const c_void,
+    pub post_feedforward_norm: *const c_void,
 }
 
 /// `cake_b200_sampling` (include/cake_b200.h): the Sampling enum of candle_transformers::generation flattened.

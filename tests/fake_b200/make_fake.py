@@ -92,8 +92,8 @@ ORACLE = r'''
 
 /* oracle/cake_oracle.c API (test infrastructure) */
 typedef struct ora_config { int hidden, inter, n_heads, n_kv_heads, head_dim, n_layers, vocab, max_seq; float rms_eps, rope_theta, partial_rotary;
-  int qkv_bias, qk_norm, tie_embeddings; int rope_llama3; float rope_factor, rope_low, rope_high; int rope_orig_max; int dtype; int sliding_window, use_gelu_mlp; float embed_scale; int silu_mode; } ora_config;
-typedef struct ora_layer { const void *q, *k, *v, *o, *gate, *up, *down, *ln1, *ln2, *q_bias, *k_bias, *v_bias, *q_norm, *k_norm; } ora_layer;
+  int qkv_bias, qk_norm, tie_embeddings; int rope_llama3; float rope_factor, rope_low, rope_high; int rope_orig_max; int dtype; int sliding_window, use_gelu_mlp; float embed_scale; int pre_reshape_qk_norm; int silu_mode; } ora_config;
+typedef struct ora_layer { const void *q, *k, *v, *o, *gate, *up, *down, *ln1, *ln2, *q_bias, *k_bias, *v_bias, *q_norm, *k_norm, *post_attn, *post_ffn; int window, no_rope; } ora_layer;
 typedef struct ora_model ora_model;
 typedef struct ora_cache ora_cache;
 ora_model *ora_model_create(const ora_config *);
@@ -113,7 +113,7 @@ float ora_round(float f, int dt);
 
 struct cake_b200_ctx { cake_b200_config cfg; ora_config oc; ora_model *m; int n_blocks_dec; int dec_idx[512]; cake_b200_cache *dec_cache; int pos; float *last_logits;
   uint32_t cur_token; uint32_t ring[4096]; unsigned long long steps; };
-struct cake_b200_block { int layer; };
+struct cake_b200_block { int layer; cake_b200_ctx *c; ora_layer l; };
 struct cake_b200_cache { cake_b200_ctx *c; ora_cache *k; ora_cache **rows; int batch; int cap; };  /* k == rows[0] */
 static __thread char g_err[256] = "";
 static int fail(int code, const char *msg) { snprintf(g_err, sizeof g_err, "%s", msg); return code; }
@@ -158,17 +158,28 @@ int cake_b200_head_load(cake_b200_ctx *c, const void *embed, const void *ln_f, c
 int cake_b200_block_load(cake_b200_ctx *c, int layer, const void *q, const void *k, const void *v, const void *o, const void *gate,
                          const void *up, const void *down, const void *ln1, const void *ln2, const void *qb, const void *kb,
                          const void *vb, const void *qn, const void *kn, cake_b200_block **out) {
-  if (!c || !q || !k || !v || !o || !gate || !up || !down || !ln1 || !ln2 || !out) return fail(CAKE_B200_EINVAL, "null weight pointer");
+  if (!c || !q || !k || !v || !o || !gate || !up || !down || !out) return fail(CAKE_B200_EINVAL, "null weight pointer");
   if (layer < 0 || layer >= c->cfg.n_layers) return fail(CAKE_B200_EINVAL, "layer out of range");
-  ln1 = own_copy(ln1, (size_t)c->cfg.hidden * 2);
-  ln2 = own_copy(ln2, (size_t)c->cfg.hidden * 2);
-  if (qn) qn = own_copy(qn, (size_t)c->cfg.head_dim * 2);
-  if (kn) kn = own_copy(kn, (size_t)c->cfg.head_dim * 2);
-  ora_layer l = {q, k, v, o, gate, up, down, ln1, ln2, qb, kb, vb, qn, kn};
+  const size_t sq_ = (size_t)c->cfg.n_heads * c->cfg.head_dim, skv_ = (size_t)c->cfg.n_kv_heads * c->cfg.head_dim;
+  if (ln1) ln1 = own_copy(ln1, (size_t)c->cfg.hidden * 2);
+  if (ln2) ln2 = own_copy(ln2, (size_t)c->cfg.hidden * 2);
+  if (qn) qn = own_copy(qn, (c->cfg.pre_reshape_qk_norm ? sq_ : (size_t)c->cfg.head_dim) * 2);
+  if (kn) kn = own_copy(kn, (c->cfg.pre_reshape_qk_norm ? skv_ : (size_t)c->cfg.head_dim) * 2);
+  ora_layer l = {q, k, v, o, gate, up, down, ln1, ln2, qb, kb, vb, qn, kn, NULL, NULL, -1, 0};
   ora_model_set_layer(c->m, layer, &l);
   cake_b200_block *b = (cake_b200_block *)malloc(sizeof *b);
-  b->layer = layer;
+  b->layer = layer; b->c = c; b->l = l;
   *out = b;
+  return 0;
+}
+int cake_b200_block_set_variant(cake_b200_block *b, const cake_b200_block_variant *v) {
+  if (!b || !v) return fail(CAKE_B200_EINVAL, "null argument");
+  if (v->sliding_window < -1) return fail(CAKE_B200_EINVAL, "bad sliding_window");
+  if (v->post_attention_norm) b->l.post_attn = own_copy(v->post_attention_norm, (size_t)b->c->cfg.hidden * 2);
+  if (v->post_feedforward_norm) b->l.post_ffn = own_copy(v->post_feedforward_norm, (size_t)b->c->cfg.hidden * 2);
+  b->l.window = v->sliding_window;
+  b->l.no_rope = v->use_rope ? 0 : 1;
+  ora_model_set_layer(b->c->m, b->layer, &b->l);
   return 0;
 }
 void cake_b200_block_free(cake_b200_block *b) { free(b); }
@@ -222,8 +233,10 @@ int cake_b200_forward_batch(cake_b200_ctx *c, cake_b200_block *const *blocks, co
   if (!c || !blocks || !idx || !kc || !x || !y || n < 1) return fail(CAKE_B200_EINVAL, "null/empty argument");
   if (batch != kc->batch) { snprintf(g_err, sizeof g_err, "batch %d != cache batch %d", batch, kc->batch); return CAKE_B200_EINVAL; }
   if (seq < 1 || pos < 0) return fail(CAKE_B200_ESTATE, "bad position");
-  if (c->cfg.sliding_window > 0 && pos > 0 && seq > c->cfg.sliding_window)
-    return fail(CAKE_B200_EINVAL, "a chunk on a non-empty cache exceeds the sliding window");
+  for (int i = 0; i < n; i++) {
+    const int w = blocks[i]->l.window >= 0 ? blocks[i]->l.window : c->cfg.sliding_window;
+    if (w > 0 && pos > 0 && seq > w) return fail(CAKE_B200_EINVAL, "a chunk on a non-empty cache exceeds the sliding window");
+  }
   const size_t ne = (size_t)seq * c->cfg.hidden;
   float *f = (float *)malloc(ne * 4);
   int rc = 0;
@@ -280,6 +293,9 @@ int cake_b200_repeat_penalty_argmax(cake_b200_ctx *c, void *logits_dev, float pe
 static cake_b200_block g_dec_blocks[512];
 int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *blocks, const int *idx, int n, cake_b200_cache *kc, int rank, int world) {
   if (!c || !blocks || !idx || !kc || n < 1 || n > 512) return fail(CAKE_B200_EINVAL, "bad decode_build arguments");
+  for (int i = 0; i < n; i++)
+    if (!blocks[i]->l.ln1 || !blocks[i]->l.ln2 || blocks[i]->l.post_attn || blocks[i]->l.post_ffn || blocks[i]->l.window >= 0 || blocks[i]->l.no_rope || c->cfg.pre_reshape_qk_norm)
+      return fail(CAKE_B200_EINVAL, "sibling block structure: the decode graph covers the standard block only; step it with cake_b200_forward_batch");
   if (world != 1 || rank != 0) return fail(CAKE_B200_EINVAL, "the emulation handles world == 1");
   c->n_blocks_dec = n; c->dec_cache = kc;
   for (int i = 0; i < n; i++) { c->dec_idx[i] = idx[i]; g_dec_blocks[i] = *blocks[i]; }
@@ -324,7 +340,7 @@ int cake_b200_decode_logits(cake_b200_ctx *c, void *logits_host, size_t bytes) {
 '''
 
 DONE_ORACLE = {"cake_b200_last_error", "cake_b200_version", "cake_b200_ctx_create", "cake_b200_ctx_destroy", "cake_b200_sync", "cake_b200_dev_alloc",
-               "cake_b200_dev_free", "cake_b200_head_load", "cake_b200_block_load", "cake_b200_block_free", "cake_b200_block_layer",
+               "cake_b200_dev_free", "cake_b200_head_load", "cake_b200_block_load", "cake_b200_block_set_variant", "cake_b200_block_free", "cake_b200_block_layer",
                "cake_b200_cache_create", "cake_b200_cache_clear", "cake_b200_cache_free", "cake_b200_cache_len", "cake_b200_cache_read", "cake_b200_forward_batch",
                "cake_b200_forward_batch_host", "cake_b200_embed", "cake_b200_logits", "cake_b200_repeat_penalty_argmax", "cake_b200_decode_build",
                "cake_b200_decode_begin", "cake_b200_decode_step_host", "cake_b200_decode_run", "cake_b200_decode_tokens", "cake_b200_decode_logits"}

@@ -42,7 +42,7 @@ def _prototypes(src: str, pattern: str) -> dict:
 
 def test_rust_binding_declares_every_entry_point_with_the_same_arity():
     """rust/ffi.rs cannot be compiled here (no rustc): at least its extern block must list exactly the header's
-    functions with the header's argument counts, and its config struct the header's 23 fields in order."""
+    functions with the header's argument counts, and its config struct the header's 24 fields in order."""
     hdr = open(os.path.join(ROOT, "include", "cake_b200.h")).read()
     rs = open(os.path.join(ROOT, "rust", "ffi.rs")).read()
     c = _prototypes(hdr, r"\b(cake_b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;")
@@ -58,8 +58,8 @@ def test_rust_binding_declares_every_entry_point_with_the_same_arity():
 
 
 def test_cconfig_matches_header_layout():
-    # 23 4-byte fields, no padding
-    assert ctypes.sizeof(CConfig) == 23 * 4
+    # 24 4-byte fields, no padding
+    assert ctypes.sizeof(CConfig) == 24 * 4
     c = CConfig.from_config(llama3_8b(), "bf16")
     assert (c.hidden, c.inter, c.n_heads, c.n_kv_heads, c.head_dim, c.n_layers, c.vocab) == \
            (4096, 14336, 32, 8, 128, 32, 128256)

@@ -73,14 +73,44 @@ def test_python_and_cpp_resolve_the_same_block_config(tmp_path, name):
 
 @pytest.mark.parametrize("arch", ["Gemma3ForCausalLM", "Qwen3MoeForCausalLM", "OLMo2ForCausalLM", "ExaoneForCausalLM"])
 def test_other_block_types_are_refused_by_name(tmp_path, arch):
+    """MoE / linear-attention blocks are outside the path everywhere; the three dense sibling blocks are served by the
+    library and the Python host (next test) while the compiled C++ host still steps the standard block only."""
     d = {**BASE, "architectures": [arch]}
-    with pytest.raises(ValueError, match="outside the block-forward path"):
-        Config.from_hf(d)
+    if arch == "Qwen3MoeForCausalLM":
+        with pytest.raises(ValueError, match="outside the block-forward path"):
+            Config.from_hf(d)
     build_host()
     with open(tmp_path / "config.json", "w") as f:
         json.dump(d, f)
     r = subprocess.run([RUN, str(tmp_path), "--show-config"], capture_output=True, text=True)
     assert r.returncode == 1 and "outside the block-forward path" in r.stderr
+
+
+def test_sibling_block_structures_resolve_like_the_reference():
+    """models/{olmo2,gemma3,exaone4}/config.rs into_config + block.rs load: flags, per-layer schedule, norm placement."""
+    o = Config.from_hf({**BASE, "architectures": ["Olmo2ForCausalLM"]})
+    assert (o.block_kind, o.use_qk_norm, o.pre_reshape_qk_norm, o.rope_theta, o.sliding_window) == ("olmo2", True, True, 500000.0, None)
+    assert o.layer_variant(0) == dict(pre_norms=False, post_norms=True, window=-1, no_rope=False)
+    assert CConfig.from_config(o, "bf16").pre_reshape_qk_norm == 1
+
+    e = Config.from_hf({**BASE, "architectures": ["ExaoneForCausalLM"], "num_hidden_layers": 8, "sliding_window": 16,
+                        "max_position_embeddings": 64})
+    assert e.block_kind == "exaone4" and e.use_qk_norm and not e.pre_reshape_qk_norm
+    assert e.global_layers == [False, False, False, True, False, False, False, True]       # exaone4/config.rs is_global_layer, period 4
+    assert e.layer_variant(0) == dict(pre_norms=True, post_norms=False, window=16, no_rope=False)   # local: window + RoPE
+    assert e.layer_variant(3) == dict(pre_norms=True, post_norms=False, window=0, no_rope=True)     # global: full context, no RoPE
+    assert e.layer_variant(0, max_seq=16)["window"] == 0                                            # a window that can never bite
+
+    g = Config.from_hf({**BASE, "architectures": ["Gemma3ForCausalLM"], "num_hidden_layers": 12, "sliding_window": 16,
+                        "max_position_embeddings": 64, "hidden_size": 1152})
+    assert g.block_kind == "gemma3" and g.residual_rms_norm and g.use_gelu_mlp and g.tie_word_embeddings and g.use_qk_norm
+    assert abs(g.embed_scale - 1152 ** 0.5) < 1e-5 and g.rope_theta == 10000.0
+    assert [i for i, x in enumerate(g.global_layers) if x] == [5, 11]                       # gemma3/config.rs test_gemma3_pattern
+    assert g.layer_variant(0) == dict(pre_norms=True, post_norms=True, window=16, no_rope=True)     # local: window, NO RoPE
+    assert g.layer_variant(5) == dict(pre_norms=True, post_norms=True, window=0, no_rope=False)     # global: full context + RoPE
+    g2 = Config.from_hf({**BASE, "architectures": ["Gemma3ForCausalLM"], "num_hidden_layers": 3,
+                         "sliding_window_attention_schedule": [True, False, True]})
+    assert g2.global_layers == [True, False, True]
 
 
 def test_active_sliding_window_reaches_the_library(tmp_path):
