@@ -75,6 +75,11 @@ class Config:
             return dict(pre_norms=True, post_norms=True, window=0 if is_global else win(self.sliding_window), no_rope=not is_global)
         if self.block_kind == "exaone4":
             return dict(pre_norms=True, post_norms=False, window=0 if is_global else win(self.sliding_window), no_rope=is_global)
+        if self.block_kind == "exaone4_hf":
+            # NOT a reference block: the structure HF transformers gives EXAONE 4.0 (post-norms like OLMo2 + the hybrid
+            # schedule).  Test-only: it pins the oracle's per-layer NoPE / window handling to an independent implementation
+            # (tests/golden/hf_exaone4_hf_tiny.npz); the reference's own EXAONE4 block is pre-norm (exaone4/block.rs:96-110).
+            return dict(pre_norms=False, post_norms=True, window=0 if is_global else win(self.sliding_window), no_rope=is_global)
         return dict(pre_norms=True, post_norms=False, window=-1, no_rope=False)
 
     @property

@@ -254,7 +254,7 @@ def block_tensors(vb, cfg: Config, name: str) -> Dict[str, Optional[torch.Tensor
     kind = getattr(cfg, "block_kind", "llama")
     out.update({k: None for k in EXTRA_TENSORS})
     norm = lambda short: rms_norm_weight(get(short, (H,)), cfg)
-    if kind == "olmo2":
+    if kind in ("olmo2", "exaone4_hf"):
         out["post_attn_norm"], out["post_ffn_norm"] = norm("post_attention_layernorm.weight"), norm("post_feedforward_layernorm.weight")
     elif kind == "gemma3":
         out["input_layernorm.weight"] = norm("input_layernorm.weight")

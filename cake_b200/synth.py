@@ -32,10 +32,25 @@ def layer_tensor_shapes(cfg: Config) -> dict:
         s["self_attn.q_proj.bias"] = (cfg.size_q,)
         s["self_attn.k_proj.bias"] = (cfg.size_kv,)
         s["self_attn.v_proj.bias"] = (cfg.size_kv,)
-    if cfg.use_qk_norm:
-        s["self_attn.q_norm.weight"] = (cfg.hd,)
-        s["self_attn.k_norm.weight"] = (cfg.hd,)
+    if cfg.use_qk_norm:  # attention.rs:121-122: over head_dim, or over the whole projection (OLMo2)
+        pre = getattr(cfg, "pre_reshape_qk_norm", False)
+        s["self_attn.q_norm.weight"] = (cfg.size_q if pre else cfg.hd,)
+        s["self_attn.k_norm.weight"] = (cfg.size_kv if pre else cfg.hd,)
+    kind = getattr(cfg, "block_kind", "llama")
+    if kind in ("olmo2", "exaone4_hf"):     # olmo2/block.rs:49-52: two post-norms, no input norms
+        del s["input_layernorm.weight"]
+        s["post_feedforward_layernorm.weight"] = (H,)
+    elif kind == "gemma3":  # gemma3/block.rs:84-91: four norms
+        s["pre_feedforward_layernorm.weight"] = (H,)
+        s["post_feedforward_layernorm.weight"] = (H,)
     return s
+
+
+def residual_deltas(sd: dict) -> dict:
+    """Checkpoints of ``residual_rms_norm`` models (Gemma3) store norm weights as deltas around 0 (forward weight = 1 + w,
+    config.rs:155-173): turn a synthetic checkpoint whose norm vectors sit around 1 into that convention."""
+    return {k: ((v.float() - 1.0).to(v.dtype) if (k.endswith("norm.weight") or k.endswith("layernorm.weight")) else v)
+            for k, v in sd.items()}
 
 
 def _fill(shape, name: str, gen: torch.Generator, device, dtype, std: float):

@@ -403,3 +403,62 @@ def test_tcgen05_prefill_attention_head_dim_128_shapes(dtype):
                 assert e <= BLOCK_TOL_ULP, f"window {window}, batch row {b}, {n} tokens @ {pos}: {e} ulp"
             pos += n
         ctx.close()
+
+
+SIBLINGS = {
+    # models/olmo2/block.rs:62-90 + attention.rs:176-192: no pre-norms, post-norms, QK-norm over the whole projection
+    "olmo2": dict(block_kind="olmo2", use_qk_norm=True, pre_reshape_qk_norm=True),
+    # models/gemma3/block.rs:60-135: four norms with (1 + w) weights, gelu MLP, scaled embeddings, tied head; local layers
+    # (0, 2): window 5, NO RoPE; global layers (1, 3): full context + RoPE
+    "gemma3": dict(block_kind="gemma3", use_qk_norm=True, residual_rms_norm=True, use_gelu_mlp=True, tie_word_embeddings=True,
+                   embed_scale=22.627416997969522, sliding_window=5, global_layers=[False, True, False, True]),
+    # models/exaone4/block.rs:50-110: the standard pre-norm block; local layers: window 5 + RoPE, global: full context, NO RoPE
+    "exaone4": dict(block_kind="exaone4", use_qk_norm=True, sliding_window=5, global_layers=[False, True, False, True]),
+}
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("kind", list(SIBLINGS))
+def test_sibling_block_structures_match_oracle(kind, dtype):
+    """The OLMo2 / Gemma3 / EXAONE4 blocks (cake_b200_block_set_variant + pre-reshape QK-norm) through the model: a prompt
+    that fits the local window, then host-stepped tokens far past it (single-token steps of these blocks go through the
+    batched path), logits and greedy tokens against the oracle; then every block on a multi-token second chunk."""
+    from cake_b200.model import B200Transformer, Context, TextModelBase
+    from cake_b200.synth import residual_deltas
+    from cake_b200.capi import CakeB200Error
+    from tests.util import ulp_at_scale
+    cfg = medium_config(num_hidden_layers=4, **SIBLINGS[kind])
+    sd = checkpoint(cfg, dtype, seed=91, peaked=not cfg.tie_word_embeddings)
+    if cfg.residual_rms_norm:
+        sd = residual_deltas(sd)
+    om = O.OracleModel(cfg, sd, dtype, max_seq=64)
+    prompt = [3, 700, 41, 9, 256]
+    ref_toks, ref_logits = om.generate(prompt, 14)
+    ctx = Context(cfg, sd, dtype, device=0, max_seq=64)
+    m = TextModelBase.load(ctx)
+    with pytest.raises(CakeB200Error, match="sibling block structure"):
+        m.decode_build()   # the decode graph covers the standard block only
+    m.prepare_prompt(prompt)
+    for i in range(14):    # teacher-forced on the oracle's greedy sequence
+        t = m.next_token(i)
+        e = max_ulp_err(to_np(m.last_logits), ref_logits[i], dtype)
+        assert e <= LOGIT_TOL_ULP, f"{kind} step {i}: logits {e} ulp"
+        top2 = np.sort(ref_logits[i])[-2:]
+        if top2[1] - top2[0] > 2 * LOGIT_TOL_ULP * ulp_at_scale(ref_logits[i], dtype):
+            assert t.id == ref_toks[i], f"{kind} step {i}: token {t.id} != {ref_toks[i]}"
+        m.tokens[-1] = int(ref_toks[i])
+    # block level: 4 tokens, then a 3-token chunk on the non-empty cache (<= the window), then single tokens
+    x = rand_x((1, 12, cfg.hidden_size), dtype, seed=92)
+    for layer in range(4):
+        ctx.cache.clear()
+        oc = om.new_cache()
+        blk = m.blocks[layer]
+        pos = 0
+        for n in (4, 3, 1, 1, 2, 1):
+            y_ref = om.block_forward(layer, x[0, pos:pos + n].float().numpy(), pos, oc)
+            y = blk.forward(ctx.to_device(x[:, pos:pos + n]), pos, layer, ctx)
+            ctx.sync()
+            e = max_ulp_err(to_np(y[0]), y_ref, dtype)
+            assert e <= BLOCK_TOL_ULP, f"{kind} layer {layer}: {n} token(s) @ {pos}: {e} ulp"
+            pos += n
+    ctx.close()
