@@ -1261,7 +1261,10 @@ extern "C" int cake_b200_forward_batch(cake_b200_ctx *c, cake_b200_block *const 
                   block_idx[i], index_pos, kc->len[block_idx[i]]);
   }
   bool variant = false;  // sibling block structures step through the batched path (cake_b200_block_set_variant)
-  for (int i = 0; i < n_blocks; i++) variant = variant || blocks[i]->variant();
+  for (int i = 0; i < n_blocks; i++) {
+    if (!blocks[i]) return fail(CAKE_B200_EINVAL, "blocks[%d] is null", i);
+    variant = variant || blocks[i]->variant();
+  }
   if (batch == 1 && seq == 1 && !variant) {
     set_int_kernel<<<1, 1, 0, c->stream>>>(kc->d_pos, index_pos);
     c->launches++;
@@ -1543,7 +1546,7 @@ extern "C" int cake_b200_decode_build(cake_b200_ctx *c, cake_b200_block *const *
   if (world > 1 && !c->comm) return fail(CAKE_B200_ESTATE, "world > 1 needs cake_b200_comm_init first");
   if (rank == 0 && !c->lm_head) return fail(CAKE_B200_ESTATE, "rank 0 needs cake_b200_head_load first");
   for (int i = 0; i < n_blocks; i++)
-    if (blocks[i]->variant())
+    if (blocks[i] && blocks[i]->variant())
       return fail(CAKE_B200_EINVAL, "block %d is a sibling block structure (cake_b200_block_set_variant / pre-reshape QK-norm): "
                   "the decode graph covers the standard block only; step it with cake_b200_forward_batch", block_idx[i]);
   CU(cudaSetDevice(c->device));
@@ -1724,6 +1727,8 @@ extern "C" int cake_b200_bench_kernel(cake_b200_ctx *c, cake_b200_block *const *
                                       int n_blocks, cake_b200_cache *kc, int which, int reps, float *ms_per_launch) {
   if (!c || !blocks || !kc || !ms_per_launch || n_blocks < 1 || reps < 1 || which < 0 || which > 4)
     return fail(CAKE_B200_EINVAL, "bad bench_kernel arguments");
+  for (int i = 0; i < n_blocks; i++)
+    if (!blocks[i] || blocks[i]->variant()) return fail(CAKE_B200_EINVAL, "bench_kernel times the per-op kernels of standard blocks only");
   CU(cudaSetDevice(c->device));
   RC(wait_loads(c));
   for (int i = 0; i < n_blocks; i++) RC(cache_ensure(kc, block_idx[i]));
