@@ -27,6 +27,7 @@ Besides the headline metric the line carries (N = 1 unless noted):
 from __future__ import annotations
 
 import argparse
+import gc
 import hashlib
 import json
 import os
@@ -482,6 +483,11 @@ def decode_leg(env: Env, model: str, K: int, W: int, n_e2e: int, parity: bool, i
     if n_e2e > 0:
         tok = all_tokens[-1] if rank == 0 else 0
         sh.begin(tok)
+        # a generation-2 collection of this process's heap (torch + numpy + the checkpoint dicts: ~1M tracked objects) takes
+        # tens of ms and lands on whichever step trips the counter — the N=4 rehearsal showed exactly one 70 ms step in 64
+        # (p50 3.00 ms): collect now, keep the collector off while steps are being timed with the host clock
+        gc.collect()
+        gc.disable()
         env.barrier()
         if rank == 0:
             nxt = c_uint32()
@@ -500,6 +506,7 @@ def decode_leg(env: Env, model: str, K: int, W: int, n_e2e: int, parity: bool, i
         else:
             sh.run(n_e2e + E2E_WARM)
             sh.wait(sh.event())
+        gc.enable()
         env.barrier()
 
     # ---- parity: the first tokens of this very model against the oracle, teacher-forced (rank 0 checks) ----------
