@@ -180,7 +180,25 @@ def test_master_worker_protocol_world2_gloo():
 
 
 # ---- the same protocol with the real block class over the emulated library -------------------------------------------
-def _run_real_blocks(rank, world, port, q, so_path):
+_REAL_KINDS = {
+    "llama": dict(),
+    # a sibling block structure through the same master / worker plumbing: per-layer variants are set on whichever rank
+    # loads the layer (gemma3/block.rs: local layers 0, 2 = window 5 without RoPE; global layers 1, 3 = full context + RoPE)
+    "gemma3": dict(block_kind="gemma3", use_qk_norm=True, residual_rms_norm=True, use_gelu_mlp=True, tie_word_embeddings=True,
+                   embed_scale=11.313708498984761, sliding_window=5, global_layers=[False, True, False, True]),
+}
+
+
+def _real_cfg_sd(kind):
+    from cake_b200.synth import residual_deltas
+    from tests.util import checkpoint, medium_config
+    cfg = medium_config(num_hidden_layers=4, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+                        num_key_value_heads=2, head_dim=32, **_REAL_KINDS[kind])
+    sd = checkpoint(cfg, "bf16", seed=23, peaked=not cfg.tie_word_embeddings)
+    return cfg, (residual_deltas(sd) if cfg.residual_rms_norm else sd)
+
+
+def _run_real_blocks(rank, world, port, q, so_path, kind="llama"):
     """rank 0: TextModelBase whose layers 2-3 are `Client`s (GlooTransport); rank 1: `Worker` with B200Transformer blocks.
     The C ABI behind both is the oracle-backed emulation (tests/fake_b200), contexts are tests/cpu_ctx.CpuContext."""
     import numpy as np
@@ -191,9 +209,7 @@ def _run_real_blocks(rank, world, port, q, so_path):
     capi.SO_PATH, capi._lib = so_path, None
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    cfg = medium_config(num_hidden_layers=4, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
-                        num_key_value_heads=2, head_dim=32)
-    sd = checkpoint(cfg, "bf16", seed=23, peaked=True)
+    cfg, sd = _real_cfg_sd(kind)
     ctx = CpuContext(cfg, sd, "bf16", max_seq=64)
     tr = GlooTransport()
     try:
@@ -217,7 +233,8 @@ def _run_real_blocks(rank, world, port, q, so_path):
         ctx.close()
 
 
-def test_sharded_master_and_worker_with_real_blocks_over_gloo(tmp_path):
+@pytest.mark.parametrize("kind", list(_REAL_KINDS))
+def test_sharded_master_and_worker_with_real_blocks_over_gloo(tmp_path, kind):
     from oracle import oracle as O
     from tests.fake_b200.make_fake import build as build_fake
     from tests.util import checkpoint, medium_config
@@ -225,7 +242,7 @@ def test_sharded_master_and_worker_with_real_blocks_over_gloo(tmp_path):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_run_real_blocks, args=(r, 2, port, q, so)) for r in range(2)]
+    procs = [ctx.Process(target=_run_real_blocks, args=(r, 2, port, q, so, kind)) for r in range(2)]
     for p in procs:
         p.start()
     res = dict()
@@ -236,9 +253,7 @@ def test_sharded_master_and_worker_with_real_blocks_over_gloo(tmp_path):
         p.join(timeout=60)
         assert p.exitcode == 0
     toks, toks2, prompt = res["master"]
-    cfg = medium_config(num_hidden_layers=4, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
-                        num_key_value_heads=2, head_dim=32)
-    sd = checkpoint(cfg, "bf16", seed=23, peaked=True)
+    cfg, sd = _real_cfg_sd(kind)
     om = O.OracleModel(cfg, sd, "bf16", max_seq=64)
     assert toks == list(om.generate(prompt, 6)[0]) and toks2 == list(om.generate(prompt[:4], 3)[0])
     assert res["worker"] == (6 + 3, 4 + 2)   # one batch per forward; the worker's cache holds the second prompt: 4 + 2 fed-back tokens
