@@ -230,6 +230,15 @@ class Config:
             d["partial_rotary_factor"] = self.partial_rotary_factor
         if self.rope_scaling:
             d["rope_scaling"] = asdict(self.rope_scaling)
+        # the keys the sibling architectures' config.rs read (models/{gemma3,exaone4}/config.rs)
+        if self.block_kind == "gemma3":
+            d["sliding_window_attention_schedule"] = [bool(g) for g in self.global_layers]
+        elif self.block_kind == "exaone4":
+            hits = [i + 1 for i, g in enumerate(self.global_layers) if g]
+            period = hits[0] if hits else self.num_hidden_layers + 1
+            if [(i + 1) % period == 0 for i in range(self.num_hidden_layers)] != [bool(g) for g in self.global_layers]:
+                raise ValueError("EXAONE4 can only express an every-n-th global-layer schedule (global_layer_period)")
+            d["global_layer_period"] = period
         return d
 
     def is_eos(self, tok: int) -> bool:

@@ -19,6 +19,7 @@
 #include <unistd.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <fstream>
@@ -146,6 +147,21 @@ struct Config {
   std::vector<uint32_t> eos;
   std::string arch;
   bool fused_qkv_proj = false, fused_gate_up_proj = false;  // attention.rs:90-94, mlp.rs:38-40
+  // the sibling block structures (models/{olmo2,gemma3,exaone4}/block.rs)
+  std::string block_kind = "llama";   // "llama" (common/transformer.rs) | "olmo2" | "gemma3" | "exaone4"
+  std::vector<bool> global_layers;    // config.rs:126-130: per-layer schedule, true = global (full context)
+  bool residual_rms_norm = false;     // config.rs:113: norm weights stored as deltas, (1 + w) in f32 at load (config.rs:155-173)
+  int layer_window = 0;               // the local layers' sliding window (already 0 when it can never bite)
+  struct Variant { bool pre_norms, post_norms; int window; bool no_rope; };
+  // norm placement and attention mode of layer i, as each block.rs sets them up (see cake_b200_block_set_variant)
+  Variant layer_variant(int i) const {
+    const bool g = i < (int)global_layers.size() && global_layers[i];
+    if (block_kind == "olmo2") return {false, true, -1, false};                        // olmo2/block.rs:62-90
+    if (block_kind == "gemma3") return {true, true, g ? 0 : layer_window, !g};          // gemma3/block.rs:60-66: local = window, no RoPE
+    if (block_kind == "exaone4") return {true, false, g ? 0 : layer_window, g};         // exaone4/block.rs:50-58: global = no RoPE
+    return {true, false, -1, false};
+  }
+  bool standard_blocks() const { return block_kind == "llama"; }
   static Config from_path(const std::string &path, int dtype, int max_seq_override = 0) {
     std::string txt = slurp(path);
     Json j = JsonParser(txt.data(), txt.size()).value();
@@ -168,13 +184,24 @@ struct Config {
         {"Phi4ForCausalLM", 1000000.0, 131072, false, false, true, false, true},
     };
     static const char *other_blocks[] = {"Qwen3_5ForConditionalGeneration", "Qwen3MoeForCausalLM",
-        "Qwen3_5MoeForConditionalGeneration", "Gemma3ForCausalLM",
-        "OLMo2ForCausalLM", "Olmo2ForCausalLM", "ExaoneForCausalLM", "LuxTTSForTextToSpeech"};
+        "Qwen3_5MoeForConditionalGeneration", "LuxTTSForTextToSpeech"};
+    // cake/mod.rs:99-105: the dense sibling blocks; serde defaults of models/{gemma3,olmo2,exaone4}/config.rs
+    static const Arch siblings[] = {
+        {"Gemma3ForCausalLM", 10000.0, 131072, false, true, true, false, false},
+        {"OLMo2ForCausalLM", 500000.0, 4096, false, true, true, false, false},
+        {"Olmo2ForCausalLM", 500000.0, 4096, false, true, true, false, false},
+        {"ExaoneForCausalLM", 500000.0, 131072, false, true, true, false, false},
+    };
     for (const char *o : other_blocks)
       if (k.arch == o) throw Error("architecture " + k.arch + " is outside the block-forward path built here");
     const Arch *ar = &archs[0];
     for (auto &a : archs)
       if (k.arch == a.name) ar = &a;
+    for (auto &a : siblings)
+      if (k.arch == a.name) {
+        ar = &a;
+        k.block_kind = k.arch == "Gemma3ForCausalLM" ? "gemma3" : k.arch == "ExaoneForCausalLM" ? "exaone4" : "olmo2";
+      }
     auto &c = k.c;
     // the fields every *Config struct of the reference declares without a serde default: absent -> parse error
     auto required = [&](const char *name) -> int {
@@ -203,6 +230,31 @@ struct Config {
     if (ar->window) {
       const int w = (int)j.number("sliding_window", 0);  // null / absent -> 0
       c.sliding_window = (w > 0 && w < c.max_seq) ? w : 0;  // cache.rs:173-205: limit = min(window, max_seq_len)
+    }
+    if (k.block_kind != "llama") {
+      const int n = c.n_layers;
+      if (k.block_kind == "olmo2") {  // olmo2/config.rs:52-90
+        c.pre_reshape_qk_norm = 1;
+      } else {
+        const int w = (int)j.number("sliding_window", k.block_kind == "gemma3" ? 1024 : 4096);
+        k.layer_window = (w > 0 && w < c.max_seq) ? w : 0;
+        k.global_layers.assign(n, false);
+        if (k.block_kind == "exaone4") {  // exaone4/config.rs:62-65: every `global_layer_period`-th layer is global
+          const int period = (int)j.number("global_layer_period", 4);
+          for (int i = 0; i < n; i++) k.global_layers[i] = period > 0 && (i + 1) % period == 0;
+        } else {                          // gemma3/config.rs:76-90: explicit schedule (true = global) or every pattern-th layer
+          const Json *sched = j.get("sliding_window_attention_schedule");
+          const int pattern = (int)j.number("sliding_window_pattern", 6);
+          for (int i = 0; i < n; i++)
+            k.global_layers[i] = (sched && sched->kind == Json::Arr && !sched->arr.empty())
+                                     ? (i < (int)sched->arr.size() && sched->arr[i].kind == Json::Bool && sched->arr[i].b)
+                                     : (pattern > 0 && (i + 1) % pattern == 0);
+          c.tie_embeddings = 1;             // gemma3/config.rs:103
+          k.residual_rms_norm = true;       // :110
+          c.use_gelu_mlp = 1;               // :117
+          c.embed_scale = sqrtf((float)c.hidden);  // :118
+        }
+      }
     }
     c.dtype = dtype;
     c.rope_factor = 1.f; c.rope_low = 1.f; c.rope_high = 4.f;
@@ -355,6 +407,54 @@ class VarBuilder {
 };
 
 // ---------------------------------------------------------------------------------------------- Cache / Context
+// ---------------------------------------------------------------------------------------------- D <-> f32 (load-time only)
+inline float d_to_f32(uint16_t h, int dtype) {
+  uint32_t u;
+  if (dtype == CAKE_B200_BF16) u = (uint32_t)h << 16;
+  else {
+    const uint32_t s = (h >> 15) & 1u, e = (h >> 10) & 31u;
+    uint32_t m = h & 1023u;
+    if (e == 0) {
+      if (!m) u = s << 31;
+      else {  // subnormal: renormalise
+        int ex = 113;
+        while (!(m & 1024u)) { m <<= 1; ex--; }
+        u = (s << 31) | ((uint32_t)ex << 23) | ((m & 1023u) << 13);
+      }
+    } else if (e == 31) u = (s << 31) | 0x7f800000u | (m << 13);
+    else u = (s << 31) | ((e + 112u) << 23) | (m << 13);
+  }
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline uint16_t f32_to_d(float f, int dtype) {  // round to nearest even, as candle's / torch's to_dtype
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if (dtype == CAKE_B200_BF16) {
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);  // NaN
+    return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+  }
+  const uint32_t s = (u >> 16) & 0x8000u;
+  const int32_t e = (int32_t)((u >> 23) & 255u) - 127 + 15;
+  uint32_t m = u & 0x7fffffu;
+  if (((u >> 23) & 255u) == 255u) return (uint16_t)(s | 0x7c00u | (m ? 0x200u : 0u));
+  if (e >= 31) return (uint16_t)(s | 0x7c00u);
+  if (e <= 0) {
+    if (e < -10) return (uint16_t)s;
+    m |= 0x800000u;
+    const int sh = 14 - e;
+    uint32_t r = m >> sh;
+    const uint32_t rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
+    if (rem > half || (rem == half && (r & 1u))) r++;
+    return (uint16_t)(s | r);
+  }
+  uint32_t r = ((uint32_t)e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) r++;  // may carry into the exponent: still the right encoding
+  return (uint16_t)(s | r);
+}
+
 struct Context;
 class Cache {  // cache.rs:9
  public:
@@ -388,6 +488,18 @@ struct Context {  // cake/mod.rs:41-65
     if (h) cake_b200_ctx_destroy(h);
   }
   Context(const Context &) = delete;
+  // config.rs:155-173 load_rms_norm_weight: with residual_rms_norm the checkpoint stores deltas and the forward weight is
+  // (1 + w), added in f32 and cast back to the model dtype at load time.  Returns the tensor itself otherwise.
+  const void *rms_norm_weight(const std::string &name, int64_t n) {
+    const void *p = var_builder->get(name, dtype_name, {n});
+    if (!config.residual_rms_norm) return p;
+    norm_store.emplace_back((size_t)n);
+    const uint16_t *src = (const uint16_t *)p;
+    for (int64_t i = 0; i < n; i++) norm_store.back()[(size_t)i] = f32_to_d(d_to_f32(src[i], config.c.dtype) + 1.0f, config.c.dtype);
+    return norm_store.back().data();
+  }
+ private:
+  std::vector<std::vector<uint16_t>> norm_store;  // the library copies at load; kept until the ctx goes for simplicity
 };
 
 // ---------------------------------------------------------------------------------------------- Forwarder
@@ -433,14 +545,35 @@ class Transformer : public Forwarder {  // transformer.rs:14-150, backed by the 
     } else {
       gate = g("mlp.gate_proj.weight", Sh{I, H}); up = g("mlp.up_proj.weight", Sh{I, H});
     }
+    // norm vectors by ROLE: ln1 = pre-attention, ln2 = pre-MLP, post_attn / post_ffn = the sandwich norms.  Checkpoint names:
+    //   llama / exaone4 (transformer.rs:84-90, exaone4/block.rs:74-77): input_layernorm | post_attention_layernorm (= pre-MLP)
+    //   gemma3 (gemma3/block.rs:84-91): input_layernorm | post_attention_layernorm (POST-attention) | pre_feedforward_layernorm
+    //                                   | post_feedforward_layernorm
+    //   olmo2 (olmo2/block.rs:49-52): post_attention_layernorm, post_feedforward_layernorm only
+    const Config::Variant var = ctx.config.layer_variant(layer);
+    const std::string &kind = ctx.config.block_kind;
+    auto nw = [&](const char *s) { return ctx.rms_norm_weight(name + "." + s, H); };
+    const void *ln1 = nullptr, *ln2 = nullptr, *post_attn = nullptr, *post_ffn = nullptr;
+    if (kind == "olmo2") {
+      post_attn = nw("post_attention_layernorm.weight"); post_ffn = nw("post_feedforward_layernorm.weight");
+    } else if (kind == "gemma3") {
+      ln1 = nw("input_layernorm.weight"); post_attn = nw("post_attention_layernorm.weight");
+      ln2 = nw("pre_feedforward_layernorm.weight"); post_ffn = nw("post_feedforward_layernorm.weight");
+    } else {
+      ln1 = nw("input_layernorm.weight"); ln2 = nw("post_attention_layernorm.weight");
+    }
+    const int64_t qn_dim = c.pre_reshape_qk_norm ? sq : hd, kn_dim = c.pre_reshape_qk_norm ? skv : hd;  // attention.rs:121-122
     check(cake_b200_block_load(ctx.h, layer, q, k, v, g("self_attn.o_proj.weight", Sh{H, sq}),
-                               gate, up, g("mlp.down_proj.weight", Sh{H, I}),
-                               g("input_layernorm.weight", Sh{H}), g("post_attention_layernorm.weight", Sh{H}),
+                               gate, up, g("mlp.down_proj.weight", Sh{H, I}), ln1, ln2,
                                c.qkv_bias ? g("self_attn.q_proj.bias", Sh{sq}) : nullptr, c.qkv_bias ? g("self_attn.k_proj.bias", Sh{skv}) : nullptr,
                                c.qkv_bias ? g("self_attn.v_proj.bias", Sh{skv}) : nullptr,
-                               c.qk_norm ? g("self_attn.q_norm.weight", Sh{hd}) : nullptr,   // attention.rs:120-129: only when use_qk_norm
-                               c.qk_norm ? g("self_attn.k_norm.weight", Sh{hd}) : nullptr, &t->h_),
+                               c.qk_norm ? ctx.rms_norm_weight(name + ".self_attn.q_norm.weight", qn_dim) : nullptr,   // attention.rs:120-129
+                               c.qk_norm ? ctx.rms_norm_weight(name + ".self_attn.k_norm.weight", kn_dim) : nullptr, &t->h_),
           name);
+    if (var.post_norms || var.window >= 0 || var.no_rope) {  // load_custom(vb, cfg, use_qk_norm, sliding_window, use_rope)
+      cake_b200_block_variant bv{var.window, var.no_rope ? 0 : 1, post_attn, post_ffn};
+      check(cake_b200_block_set_variant(t->h_, &bv), name);
+    }
     return t;
   }
   ~Transformer() override { cake_b200_block_free(h_); }
@@ -476,7 +609,7 @@ class TextModelBase {  // text_model.rs:133-530 for token-id prompts
     const VarBuilder &vb = *ctx.var_builder;
     const std::string p = ctx.config.model_prefix, &dt = ctx.dtype_name;
     const int64_t V = ctx.config.c.vocab, H = ctx.config.c.hidden;
-    check(cake_b200_head_load(ctx.h, vb.get(p + ".embed_tokens.weight", dt, {V, H}), vb.get(p + ".norm.weight", dt, {H}),
+    check(cake_b200_head_load(ctx.h, vb.get(p + ".embed_tokens.weight", dt, {V, H}), ctx.rms_norm_weight(p + ".norm.weight", H),
                               ctx.config.c.tie_embeddings ? nullptr : vb.get("lm_head.weight", dt, {V, H})),
           "head_load");
     for (int i = 0; i < ctx.config.c.n_layers; i++) m->blocks.push_back(Transformer::load(ctx.config.layer_name(i), ctx));
@@ -499,7 +632,7 @@ class TextModelBase {  // text_model.rs:133-530 for token-id prompts
   Token next_token(size_t index) {
     const auto &c = ctx.config.c;
     uint32_t next = 0;
-    if (index == 0 || repeat_penalty != 1.0f) {
+    if (index == 0 || repeat_penalty != 1.0f || !ctx.config.standard_blocks()) {  // the decode graph covers the standard block only
       std::vector<uint32_t> in = (index > 0) ? std::vector<uint32_t>{tokens.back()} : tokens;
       const size_t pos = (index > 0) ? index_pos : 0;
       if (in.empty()) throw Error("empty prompt");

@@ -40,10 +40,13 @@ int main(int argc, char **argv) {
       Config k = Config::from_path(dir + "/config.json", dtype, max_seq);
       const auto &c = k.c;
       printf("arch=%s hidden=%d inter=%d heads=%d kv_heads=%d head_dim=%d layers=%d vocab=%d max_seq=%d rms_eps=%g "
-             "rope_theta=%g qkv_bias=%d qk_norm=%d tie=%d rope_llama3=%d n_eos=%zu partial_rotary=%g fused=%d sliding_window=%d\n",
+             "rope_theta=%g qkv_bias=%d qk_norm=%d tie=%d rope_llama3=%d n_eos=%zu partial_rotary=%g fused=%d sliding_window=%d "
+             "block_kind=%s pre_reshape_qk_norm=%d gelu=%d embed_scale=%g residual_rms_norm=%d layer_window=%d globals=%s\n",
              k.arch.c_str(), c.hidden, c.inter, c.n_heads, c.n_kv_heads, c.head_dim, c.n_layers, c.vocab, c.max_seq,
              (double)c.rms_eps, (double)c.rope_theta, c.qkv_bias, c.qk_norm, c.tie_embeddings, c.rope_llama3, k.eos.size(),
-             (double)c.partial_rotary, (int)(k.fused_qkv_proj && k.fused_gate_up_proj), c.sliding_window);
+             (double)c.partial_rotary, (int)(k.fused_qkv_proj && k.fused_gate_up_proj), c.sliding_window,
+             k.block_kind.c_str(), c.pre_reshape_qk_norm, c.use_gelu_mlp, (double)c.embed_scale, (int)k.residual_rms_norm, k.layer_window,
+             [&]() { std::string g; for (bool b : k.global_layers) g += b ? '1' : '0'; return g.empty() ? std::string("-") : g; }().c_str());
       return 0;
     }
     Context ctx(dir, 0, dtype, max_seq);

@@ -49,14 +49,19 @@ def _python_view(d: dict) -> dict:
                 partial_rotary=float(cc.partial_rotary), fused=int(c.fused_qkv_proj and c.fused_gate_up_proj))
 
 
-def _cpp_view(tmp_path, d: dict) -> dict:
+def _cpp_kv(tmp_path, d: dict) -> dict:
     build_host()
     with open(tmp_path / "config.json", "w") as f:
         json.dump(d, f)
     r = subprocess.run([RUN, str(tmp_path), "--show-config"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    kv = dict(p.split("=", 1) for p in r.stdout.split())
-    return {k: (float(v) if k in ("rope_theta", "rms_eps", "partial_rotary") else v if k == "arch" else int(v)) for k, v in kv.items()}
+    return dict(p.split("=", 1) for p in r.stdout.split())
+
+
+def _cpp_view(tmp_path, d: dict) -> dict:
+    kv = _cpp_kv(tmp_path, d)
+    return {k: (float(v) if k in ("rope_theta", "rms_eps", "partial_rotary", "embed_scale") else v if k in ("arch", "block_kind", "globals") else int(v))
+            for k, v in kv.items()}
 
 
 @pytest.mark.parametrize("name", list(CASES))
@@ -71,19 +76,48 @@ def test_python_and_cpp_resolve_the_same_block_config(tmp_path, name):
         assert py[k] == cpp[k], (name, k, py[k], cpp[k])
 
 
-@pytest.mark.parametrize("arch", ["Gemma3ForCausalLM", "Qwen3MoeForCausalLM", "OLMo2ForCausalLM", "ExaoneForCausalLM"])
+@pytest.mark.parametrize("arch", ["Qwen3MoeForCausalLM", "Qwen3_5ForConditionalGeneration", "LuxTTSForTextToSpeech"])
 def test_other_block_types_are_refused_by_name(tmp_path, arch):
-    """MoE / linear-attention blocks are outside the path everywhere; the three dense sibling blocks are served by the
-    library and the Python host (next test) while the compiled C++ host still steps the standard block only."""
+    """MoE / linear-attention / TTS blocks are outside the path in both hosts."""
     d = {**BASE, "architectures": [arch]}
-    if arch == "Qwen3MoeForCausalLM":
-        with pytest.raises(ValueError, match="outside the block-forward path"):
-            Config.from_hf(d)
+    with pytest.raises(ValueError, match="outside the block-forward path"):
+        Config.from_hf(d)
     build_host()
     with open(tmp_path / "config.json", "w") as f:
         json.dump(d, f)
     r = subprocess.run([RUN, str(tmp_path), "--show-config"], capture_output=True, text=True)
     assert r.returncode == 1 and "outside the block-forward path" in r.stderr
+
+
+SIBLING_JSON = {
+    "olmo2": {"architectures": ["Olmo2ForCausalLM"]},
+    "olmo2_caps": {"architectures": ["OLMo2ForCausalLM"], "head_dim": 32, "tie_word_embeddings": True},
+    "exaone4": {"architectures": ["ExaoneForCausalLM"], "num_hidden_layers": 8, "sliding_window": 16, "max_position_embeddings": 64},
+    "exaone4_defaults": {"architectures": ["ExaoneForCausalLM"], "num_hidden_layers": 5, "global_layer_period": 2},
+    "gemma3_pattern": {"architectures": ["Gemma3ForCausalLM"], "num_hidden_layers": 12, "sliding_window": 16, "max_position_embeddings": 64,
+                       "hidden_size": 1152, "num_attention_heads": 4, "head_dim": 256},
+    "gemma3_schedule": {"architectures": ["Gemma3ForCausalLM"], "num_hidden_layers": 3, "sliding_window_attention_schedule": [True, False, True]},
+}
+
+
+@pytest.mark.parametrize("name", list(SIBLING_JSON))
+def test_python_and_cpp_resolve_the_same_sibling_block_config(tmp_path, name):
+    """models/{olmo2,gemma3,exaone4}/config.rs into_config in both hosts: serde defaults, hard-wired flags, per-layer schedule."""
+    d = {**BASE, **SIBLING_JSON[name]}
+    c = Config.from_hf(d)
+    cc = CConfig.from_config(c, "bf16")
+    kv = _cpp_kv(tmp_path, d)
+    var = [c.layer_variant(i) for i in range(c.num_hidden_layers)]
+    local = [v["window"] for v in var if v["window"] > 0]
+    want = dict(block_kind=c.block_kind, rope_theta=float(cc.rope_theta), max_seq=cc.max_seq, qk_norm=cc.qk_norm, tie=cc.tie_embeddings,
+                head_dim=cc.head_dim, kv_heads=cc.n_kv_heads, pre_reshape_qk_norm=cc.pre_reshape_qk_norm, gelu=cc.use_gelu_mlp,
+                residual_rms_norm=int(c.residual_rms_norm), sliding_window=cc.sliding_window if c.block_kind == "olmo2" else 0,
+                layer_window=local[0] if local else 0,
+                globals="".join("1" if g else "0" for g in c.global_layers) or "-")
+    for k, v in want.items():
+        got = kv[k]
+        assert (float(got) == float(v)) if isinstance(v, float) else (str(got) == str(v)), (name, k, got, v)
+    assert abs(float(kv["embed_scale"]) - float(cc.embed_scale)) < 1e-4
 
 
 def test_sibling_block_structures_resolve_like_the_reference():

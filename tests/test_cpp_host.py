@@ -210,6 +210,42 @@ def test_cake_run_host_loop_reproduces_the_oracle_on_the_cpu(tmp_path, flavour, 
     assert "tok/s:" in r.stdout
 
 
+SIBLING_CKPT = {
+    "olmo2": ("Olmo2ForCausalLM", dict(block_kind="olmo2", use_qk_norm=True, pre_reshape_qk_norm=True)),
+    "gemma3": ("Gemma3ForCausalLM", dict(block_kind="gemma3", use_qk_norm=True, residual_rms_norm=True, use_gelu_mlp=True,
+                                         tie_word_embeddings=True, embed_scale=float(np.sqrt(np.float32(128))), sliding_window=5,
+                                         global_layers=[False, True, False, True], rope_theta=10000.0)),
+    "exaone4": ("ExaoneForCausalLM", dict(block_kind="exaone4", use_qk_norm=True, sliding_window=5, global_layers=[False, True, False, True])),
+}
+
+
+@pytest.mark.parametrize("kind,dtype", [("olmo2", "bf16"), ("gemma3", "bf16"), ("gemma3", "f16"), ("exaone4", "bf16")])
+def test_cake_run_steps_the_sibling_block_structures_on_the_cpu(tmp_path, kind, dtype):
+    """models/{olmo2,gemma3,exaone4}: config.json -> per-layer variants, the architectures' own tensor names, (1 + w) norm
+    weights computed at load in the model dtype (config.rs:155-173), embed_scale, and host-stepped decode (no decode graph
+    for these blocks) — the compiled host over the oracle-backed emulation must emit the oracle's tokens."""
+    from cake_b200.loader import save_checkpoint
+    from cake_b200.synth import residual_deltas
+    from oracle import oracle as O
+    env = _emulation(tmp_path)
+    arch, extra = SIBLING_CKPT[kind]
+    cfg = medium_config(num_hidden_layers=4, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+                        num_key_value_heads=2, head_dim=32, **extra)
+    sd = checkpoint(cfg, dtype, seed=17, peaked=not cfg.tie_word_embeddings)
+    if cfg.residual_rms_norm:
+        sd = residual_deltas(sd)
+    model = tmp_path / "model"
+    save_checkpoint(str(model), cfg, sd, arch=arch, shard_bytes=300_000)
+    prompt = np.random.default_rng(5).integers(0, cfg.vocab_size - 1, 4).tolist()   # fits the local window of 5
+    n = 12
+    r = subprocess.run([RUN, str(model), "--prompt-ids", ",".join(map(str, prompt)), "-n", str(n), "--max-seq", "64", "--dtype", dtype],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = [int(t) for t in r.stdout.splitlines()[0].split(":")[1].split()]
+    om = O.OracleModel(cfg, sd, dtype, max_seq=64)
+    assert got == list(om.generate(prompt, n)[0])
+
+
 def test_cake_worker_sessions_and_errors_on_the_cpu(tmp_path):
     """cake_worker's B200Backend (one KV cache per connection, forwards under a lock, errors reported per request) over
     the oracle-backed emulation: activations must equal the oracle's block outputs bit for bit, a second connection
