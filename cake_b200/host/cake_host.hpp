@@ -285,6 +285,54 @@ struct Config {
   std::string layer_name(int i) const { return model_prefix + ".layers." + std::to_string(i); }  // text_model.rs:205
 };
 
+// ---------------------------------------------------------------------------------------------- D <-> f32 (load-time only)
+inline float d_to_f32(uint16_t h, int dtype) {
+  uint32_t u;
+  if (dtype == CAKE_B200_BF16) u = (uint32_t)h << 16;
+  else {
+    const uint32_t s = (h >> 15) & 1u, e = (h >> 10) & 31u;
+    uint32_t m = h & 1023u;
+    if (e == 0) {
+      if (!m) u = s << 31;
+      else {  // subnormal: renormalise
+        int ex = 113;
+        while (!(m & 1024u)) { m <<= 1; ex--; }
+        u = (s << 31) | ((uint32_t)ex << 23) | ((m & 1023u) << 13);
+      }
+    } else if (e == 31) u = (s << 31) | 0x7f800000u | (m << 13);
+    else u = (s << 31) | ((e + 112u) << 23) | (m << 13);
+  }
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+inline uint16_t f32_to_d(float f, int dtype) {  // round to nearest even, as candle's / torch's to_dtype
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if (dtype == CAKE_B200_BF16) {
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);  // NaN
+    return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
+  }
+  const uint32_t s = (u >> 16) & 0x8000u;
+  const int32_t e = (int32_t)((u >> 23) & 255u) - 127 + 15;
+  uint32_t m = u & 0x7fffffu;
+  if (((u >> 23) & 255u) == 255u) return (uint16_t)(s | 0x7c00u | (m ? 0x200u : 0u));
+  if (e >= 31) return (uint16_t)(s | 0x7c00u);
+  if (e <= 0) {
+    if (e < -10) return (uint16_t)s;
+    m |= 0x800000u;
+    const int sh = 14 - e;
+    uint32_t r = m >> sh;
+    const uint32_t rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
+    if (rem > half || (rem == half && (r & 1u))) r++;
+    return (uint16_t)(s | r);
+  }
+  uint32_t r = ((uint32_t)e << 10) | (m >> 13);
+  const uint32_t rem = m & 0x1fffu;
+  if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) r++;  // may carry into the exponent: still the right encoding
+  return (uint16_t)(s | r);
+}
+
 // ---------------------------------------------------------------------------------------------- VarBuilder
 // mmapped safetensors: 8-byte little-endian header length, JSON {name: {dtype, shape, data_offsets}}, raw data
 // (utils/mod.rs:255-272 single file; :333-384 model.safetensors.index.json -> the shards that hold the names).
@@ -298,6 +346,7 @@ class VarBuilder {
   struct Map { void *p; size_t n; };
   std::vector<Map> maps_;
   std::map<std::string, TensorView> t_;
+  mutable std::map<std::string, std::vector<uint16_t>> converted_;  // tensors whose checkpoint dtype differs from the model dtype
   void add_file(const std::string &path) {
     int fd = open(path.c_str(), O_RDONLY);
     if (fd < 0) throw Error("can't open " + path);
@@ -394,12 +443,33 @@ class VarBuilder {
   const void *get(const std::string &name, const std::string &want_dtype, const std::vector<int64_t> &shape) const {
     const TensorView *v = find(name);
     if (!v) throw Error("cannot find tensor " + name);  // candle VarBuilder error text
-    if (v->dtype != want_dtype) throw Error("tensor " + name + " is " + v->dtype + ", expected " + want_dtype);
     if (v->shape != shape) {
       auto str = [](const std::vector<int64_t> &s) { std::string o = "["; for (size_t i = 0; i < s.size(); i++) o += (i ? ", " : "") + std::to_string(s[i]); return o + "]"; };
       throw Error("shape mismatch for " + name + ", expected: " + str(shape) + ", got: " + str(v->shape));
     }
-    return v->data;
+    if (v->dtype == want_dtype) return v->data;
+    // The reference converts on load (candle VarBuilder::get casts to the builder's dtype; utils/mod.rs:250-267 builds it
+    // with the --dtype of the run): F32 / F16 / BF16 checkpoints are accepted for either model dtype, rounded to nearest even.
+    auto known = [](const std::string &d) { return d == "BF16" || d == "F16" || d == "F32"; };
+    if (!known(v->dtype) || !known(want_dtype) || want_dtype == "F32")
+      throw Error("tensor " + name + " is " + v->dtype + ", expected " + want_dtype);
+    auto it = converted_.find(name);
+    if (it == converted_.end()) {
+      size_t n = 1;
+      for (auto d : v->shape) n *= (size_t)d;
+      std::vector<uint16_t> out(n);
+      const int to = want_dtype == "BF16" ? CAKE_B200_BF16 : CAKE_B200_F16;
+      if (v->dtype == "F32") {
+        const float *src = (const float *)v->data;
+        for (size_t i = 0; i < n; i++) out[i] = f32_to_d(src[i], to);
+      } else {
+        const uint16_t *src = (const uint16_t *)v->data;
+        const int from = v->dtype == "BF16" ? CAKE_B200_BF16 : CAKE_B200_F16;
+        for (size_t i = 0; i < n; i++) out[i] = f32_to_d(d_to_f32(src[i], from), to);
+      }
+      it = converted_.emplace(name, std::move(out)).first;
+    }
+    return it->second.data();
   }
   const void *get_opt(const std::string &name, const std::string &want_dtype, const std::vector<int64_t> &shape) const {
     return find(name) ? get(name, want_dtype, shape) : nullptr;
@@ -407,54 +477,6 @@ class VarBuilder {
 };
 
 // ---------------------------------------------------------------------------------------------- Cache / Context
-// ---------------------------------------------------------------------------------------------- D <-> f32 (load-time only)
-inline float d_to_f32(uint16_t h, int dtype) {
-  uint32_t u;
-  if (dtype == CAKE_B200_BF16) u = (uint32_t)h << 16;
-  else {
-    const uint32_t s = (h >> 15) & 1u, e = (h >> 10) & 31u;
-    uint32_t m = h & 1023u;
-    if (e == 0) {
-      if (!m) u = s << 31;
-      else {  // subnormal: renormalise
-        int ex = 113;
-        while (!(m & 1024u)) { m <<= 1; ex--; }
-        u = (s << 31) | ((uint32_t)ex << 23) | ((m & 1023u) << 13);
-      }
-    } else if (e == 31) u = (s << 31) | 0x7f800000u | (m << 13);
-    else u = (s << 31) | ((e + 112u) << 23) | (m << 13);
-  }
-  float f;
-  memcpy(&f, &u, 4);
-  return f;
-}
-inline uint16_t f32_to_d(float f, int dtype) {  // round to nearest even, as candle's / torch's to_dtype
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if (dtype == CAKE_B200_BF16) {
-    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40u);  // NaN
-    return (uint16_t)((u + 0x7fffu + ((u >> 16) & 1u)) >> 16);
-  }
-  const uint32_t s = (u >> 16) & 0x8000u;
-  const int32_t e = (int32_t)((u >> 23) & 255u) - 127 + 15;
-  uint32_t m = u & 0x7fffffu;
-  if (((u >> 23) & 255u) == 255u) return (uint16_t)(s | 0x7c00u | (m ? 0x200u : 0u));
-  if (e >= 31) return (uint16_t)(s | 0x7c00u);
-  if (e <= 0) {
-    if (e < -10) return (uint16_t)s;
-    m |= 0x800000u;
-    const int sh = 14 - e;
-    uint32_t r = m >> sh;
-    const uint32_t rem = m & ((1u << sh) - 1u), half = 1u << (sh - 1);
-    if (rem > half || (rem == half && (r & 1u))) r++;
-    return (uint16_t)(s | r);
-  }
-  uint32_t r = ((uint32_t)e << 10) | (m >> 13);
-  const uint32_t rem = m & 0x1fffu;
-  if (rem > 0x1000u || (rem == 0x1000u && (r & 1u))) r++;  // may carry into the exponent: still the right encoding
-  return (uint16_t)(s | r);
-}
-
 struct Context;
 class Cache {  // cache.rs:9
  public:

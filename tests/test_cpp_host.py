@@ -210,6 +210,31 @@ def test_cake_run_host_loop_reproduces_the_oracle_on_the_cpu(tmp_path, flavour, 
     assert "tok/s:" in r.stdout
 
 
+@pytest.mark.parametrize("ckpt_dtype,model_dtype", [("f32", "bf16"), ("f16", "bf16"), ("bf16", "f16")])
+def test_cake_run_converts_checkpoints_of_another_dtype_on_load(tmp_path, ckpt_dtype, model_dtype):
+    """The reference's VarBuilder casts every tensor to the run's --dtype on load (utils/mod.rs:250-267 + candle's
+    VarBuilder::get): an F32 / F16 checkpoint under --dtype bf16 (and BF16 under f16) must behave like the checkpoint
+    rounded to the model dtype, as the Python host's `.to(dtype)` does."""
+    import torch
+    from cake_b200.loader import save_checkpoint
+    from cake_b200.synth import TORCH_DTYPES
+    from oracle import oracle as O
+    env = _emulation(tmp_path)
+    cfg = medium_config(num_hidden_layers=3, hidden_size=128, intermediate_size=256, vocab_size=256, num_attention_heads=4,
+                        num_key_value_heads=2, head_dim=32, use_qk_norm=True)
+    sd = checkpoint(cfg, ckpt_dtype, seed=29, peaked=True)
+    model = tmp_path / "model"
+    save_checkpoint(str(model), cfg, sd, arch="Qwen3ForCausalLM", shard_bytes=400_000)
+    prompt = [5, 17, 200, 3, 77]
+    r = subprocess.run([RUN, str(model), "--prompt-ids", ",".join(map(str, prompt)), "-n", "10", "--max-seq", "64", "--dtype", model_dtype],
+                       capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0, r.stderr
+    got = [int(t) for t in r.stdout.splitlines()[0].split(":")[1].split()]
+    sd_d = {k: v.to(TORCH_DTYPES[model_dtype]) for k, v in sd.items()}
+    om = O.OracleModel(cfg, sd_d, model_dtype, max_seq=64)
+    assert got == list(om.generate(prompt, 10)[0])
+
+
 SIBLING_CKPT = {
     "olmo2": ("Olmo2ForCausalLM", dict(block_kind="olmo2", use_qk_norm=True, pre_reshape_qk_norm=True)),
     "gemma3": ("Gemma3ForCausalLM", dict(block_kind="gemma3", use_qk_norm=True, residual_rms_norm=True, use_gelu_mlp=True,
