@@ -395,6 +395,8 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
   CU(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10) return fail(CAKE_B200_ECUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
   auto *c = new cake_b200_ctx();
+  // any failure below returns through CU / RC: release what was set up so far (ctx_destroy tolerates a half-built ctx)
+  struct Guard { cake_b200_ctx *c; ~Guard() { if (c) { cake_b200_ctx_destroy(c); (void)cudaGetLastError(); } } } guard{c};
   c->device = device;
   c->cfg = *cfg;
   c->es = 2;
@@ -463,6 +465,7 @@ extern "C" int cake_b200_ctx_create(int device, const cake_b200_config *cfg, cak
     std::lock_guard<std::mutex> lk(g_live_mu);
     g_live_ctx.insert(c);
   }
+  guard.c = nullptr;
   *out = c;
   return CAKE_B200_OK;
 }
